@@ -1,0 +1,266 @@
+/*
+ * mbt_b200.h -- C ABI of libmbt_b200.so: the B200 (sm_100a) implementation of the ONE hot
+ * path of JJJerome/mbt_gym, `TradingEnvironment.step()` / `reset()` and the rollout loop
+ * around them.  Plain C, no torch / C++ types: pointers, sizes, PODs.
+ *
+ * The reference has no FFI; its "plugin API" for this path is the gym.Env surface of
+ * mbt_gym/gym/TradingEnvironment.py.  Each entry point below names the reference code it
+ * replaces; INTEGRATION.md shows the ctypes stub a maintainer would add to the reference.
+ *
+ *   mbt_create      <- TradingEnvironment.__init__            TradingEnvironment.py:27-94
+ *   mbt_seed        <- TradingEnvironment.seed                TradingEnvironment.py:345-348
+ *   mbt_reset       <- TradingEnvironment.reset/initial_state TradingEnvironment.py:96-101,131-140
+ *   mbt_step        <- TradingEnvironment.step                TradingEnvironment.py:103-110
+ *                      (+ everything it calls: ModelDynamics.py:108-131,262-267;
+ *                       arrival_models.py:54-56,110-123; fill_probability_models.py:28-34,57-58;
+ *                       midprice_models.py:60-65,97-105,140-143; price_impact_models.py:88-92;
+ *                       RewardFunctions.py:23-33,55-70,96-109,128-138)
+ *   mbt_get_state   <- TradingEnvironment.state (property)    TradingEnvironment.py:142-144
+ *   mbt_set_state   <- `env.model_dynamics.state = ...`        ModelDynamics.py:39 (test injection / resume)
+ *   mbt_reward_eval <- RewardFunction.calculate               RewardFunctions.py:8-13
+ *   mbt_rollout     <- generate_trajectory + summary table    gym/helpers/generate_trajectory.py:8-38,
+ *                                                             gym/helpers/plotting.py:94-108
+ *
+ * Conventions
+ *   - every function returns 0 (MBT_OK) or a negative MBT_E_* code and never throws;
+ *     mbt_last_error() returns a thread-local message for the last failure.
+ *   - one handle = one CUDA device = one stream.  A handle is NOT thread-safe (the reference
+ *     is single-threaded per env); different handles may be driven from different threads.
+ *   - the handle owns its device state (structure-of-arrays) and pinned staging;
+ *     the caller owns every buffer it passes in.  `mem` says where a caller buffer lives.
+ *   - layouts of caller buffers are the reference's: actions (N, A) row-major, observations
+ *     (N, D) row-major, rewards (N,), in the handle's precision (float64 or float32).
+ *   - there is NO CPU implementation behind this ABI.  If no CUDA device is usable, mbt_create
+ *     fails with MBT_E_CUDA.
+ */
+#ifndef MBT_B200_H
+#define MBT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBT_ABI_VERSION 1
+
+/* error codes */
+#define MBT_OK 0
+#define MBT_E_INVALID_ARG (-1)
+#define MBT_E_CUDA (-2)
+#define MBT_E_STATE (-3)
+#define MBT_E_UNSUPPORTED (-4)
+#define MBT_E_NOMEM (-5)
+
+/* where a caller buffer lives */
+#define MBT_MEM_HOST 0   /* pageable or pinned host memory; copies are inside the call      */
+#define MBT_MEM_DEVICE 1 /* device memory on the handle's device; call is enqueue-only      */
+
+/* arithmetic type of the whole path */
+#define MBT_F64 0 /* the reference's type (every reference array is float64)               */
+#define MBT_F32 1 /* opt-in fast mode, same formulas evaluated in float                     */
+
+/* ModelDynamics.py */
+#define MBT_DYN_LIMIT 0            /* LimitOrderModelDynamics              :87-131  A=2 */
+#define MBT_DYN_SPEED 1            /* TradinghWithSpeedModelDynamics       :243-275 A=1 */
+#define MBT_DYN_AT_TOUCH 2         /* AtTheTouchModelDynamics              :134-176 A=2 */
+#define MBT_DYN_LIMIT_AND_MARKET 3 /* LimitAndMarketOrderModelDynamics     :179-240 A=4 */
+
+/* midprice_models.py */
+#define MBT_MID_CONSTANT 0 /* ConstantMidpriceModel                :12-33   */
+#define MBT_MID_BM 1       /* BrownianMotionMidpriceModel          :36-68   */
+#define MBT_MID_GBM 2      /* GeometricBrownianMotionMidpriceModel :71-111  */
+#define MBT_MID_OU 3       /* OuMidpriceModel                      :114-146 */
+
+/* arrival_models.py */
+#define MBT_ARR_NONE 0
+#define MBT_ARR_POISSON 1           /* PoissonArrivalModel          :33-56  p = lambda*dt         */
+#define MBT_ARR_POISSON_NONLINEAR 2 /* PoissonArrivalNonLinearModel :59-83  p = 1-exp(-lambda*dt) */
+#define MBT_ARR_HAWKES 3            /* HawkesArrivalModel           :86-126 state = (lam_b, lam_a) */
+
+/* fill_probability_models.py */
+#define MBT_FILL_NONE 0
+#define MBT_FILL_EXPONENTIAL 1 /* ExponentialFillFunction :42-65 */
+
+/* price_impact_models.py */
+#define MBT_IMP_NONE 0
+#define MBT_IMP_TEMP_PERM 1  /* TemporaryAndPermanentPriceImpact :64-96 state = (I)        */
+#define MBT_IMP_TEMP_POWER 2 /* TemporaryPowerPriceImpact        :34-61 stateless          */
+
+/* RewardFunctions.py */
+#define MBT_REW_PNL 0                       /* PnL                     :20-36   */
+#define MBT_REW_RUNNING_INVENTORY_PENALTY 1 /* = CjCriterion           :116-146 */
+#define MBT_REW_CJ_MM 2                     /* CjMmCriterion           :77-113  */
+#define MBT_REW_CJ_OE 3                     /* CjOeCriterion           :39-74   */
+#define MBT_REW_EXP_UTILITY 4               /* ExponentialUtility      :149-166 */
+
+/* initial inventory (TradingEnvironment.py:270-281) */
+#define MBT_Q0_CONST 0       /* int, or the value a callable returned on the host            */
+#define MBT_Q0_UNIFORM_INT 1 /* tuple (lo, hi): rng.integers(lo, hi) per trajectory          */
+
+#define MBT_MAX_ACTION_DIM 4
+#define MBT_MAX_OBS_DIM 8
+
+/*
+ * Everything the constructors of the reference's model-builder classes hold, flattened.
+ * Field comments give the reference attribute.  All reals are float64 on the ABI regardless
+ * of `precision`; the handle converts once.
+ */
+typedef struct mbt_config {
+    int32_t struct_size; /* = sizeof(mbt_config), checked */
+    int32_t precision;   /* MBT_F64 | MBT_F32 */
+    int64_t num_trajectories; /* trajectories held by THIS handle (env.num_trajectories / n_gpus) */
+    int64_t traj_offset;      /* global id of local trajectory 0: RNG counters use offset+i      */
+    int32_t n_steps;          /* env.n_steps */
+    int32_t dynamics, midprice, arrival, fill, impact, reward; /* MBT_DYN_* ... MBT_REW_* */
+
+    double terminal_time; /* env.terminal_time */
+    double step_size;     /* env.step_size = terminal_time / n_steps */
+    double start_time;    /* default t0 (already quantised, TradingEnvironment.py:266-268) */
+    double initial_cash;  /* env.initial_cash */
+    int32_t q0_mode;      /* MBT_Q0_* */
+    int32_t _pad0;
+    double q0_const;
+    int64_t q0_lo, q0_hi; /* MBT_Q0_UNIFORM_INT: integers in [lo, hi) */
+    double max_inventory; /* env.max_inventory */
+    double max_cash;      /* env.max_cash */
+
+    /* midprice model */
+    double mid_initial; /* initial_price */
+    double mid_drift;   /* drift */
+    double mid_vol;     /* volatility */
+    double mid_step;    /* midprice_model.step_size */
+    double ou_level;    /* mean_reversion_level */
+    double ou_speed;    /* mean_reversion_speed */
+
+    /* arrival model */
+    double arr_rate[2];  /* Poisson intensity, or Hawkes baseline_arrival_rate (bid, ask) */
+    double arr_step;     /* arrival_model.step_size */
+    double hawkes_jump;  /* jump_size */
+    double hawkes_speed; /* mean_reversion_speed */
+
+    /* fill model */
+    double fill_exponent; /* ExponentialFillFunction.fill_exponent */
+
+    /* price impact model */
+    double imp_temp;     /* temporary_impact_coefficient */
+    double imp_perm;     /* permanent_impact_coefficient */
+    double imp_exponent; /* temporary_impact_exponent (TemporaryPowerPriceImpact) */
+    double imp_step;     /* price_impact_model.step_size */
+
+    /* AtTheTouch / LimitAndMarket */
+    double half_spread; /* fixed_market_half_spread */
+
+    /* reward function */
+    double rew_phi;           /* per_step_inventory_aversion */
+    double rew_alpha;         /* terminal_inventory_aversion */
+    double rew_exponent;      /* inventory_exponent */
+    double rew_terminal_time; /* reward_function.terminal_time */
+    double rew_risk_aversion; /* ExponentialUtility.risk_aversion */
+
+    /* normalisation (TradingEnvironment.py:112-129,180-194) */
+    int32_t normalise_action, normalise_obs, normalise_rewards, _pad1;
+    double act_low[MBT_MAX_ACTION_DIM];  /* original_action_space.low                    */
+    double act_grad[MBT_MAX_ACTION_DIM]; /* (high - low) / 2                            */
+    double obs_low[MBT_MAX_OBS_DIM];     /* original_observation_space.low              */
+    double obs_grad[MBT_MAX_OBS_DIM];    /* (high - low) / 2                            */
+    double reward_scaling;               /* env.reward_scaling                          */
+} mbt_config;
+
+/* Per-reset overrides (start_time / initial_inventory may be callables on the host). */
+typedef struct mbt_reset_args {
+    double start_time; /* already quantised */
+    int32_t q0_mode;
+    int32_t _pad;
+    double q0_const;
+    int64_t q0_lo, q0_hi;
+} mbt_reset_args;
+
+/* On-device policies for the fused rollout (mbt_gym/agents/BaselineAgents.py). */
+#define MBT_POL_FIXED 0              /* FixedActionAgent / FixedSpreadAgent  :25-42   */
+#define MBT_POL_AVELLANEDA_STOIKOV 1 /* AvellanedaStoikovAgent               :52-83   */
+#define MBT_POL_CJ_MM_TABLE 2        /* CarteaJaimungalMmAgent               :86-137 (h[t][q] table from the host) */
+#define MBT_POL_CJ_OE 3              /* CarteaJaimungalOeAgent               :173-210 */
+
+typedef struct mbt_policy {
+    int32_t kind;
+    int32_t table_rows;  /* CJ_MM_TABLE: n_steps (one row per decision time)            */
+    int32_t table_cols;  /* CJ_MM_TABLE: 2*Q+1                                          */
+    int32_t _pad;
+    double fixed[MBT_MAX_ACTION_DIM]; /* FIXED: the raw (de-normalised) action           */
+    double risk_aversion;             /* AVELLANEDA_STOIKOV: gamma                       */
+    double oe_phi, oe_alpha;          /* CJ_OE                                          */
+    double large_depth;               /* CJ_MM_TABLE: 10_000 (BaselineAgents.py:108)     */
+    const double *table;              /* CJ_MM_TABLE: HOST pointer, rows*cols float64    */
+} mbt_policy;
+
+/* Episode summary = the reference's results table (plotting.py:96-108) as raw moments. */
+typedef struct mbt_summary {
+    int64_t count;        /* trajectories summed                       */
+    int64_t steps;        /* env-steps per trajectory in this rollout  */
+    double sum_return;    /* sum_i R_i,  R_i = sum_t reward_{i,t}      */
+    double sum_return_sq; /* sum_i R_i^2                               */
+    double sum_q;         /* sum_i q_T                                 */
+    double sum_q_sq;      /* sum_i q_T^2                               */
+    double sum_action;    /* sum_{i,t,a} action  (mean spread = 2*mean)*/
+    double sum_reward_sq; /* sum_{i,t} reward^2 (per-step dispersion)  */
+    int64_t clipped;      /* inventory/cash clip events (TradingEnvironment.py:283-297 prints instead) */
+} mbt_summary;
+
+typedef struct mbt_env mbt_env;
+
+int mbt_abi_version(void);
+const char *mbt_last_error(void);
+
+/* dims implied by a config (no device needed): action dim A, observation dim D, state columns S */
+int mbt_config_dims(const mbt_config *cfg, int32_t *action_dim, int32_t *obs_dim, int32_t *state_cols);
+
+int mbt_create(const mbt_config *cfg, int device, mbt_env **out);
+int mbt_destroy(mbt_env *env);
+
+/* Use an external stream (e.g. torch's current stream) for all subsequent work; NULL = own stream. */
+int mbt_set_stream(mbt_env *env, void *cuda_stream);
+int mbt_sync(mbt_env *env);
+
+/* Re-key the RNG and zero the step / episode counters.  (Reference: seed=0 means "unseeded";
+ * that policy lives in the Python facade, here 0 is just a key.) */
+int mbt_seed(mbt_env *env, uint64_t seed);
+
+/* Start an episode.  args may be NULL (config defaults).  obs_out may be NULL. */
+int mbt_reset(mbt_env *env, const mbt_reset_args *args, void *obs_out, int mem);
+
+/* One env-step for all trajectories.  actions (N,A); obs_out (N,D); rew_out (N,);
+ * done_out: ONE byte, the uniform `dones[0]` (TradingEnvironment.py:218-220).  obs_out / rew_out /
+ * done_out may be NULL.  MBT_E_STATE if called before mbt_reset. */
+int mbt_step(mbt_env *env, const void *actions, void *obs_out, void *rew_out, uint8_t *done_out, int mem);
+
+/* Raw (un-normalised) state, reference layout (N, D) row-major in the handle's precision. */
+int mbt_get_state(mbt_env *env, void *state_out, int mem);
+int mbt_set_state(mbt_env *env, const void *state_in, int mem);
+
+/* Clock / counters of the handle (uniform over trajectories, TradingEnvironment.py:216-220). */
+int mbt_get_clock(mbt_env *env, double *time, int64_t *steps_this_episode, int64_t *steps_since_seed,
+                  int64_t *episodes_since_seed);
+
+/* reward_function.calculate(current_state, action, next_state, is_terminal) on (n, D)/(n, A) buffers,
+ * using the handle's reward parameters and the q0 / episode length captured at the last reset. */
+int mbt_reward_eval(mbt_env *env, int64_t n, const void *current_state, const void *action,
+                    const void *next_state, int is_terminal, void *rew_out, int mem);
+
+/* Fused rollout: from the CURRENT state run until the episode ends with an on-device policy, state
+ * in registers, no per-step HBM traffic; writes the summary (host pointer) and, if non-NULL,
+ * per-trajectory returns (N,) and terminal inventories (N,) to `mem` buffers. */
+int mbt_rollout(mbt_env *env, const mbt_policy *policy, mbt_summary *summary_out, void *returns_out,
+                void *terminal_q_out, int mem);
+
+/* Per-call statistics for bench.py: number of kernel launches issued by this handle so far, and the
+ * device time (ms, CUDA events on the handle's stream) of the most recent step kernel when enabled. */
+int mbt_get_launch_count(mbt_env *env, int64_t *launches);
+int mbt_enable_timing(mbt_env *env, int enable);
+int mbt_last_kernel_ms(mbt_env *env, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBT_B200_H */

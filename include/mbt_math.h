@@ -1,0 +1,362 @@
+/*
+ * mbt_math.h -- bit-reproducible exp / log / normal-quantile for float and double,
+ * shared by the sm_100a kernels and the CPU oracle.  Plain C99 / CUDA C++.
+ *
+ * Why it exists: one env-step takes DISCRETE decisions from transcendental values --
+ * a fill happens iff  u < exp(-kappa * depth)  (reference:
+ * mbt_gym/stochastic_processes/fill_probability_models.py:33,58) -- so a 1-ulp
+ * difference between glibc's and CUDA's `exp` can flip a fill and move a trajectory's
+ * inventory by one unit.  To make "GPU == oracle" a BIT-EXACT statement rather than a
+ * statistical one, both sides evaluate the functions below: only IEEE-754 correctly
+ * rounded primitives (+, -, *, /, sqrt, fma, int<->float conversion) in a fixed order.
+ * Build rules that keep that true: nvcc `-fmad=false` (no implicit contraction; every
+ * fused multiply-add here is an explicit fma), no --use_fast_math (IEEE div/sqrt, no
+ * FTZ); gcc `-ffp-contract=off`.
+ *
+ * Accuracy (measured in tests/test_primitives.py against libm / scipy):
+ *   mbt_exp_f32, mbt_log_f32   <= 2 ulp ;  mbt_exp_f64, mbt_log_f64  <= 4 ulp
+ *   mbt_normal_from_bits_f32   rel err <= 1e-6 ; _f64  rel err <= 1e-13
+ */
+#ifndef MBT_MATH_H
+#define MBT_MATH_H
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "mbt_philox.h" /* MBT_HD */
+
+/* ------------------------------------------------------------------ bit casts */
+MBT_HD uint32_t mbt_f32_bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, sizeof u);
+    return u;
+#endif
+}
+MBT_HD float mbt_bits_f32(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, sizeof f);
+    return f;
+#endif
+}
+MBT_HD uint64_t mbt_f64_bits(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t u;
+    memcpy(&u, &d, sizeof u);
+    return u;
+#endif
+}
+MBT_HD double mbt_bits_f64(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double d;
+    memcpy(&d, &u, sizeof d);
+    return d;
+#endif
+}
+
+/* ------------------------------------------------------------------ exp, float */
+/* Cody-Waite reduction x = n*ln2 + r, |r| <= ln2/2, degree-5 minimax tail (the classic
+ * Cephes single-precision coefficient set), scaled by 2^n through the exponent field. */
+MBT_HD float mbt_exp_f32(float x) {
+    if (!(x > -86.0f)) return (x != x) ? x : 0.0f;
+    if (x > 88.0f) return 3.402823466e38f;
+    const float magic = 12582912.0f; /* 1.5 * 2^23: adding it rounds to nearest integer */
+    float t = fmaf(x, 1.44269504088896341f, magic);
+    float n = t - magic;
+    float r = fmaf(n, -0.693359375f, x);
+    r = fmaf(n, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = fmaf(p, r, 1.3981999507e-3f);
+    p = fmaf(p, r, 8.3334519073e-3f);
+    p = fmaf(p, r, 4.1665795894e-2f);
+    p = fmaf(p, r, 1.6666665459e-1f);
+    p = fmaf(p, r, 5.0000001201e-1f);
+    float r2 = r * r;
+    float y = fmaf(p, r2, r) + 1.0f;
+    int32_t ni = (int32_t)n;
+    return mbt_bits_f32(mbt_f32_bits(y) + ((uint32_t)ni << 23));
+}
+
+/* ------------------------------------------------------------------ log, float */
+/* x = m * 2^e, m in [sqrt(1/2), sqrt(2)); log(m) by the Cephes degree-8 polynomial in
+ * f = m - 1.  Defined for finite x > 0 (the only use is on products in (0, 1]); x <= 0
+ * returns -inf / NaN like libm. */
+MBT_HD float mbt_log_f32(float x) {
+    if (!(x > 0.0f)) return (x == 0.0f) ? -INFINITY : NAN;
+    uint32_t b = mbt_f32_bits(x);
+    int32_t e = (int32_t)(b >> 23) - 126;
+    if ((b >> 23) == 0u) { /* subnormal: renormalise exactly */
+        b = mbt_f32_bits(x * 8388608.0f);
+        e = (int32_t)(b >> 23) - 126 - 23;
+    }
+    float m = mbt_bits_f32((b & 0x007FFFFFu) | 0x3F000000u); /* [0.5, 1) */
+    float f;
+    if (m < 0.707106781186547524f) {
+        e -= 1;
+        f = (m + m) - 1.0f;
+    } else {
+        f = m - 1.0f;
+    }
+    float z = f * f;
+    float p = 7.0376836292e-2f;
+    p = fmaf(p, f, -1.1514610310e-1f);
+    p = fmaf(p, f, 1.1676998740e-1f);
+    p = fmaf(p, f, -1.2420140846e-1f);
+    p = fmaf(p, f, 1.4249322787e-1f);
+    p = fmaf(p, f, -1.6668057665e-1f);
+    p = fmaf(p, f, 2.0000714765e-1f);
+    p = fmaf(p, f, -2.4999993993e-1f);
+    p = fmaf(p, f, 3.3333331174e-1f);
+    float fe = (float)e;
+    float y = (p * f) * z;
+    y = fmaf(fe, -2.12194440e-4f, y);
+    y = fmaf(z, -0.5f, y);
+    float res = f + y;
+    return fmaf(fe, 0.693359375f, res);
+}
+
+/* ------------------------------------------------------------------ exp, double */
+MBT_HD double mbt_exp_f64(double x) {
+    if (!(x > -700.0)) return (x != x) ? x : 0.0;
+    if (x > 700.0) return 1.7976931348623157e308;
+    const double magic = 6755399441055744.0; /* 1.5 * 2^52 */
+    double t = fma(x, 1.4426950408889634074, magic);
+    double n = t - magic;
+    double r = fma(n, -6.93147180369123816490e-01, x); /* ln2 high part (fdlibm split) */
+    r = fma(n, -1.90821492927058770002e-10, r);        /* ln2 low part               */
+    /* Taylor series to r^13: truncation < 5e-18 on |r| <= 0.3466 */
+    double p = 1.6059043836821614599e-10; /* 1/13! */
+    p = fma(p, r, 2.0876756987868098979e-9);  /* 1/12! */
+    p = fma(p, r, 2.5052108385441718775e-8);  /* 1/11! */
+    p = fma(p, r, 2.7557319223985890653e-7);  /* 1/10! */
+    p = fma(p, r, 2.7557319223985890653e-6);  /* 1/9!  */
+    p = fma(p, r, 2.4801587301587301587e-5);  /* 1/8!  */
+    p = fma(p, r, 1.9841269841269841270e-4);  /* 1/7!  */
+    p = fma(p, r, 1.3888888888888888889e-3);  /* 1/6!  */
+    p = fma(p, r, 8.3333333333333333333e-3);  /* 1/5!  */
+    p = fma(p, r, 4.1666666666666666667e-2);  /* 1/4!  */
+    p = fma(p, r, 1.6666666666666666667e-1);  /* 1/3!  */
+    p = fma(p, r, 0.5);
+    double r2 = r * r;
+    double y = fma(p, r2, r) + 1.0;
+    int64_t ni = (int64_t)n;
+    return mbt_bits_f64(mbt_f64_bits(y) + ((uint64_t)ni << 52));
+}
+
+/* ------------------------------------------------------------------ log, double */
+/* log(m) = 2*atanh(s), s = f/(2+f), odd series to s^23 (|s| <= 0.1716 -> trunc < 2e-19). */
+MBT_HD double mbt_log_f64(double x) {
+    if (!(x > 0.0)) return (x == 0.0) ? -(double)INFINITY : (double)NAN;
+    uint64_t b = mbt_f64_bits(x);
+    int32_t e = (int32_t)(b >> 52) - 1022;
+    if ((b >> 52) == 0u) {
+        b = mbt_f64_bits(x * 4503599627370496.0);
+        e = (int32_t)(b >> 52) - 1022 - 52;
+    }
+    double m = mbt_bits_f64((b & 0x000FFFFFFFFFFFFFull) | 0x3FE0000000000000ull); /* [0.5,1) */
+    double f;
+    if (m < 0.70710678118654752440) {
+        e -= 1;
+        f = (m + m) - 1.0;
+    } else {
+        f = m - 1.0;
+    }
+    double s = f / (2.0 + f);
+    double s2 = s * s;
+    double p = 1.0 / 23.0;
+    p = fma(p, s2, 1.0 / 21.0);
+    p = fma(p, s2, 1.0 / 19.0);
+    p = fma(p, s2, 1.0 / 17.0);
+    p = fma(p, s2, 1.0 / 15.0);
+    p = fma(p, s2, 1.0 / 13.0);
+    p = fma(p, s2, 1.0 / 11.0);
+    p = fma(p, s2, 1.0 / 9.0);
+    p = fma(p, s2, 1.0 / 7.0);
+    p = fma(p, s2, 1.0 / 5.0);
+    p = fma(p, s2, 1.0 / 3.0);
+    /* log(m) = 2s + 2s*s2*p */
+    double two_s = s + s;
+    double lm = fma(two_s * s2, p, two_s);
+    double fe = (double)e;
+    double lo = fma(fe, 1.90821492927058770002e-10, lm);
+    return fma(fe, 6.93147180369123816490e-01, lo);
+}
+
+/* ------------------------------------------------------------------ normal from 32 bits */
+/*
+ * Standard normal from 32 random bits by inversion: bit 31 is the sign, the low 31 bits m
+ * give the half-normal probability level.  With mc = 2^31-1-m,
+ *     t = (mc + 1/2) / 2^31  in (0,1)     (upper-tail mass; small t = far tail, converted
+ *                                          from the integer so the tail keeps full precision)
+ *     v = 1 - t,   w = -log(t * (2 - t)) = -log(1 - v^2),
+ *     |z| = sqrt(2) * erfinv(v) = sqrt(2) * v * P(w)
+ * P: Giles' piecewise polynomials ("Approximating the erfinv function", 2011) --
+ * float: his published single-precision pair; double: three segments fitted by
+ * tools/fit_normal_icdf.py.  Largest |z| = 6.3 (t = 2^-32).
+ */
+MBT_HD float mbt_normal_from_bits_f32(uint32_t bits) {
+    uint32_t mc = 0x7FFFFFFFu - (bits & 0x7FFFFFFFu);
+    float t = fmaf((float)mc, 4.656612873077392578125e-10f /* 2^-31 */, 2.3283064365386962890625e-10f /* 2^-32 */);
+    float v = 1.0f - t;
+    float w = -mbt_log_f32(t * (2.0f - t));
+    float p;
+    if (w < 5.0f) {
+        w = w - 2.5f;
+        p = 2.81022636e-08f;
+        p = fmaf(p, w, 3.43273939e-07f);
+        p = fmaf(p, w, -3.5233877e-06f);
+        p = fmaf(p, w, -4.39150654e-06f);
+        p = fmaf(p, w, 0.00021858087f);
+        p = fmaf(p, w, -0.00125372503f);
+        p = fmaf(p, w, -0.00417768164f);
+        p = fmaf(p, w, 0.246640727f);
+        p = fmaf(p, w, 1.50140941f);
+    } else if (w >= 16.0f) { /* beyond Giles' single-precision range (t < 2^-24): own degree-4 fit,
+                              * tools/fit_normal_icdf.py segment TAIL re-fitted at float accuracy */
+        w = sqrtf(w) - 4.375f;
+        p = 1.791975665e-04f;
+        p = fmaf(p, w, -5.201602471e-04f);
+        p = fmaf(p, w, 5.034005735e-04f);
+        p = fmaf(p, w, 1.010129929e+00f);
+        p = fmaf(p, w, 4.218480587e+00f);
+    } else {
+        w = sqrtf(w) - 3.0f;
+        p = -0.000200214257f;
+        p = fmaf(p, w, 0.000100950558f);
+        p = fmaf(p, w, 0.00134934322f);
+        p = fmaf(p, w, -0.00367342844f);
+        p = fmaf(p, w, 0.00573950773f);
+        p = fmaf(p, w, -0.0076224613f);
+        p = fmaf(p, w, 0.00943887047f);
+        p = fmaf(p, w, 1.00167406f);
+        p = fmaf(p, w, 2.83297682f);
+    }
+    float z = (1.41421356237309504880f * v) * p;
+    return (bits >> 31) ? -z : z;
+}
+
+MBT_HD double mbt_normal_from_bits_f64(uint32_t bits) {
+    uint32_t mc = 0x7FFFFFFFu - (bits & 0x7FFFFFFFu);
+    double t = ((double)mc + 0.5) * 4.656612873077392578125e-10; /* exact */
+    double v = 1.0 - t;
+    double w = -mbt_log_f64(t * (2.0 - t));
+    double p;
+    if (w < 6.25) {
+        w = w - 3.125;
+        p = -2.93378702136066883e-20;
+        p = fma(p, w, -1.70618749633882542e-20);
+        p = fma(p, w, 1.65276491700746045e-18);
+        p = fma(p, w, 7.64220219799399885e-19);
+        p = fma(p, w, -3.94324760557796949e-17);
+        p = fma(p, w, -1.09079577435404181e-17);
+        p = fma(p, w, 4.38503143106243651e-16);
+        p = fma(p, w, 3.16888922080693809e-16);
+        p = fma(p, w, 1.57760898062725170e-15);
+        p = fma(p, w, -4.30211992333208736e-14);
+        p = fma(p, w, -5.21610747729488213e-14);
+        p = fma(p, w, 2.64690701492755575e-12);
+        p = fma(p, w, -1.30878116424140578e-11);
+        p = fma(p, w, -5.42012076052834127e-11);
+        p = fma(p, w, 1.05149424965246830e-09);
+        p = fma(p, w, -4.11252892034572366e-09);
+        p = fma(p, w, -2.90708125408396845e-08);
+        p = fma(p, w, 4.23478637261581625e-07);
+        p = fma(p, w, -1.36546879478674747e-06);
+        p = fma(p, w, -1.38825232602688395e-05);
+        p = fma(p, w, 1.86734207843842592e-04);
+        p = fma(p, w, -7.40702534198593764e-04);
+        p = fma(p, w, -6.03367087139462018e-03);
+        p = fma(p, w, 2.40158182425592087e-01);
+        p = fma(p, w, 1.65365456268310140e+00);
+    } else {
+        double s = sqrt(w);
+        if (s < 4.0) {
+            s = s - 3.25;
+            p = -7.62029190603530220e-07;
+            p = fma(p, s, -7.16154295328572080e-08);
+            p = fma(p, s, 2.09610158764196380e-06);
+            p = fma(p, s, 2.77641204894734524e-07);
+            p = fma(p, s, -2.71235730553805872e-06);
+            p = fma(p, s, -1.86564814457334863e-07);
+            p = fma(p, s, 3.06667208412655536e-06);
+            p = fma(p, s, -3.89157826630587532e-06);
+            p = fma(p, s, 2.32027017785594476e-06);
+            p = fma(p, s, 1.24321426461071173e-05);
+            p = fma(p, s, -4.71752686387452903e-05);
+            p = fma(p, s, 6.82939857338359650e-05);
+            p = fma(p, s, 2.40106755546017631e-05);
+            p = fma(p, s, -3.55038642504593052e-04);
+            p = fma(p, s, 9.53291036442542551e-04);
+            p = fma(p, s, -1.68827548262202496e-03);
+            p = fma(p, s, 2.49144202910259443e-03);
+            p = fma(p, s, -3.75120850970072283e-03);
+            p = fma(p, s, 5.37091455460582835e-03);
+            p = fma(p, s, 1.00525896769417677e+00);
+            p = fma(p, s, 3.08388561049221810e+00);
+        } else {
+            s = s - 4.375;
+            p = -1.69490261523055272e-05;
+            p = fma(p, s, -5.01780379509045184e-07);
+            p = fma(p, s, 7.29149613974081338e-06);
+            p = fma(p, s, -1.49946089970476237e-07);
+            p = fma(p, s, -2.71249703167381524e-07);
+            p = fma(p, s, -1.78229809009254970e-06);
+            p = fma(p, s, 3.17653889324899587e-06);
+            p = fma(p, s, -5.88398956522093252e-06);
+            p = fma(p, s, 1.51372614712039134e-05);
+            p = fma(p, s, -5.07338716845259286e-05);
+            p = fma(p, s, 1.76456923611614401e-04);
+            p = fma(p, s, -5.11090819314451855e-04);
+            p = fma(p, s, 5.03497607799785864e-04);
+            p = fma(p, s, 1.01012955238797497e+00);
+            p = fma(p, s, 4.21848070765291716e+00);
+        }
+    }
+    double z = (1.41421356237309504880 * v) * p;
+    return (bits >> 31) ? -z : z;
+}
+
+/* x^p for the inventory penalties (reference: RewardFunctions.py:60-67,100-107,133-137,
+ * `q ** inventory_exponent`).  numpy evaluates `** 2.0` as a square and `** 1.0` as the
+ * identity (fast_scalar_power), so those two cases are exact; any other exponent goes
+ * through exp(p*log|x|) with numpy's sign rules (negative base, non-integer p -> NaN). */
+MBT_HD double mbt_pow_f64(double x, double p) {
+    if (p == 2.0) return x * x;
+    if (p == 1.0) return x;
+    if (p == 0.0) return 1.0;
+    if (x == 0.0) return (p > 0.0) ? 0.0 : (double)INFINITY;
+    double ax = x < 0.0 ? -x : x;
+    double r = mbt_exp_f64(p * mbt_log_f64(ax));
+    if (x < 0.0) {
+        double ip = (double)(int64_t)p;
+        if (ip != p) return (double)NAN;
+        return (((int64_t)p) & 1) ? -r : r;
+    }
+    return r;
+}
+MBT_HD float mbt_pow_f32(float x, float p) {
+    if (p == 2.0f) return x * x;
+    if (p == 1.0f) return x;
+    if (p == 0.0f) return 1.0f;
+    if (x == 0.0f) return (p > 0.0f) ? 0.0f : INFINITY;
+    float ax = x < 0.0f ? -x : x;
+    float r = mbt_exp_f32(p * mbt_log_f32(ax));
+    if (x < 0.0f) {
+        float ip = (float)(int32_t)p;
+        if (ip != p) return NAN;
+        return (((int32_t)p) & 1) ? -r : r;
+    }
+    return r;
+}
+
+#endif /* MBT_MATH_H */
