@@ -177,22 +177,27 @@ typedef struct mbt_reset_args {
     int64_t q0_lo, q0_hi;
 } mbt_reset_args;
 
-/* On-device policies for the fused rollout (mbt_gym/agents/BaselineAgents.py). */
+/* On-device policies for the fused rollout (mbt_gym/agents/BaselineAgents.py).  The host facade computes
+ * every policy constant with the reference agent's own Python expressions and passes the results. */
 #define MBT_POL_FIXED 0              /* FixedActionAgent / FixedSpreadAgent  :25-42   */
 #define MBT_POL_AVELLANEDA_STOIKOV 1 /* AvellanedaStoikovAgent               :52-83   */
-#define MBT_POL_CJ_MM_TABLE 2        /* CarteaJaimungalMmAgent               :86-137 (h[t][q] table from the host) */
-#define MBT_POL_CJ_OE 3              /* CarteaJaimungalOeAgent               :173-210 */
+#define MBT_POL_CJ_MM_TABLE 2        /* CarteaJaimungalMmAgent               :86-137: (delta_bid, delta_ask) per
+                                        (decision time, inventory index) precomputed on the host with expm */
+#define MBT_POL_SCHEDULE 3           /* any policy that depends on time only, e.g. CarteaJaimungalOeAgent
+                                        :173-210: one action row per decision time */
 
 typedef struct mbt_policy {
     int32_t kind;
-    int32_t table_rows;  /* CJ_MM_TABLE: n_steps (one row per decision time)            */
-    int32_t table_cols;  /* CJ_MM_TABLE: 2*Q+1                                          */
-    int32_t _pad;
-    double fixed[MBT_MAX_ACTION_DIM]; /* FIXED: the raw (de-normalised) action           */
-    double risk_aversion;             /* AVELLANEDA_STOIKOV: gamma                       */
-    double oe_phi, oe_alpha;          /* CJ_OE                                          */
-    double large_depth;               /* CJ_MM_TABLE: 10_000 (BaselineAgents.py:108)     */
-    const double *table;              /* CJ_MM_TABLE: HOST pointer, rows*cols float64    */
+    int32_t table_rows; /* CJ_MM_TABLE / SCHEDULE: number of decision times (>= steps to run)      */
+    int32_t table_cols; /* CJ_MM_TABLE: 2*Q+1                                                      */
+    int32_t inv_offset; /* CJ_MM_TABLE: Q, index = clip(Q + inventory, 0, 2Q)  BaselineAgents.py:121 */
+    double fixed[MBT_MAX_ACTION_DIM]; /* FIXED: the action row, as the agent would return it        */
+    double as_gamma;         /* AVELLANEDA_STOIKOV: risk_aversion                                  */
+    double as_sigma_sq;      /*   volatility**2                                 BaselineAgents.py:71 */
+    double as_fill_comp;     /*   2/gamma*log(1+gamma/kappa), or 2/kappa if gamma == 0       :73-79 */
+    double as_terminal_time; /*   env.terminal_time                                                */
+    const double *table;     /* HOST pointer.  CJ_MM_TABLE: rows*cols*2 float64 (bid, ask);
+                                SCHEDULE: rows*A float64                                           */
 } mbt_policy;
 
 /* Episode summary = the reference's results table (plotting.py:96-108) as raw moments. */
@@ -243,6 +248,10 @@ int mbt_set_state(mbt_env *env, const void *state_in, int mem);
 int mbt_get_clock(mbt_env *env, double *time, int64_t *steps_this_episode, int64_t *steps_since_seed,
                   int64_t *episodes_since_seed);
 
+/* Trajectories whose inventory or cash was clipped since mbt_create (the reference prints the arrays
+ * instead, TradingEnvironment.py:283-297). */
+int mbt_get_clip_count(mbt_env *env, int64_t *count);
+
 /* reward_function.calculate(current_state, action, next_state, is_terminal) on (n, D)/(n, A) buffers,
  * using the handle's reward parameters and the q0 / episode length captured at the last reset. */
 int mbt_reward_eval(mbt_env *env, int64_t n, const void *current_state, const void *action,
@@ -257,8 +266,15 @@ int mbt_rollout(mbt_env *env, const mbt_policy *policy, mbt_summary *summary_out
 /* Per-call statistics for bench.py: number of kernel launches issued by this handle so far, and the
  * device time (ms, CUDA events on the handle's stream) of the most recent step kernel when enabled. */
 int mbt_get_launch_count(mbt_env *env, int64_t *launches);
+/* enable != 0: bracket every subsequent hot-path kernel (step / rollout) with CUDA events on the handle's
+ * stream (up to an internal ring capacity); mbt_get_kernel_times synchronises and returns their durations. */
 int mbt_enable_timing(mbt_env *env, int enable);
-int mbt_last_kernel_ms(mbt_env *env, float *ms);
+int mbt_get_kernel_times(mbt_env *env, float *ms_out, int64_t capacity, int64_t *count);
+
+/* Pinned (page-locked) host memory for caller buffers: MBT_MEM_HOST buffers allocated here are DMA'd
+ * directly; any other host pointer is staged through the handle's own pinned buffers. */
+int mbt_host_alloc(size_t bytes, void **out);
+int mbt_host_free(void *ptr);
 
 #ifdef __cplusplus
 }

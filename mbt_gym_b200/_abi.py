@@ -54,7 +54,7 @@ MBT_Q0_UNIFORM_INT = 1
 MBT_POL_FIXED = 0
 MBT_POL_AVELLANEDA_STOIKOV = 1
 MBT_POL_CJ_MM_TABLE = 2
-MBT_POL_CJ_OE = 3
+MBT_POL_SCHEDULE = 3
 
 MBT_MAX_ACTION_DIM = 4
 MBT_MAX_OBS_DIM = 8
@@ -133,13 +133,13 @@ class mbt_policy(C.Structure):
         ("kind", C.c_int32),
         ("table_rows", C.c_int32),
         ("table_cols", C.c_int32),
-        ("_pad", C.c_int32),
+        ("inv_offset", C.c_int32),
         ("fixed", C.c_double * MBT_MAX_ACTION_DIM),
-        ("risk_aversion", C.c_double),
-        ("oe_phi", C.c_double),
-        ("oe_alpha", C.c_double),
-        ("large_depth", C.c_double),
-        ("table", C.POINTER(C.c_double)),
+        ("as_gamma", C.c_double),
+        ("as_sigma_sq", C.c_double),
+        ("as_fill_comp", C.c_double),
+        ("as_terminal_time", C.c_double),
+        ("table", C.c_void_p),
     ]
 
 

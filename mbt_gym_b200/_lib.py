@@ -1,0 +1,216 @@
+"""ctypes binding of libmbt_b200.so (include/mbt_b200.h) and a thin handle class.
+
+The product has NO CPU fallback: if the library is missing or no CUDA device is usable, the calls here raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmbt_b200.so")
+
+# every symbol include/mbt_b200.h declares (checked by tests/test_abi_symbols.py)
+ABI_SYMBOLS = [
+    "mbt_abi_version", "mbt_last_error", "mbt_config_dims", "mbt_create", "mbt_destroy", "mbt_set_stream", "mbt_sync",
+    "mbt_seed", "mbt_reset", "mbt_step", "mbt_get_state", "mbt_set_state", "mbt_get_clock", "mbt_get_clip_count",
+    "mbt_reward_eval", "mbt_rollout", "mbt_get_launch_count", "mbt_enable_timing", "mbt_get_kernel_times",
+    "mbt_host_alloc", "mbt_host_free",
+]
+
+_lib = None
+
+
+class MbtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmbt_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    """Load libmbt_b200.so (built in-tree by `python -m mbt_gym_b200._build` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found. mbt_gym_b200 has no CPU implementation: build the CUDA library first "
+            "(python -m mbt_gym_b200._build, needs nvcc)."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, i64p = C.c_void_p, C.POINTER(C.c_int64)
+    cfgp = C.POINTER(_abi.mbt_config)
+    L.mbt_abi_version.restype = C.c_int
+    L.mbt_last_error.restype = C.c_char_p
+    L.mbt_config_dims.argtypes = [cfgp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.mbt_create.argtypes = [cfgp, C.c_int, C.POINTER(vp)]
+    L.mbt_destroy.argtypes = [vp]
+    L.mbt_set_stream.argtypes = [vp, vp]
+    L.mbt_sync.argtypes = [vp]
+    L.mbt_seed.argtypes = [vp, C.c_uint64]
+    L.mbt_reset.argtypes = [vp, C.POINTER(_abi.mbt_reset_args), vp, C.c_int]
+    L.mbt_step.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_uint8), C.c_int]
+    L.mbt_get_state.argtypes = [vp, vp, C.c_int]
+    L.mbt_set_state.argtypes = [vp, vp, C.c_int]
+    L.mbt_get_clock.argtypes = [vp, C.POINTER(C.c_double), i64p, i64p, i64p]
+    L.mbt_get_clip_count.argtypes = [vp, i64p]
+    L.mbt_reward_eval.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, vp, C.c_int]
+    L.mbt_rollout.argtypes = [vp, C.POINTER(_abi.mbt_policy), C.POINTER(_abi.mbt_summary), vp, vp, C.c_int]
+    L.mbt_get_launch_count.argtypes = [vp, i64p]
+    L.mbt_enable_timing.argtypes = [vp, C.c_int]
+    L.mbt_get_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int64, i64p]
+    L.mbt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.mbt_host_free.argtypes = [vp]
+    if L.mbt_abi_version() != _abi.MBT_ABI_VERSION:
+        raise ImportError(f"libmbt_b200.so ABI {L.mbt_abi_version()} != binding ABI {_abi.MBT_ABI_VERSION}")
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise MbtError(rc, load().mbt_last_error().decode("utf-8", "replace"))
+
+
+def config_dims(cfg):
+    a, d, s = C.c_int32(), C.c_int32(), C.c_int32()
+    _check(load().mbt_config_dims(C.byref(cfg), C.byref(a), C.byref(d), C.byref(s)))
+    return a.value, d.value, s.value
+
+
+class PinnedArray:
+    """A numpy array backed by page-locked memory from mbt_host_alloc (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(int(x) for x in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        _check(load().mbt_host_alloc(max(nbytes, 1), C.byref(p)))
+        self._ptr = p
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def __del__(self):
+        p = getattr(self, "_ptr", None)
+        if p is not None and p.value:
+            try:
+                load().mbt_host_free(p)
+            except Exception:
+                pass
+            self._ptr = None
+
+
+def _addr(x):
+    """Address of a host numpy array, a raw int device pointer, or anything with data_ptr() (torch tensor)."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "__cuda_array_interface__"):
+        return x.__cuda_array_interface__["data"][0]
+    raise TypeError(f"cannot take the address of {type(x)}")
+
+
+class NativeEnv:
+    """One mbt_env handle.  Host numpy buffers (mem=HOST) or device pointers / torch tensors (mem=DEVICE)."""
+
+    def __init__(self, cfg, device=0):
+        self._h = C.c_void_p()
+        self.cfg = cfg
+        self.device = device
+        self.N = int(cfg.num_trajectories)
+        self.A, self.D, self.S = config_dims(cfg)
+        self.dtype = np.dtype(np.float64 if cfg.precision == _abi.MBT_F64 else np.float32)
+        _check(load().mbt_create(C.byref(cfg), device, C.byref(self._h)))
+
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            load().mbt_destroy(h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- control
+    def seed(self, seed):
+        _check(load().mbt_seed(self._h, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF)))
+
+    def sync(self):
+        _check(load().mbt_sync(self._h))
+
+    def set_stream(self, stream_ptr):
+        _check(load().mbt_set_stream(self._h, C.c_void_p(stream_ptr or 0)))
+
+    # -- hot path
+    def reset(self, obs_out=None, args=None, mem=_abi.MBT_MEM_HOST):
+        _check(load().mbt_reset(self._h, None if args is None else C.byref(args), _addr(obs_out), mem))
+        return obs_out
+
+    def step(self, actions, obs_out=None, rew_out=None, mem=_abi.MBT_MEM_HOST):
+        done = C.c_uint8(0)
+        _check(load().mbt_step(self._h, _addr(actions), _addr(obs_out), _addr(rew_out), C.byref(done), mem))
+        return bool(done.value)
+
+    def rollout(self, policy, returns_out=None, terminal_q_out=None, mem=_abi.MBT_MEM_HOST):
+        summary = _abi.mbt_summary()
+        _check(load().mbt_rollout(self._h, C.byref(policy), C.byref(summary), _addr(returns_out), _addr(terminal_q_out), mem))
+        return summary
+
+    # -- state
+    def get_state(self, out=None, mem=_abi.MBT_MEM_HOST):
+        if out is None:
+            out = np.empty((self.N, self.D), self.dtype)
+        _check(load().mbt_get_state(self._h, _addr(out), mem))
+        return out
+
+    def set_state(self, state, mem=_abi.MBT_MEM_HOST):
+        if mem == _abi.MBT_MEM_HOST:
+            state = np.ascontiguousarray(state, self.dtype)
+            assert state.shape == (self.N, self.D)
+        _check(load().mbt_set_state(self._h, _addr(state), mem))
+
+    def clock(self):
+        t, k, n, e = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
+        _check(load().mbt_get_clock(self._h, C.byref(t), C.byref(k), C.byref(n), C.byref(e)))
+        return dict(time=t.value, k=k.value, n_step=n.value, n_episode=e.value)
+
+    def clip_count(self):
+        c = C.c_int64()
+        _check(load().mbt_get_clip_count(self._h, C.byref(c)))
+        return c.value
+
+    def reward_eval(self, cur, act, nxt, is_terminal=False):
+        cur = np.ascontiguousarray(cur, self.dtype)
+        act = np.ascontiguousarray(act, self.dtype)
+        nxt = np.ascontiguousarray(nxt, self.dtype)
+        out = np.empty((cur.shape[0],), self.dtype)
+        _check(load().mbt_reward_eval(self._h, cur.shape[0], _addr(cur), _addr(act), _addr(nxt), int(bool(is_terminal)),
+                                      _addr(out), _abi.MBT_MEM_HOST))
+        return out
+
+    # -- statistics
+    def launch_count(self):
+        c = C.c_int64()
+        _check(load().mbt_get_launch_count(self._h, C.byref(c)))
+        return c.value
+
+    def enable_timing(self, on=True):
+        _check(load().mbt_enable_timing(self._h, int(bool(on))))
+
+    def kernel_times_ms(self):
+        n = C.c_int64()
+        _check(load().mbt_get_kernel_times(self._h, None, 0, C.byref(n)))
+        buf = (C.c_float * max(n.value, 1))()
+        _check(load().mbt_get_kernel_times(self._h, buf, n.value, C.byref(n)))
+        return np.array(buf[: n.value], dtype=np.float32)

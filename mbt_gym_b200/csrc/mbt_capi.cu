@@ -1,0 +1,754 @@
+/*
+ * mbt_capi.cu -- libmbt_b200.so: handle management and the C ABI of include/mbt_b200.h.
+ *
+ * There is no CPU implementation in this library: every entry point that computes launches one of the
+ * kernels of mbt_kernels.cuh on the handle's stream.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/mbt_b200.h"
+#include "mbt_host_params.h"
+#include "mbt_kernels.cuh"
+
+/* ------------------------------------------------------------------ errors */
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(expr)                                                                                      \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            char _b[512];                                                                             \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                     __LINE__);                                                                       \
+            return fail(MBT_E_CUDA, _b);                                                              \
+        }                                                                                             \
+    } while (0)
+
+/* ------------------------------------------------------------------ handle */
+constexpr int MBT_TIMING_RING = 8192;
+
+struct mbt_env {
+    mbt_config cfg;
+    int device = 0;
+    int A = 0, D = 0, S = 0;
+    size_t esz = 8;
+    long long N = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+
+    /* device state, structure-of-arrays (one allocation, columns of N elements) */
+    void *state_block = nullptr;
+    void *col[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; /* cash, inv, mid, x0, x1, q0 */
+    unsigned long long *d_clipped = nullptr;
+
+    /* device + pinned staging for MBT_MEM_HOST calls */
+    void *d_actions = nullptr, *d_obs = nullptr, *d_rew = nullptr;
+    void *h_actions = nullptr, *h_obs = nullptr, *h_rew = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr;
+    cudaStream_t copy_stream = nullptr;
+
+    /* rollout scratch */
+    double *d_times = nullptr;
+    int times_cap = 0;
+    void *d_table = nullptr;
+    size_t table_cap = 0;
+    double *d_block_sums = nullptr, *h_block_sums = nullptr;
+    int block_sums_cap = 0;
+
+    /* clock (uniform over trajectories) */
+    double t = 0, t0 = 0;
+    int64_t k = 0, n_step = 0, n_episode = 0;
+    bool started = false;
+    uint64_t seed = 0;
+    int q0_per_traj = 0;
+    double q0_uniform = 0;
+
+    /* statistics */
+    int64_t launches = 0;
+    bool timing = false;
+    std::vector<cudaEvent_t> ev0, ev1;
+    int64_t timed = 0;
+};
+
+template <typename T>
+static DevState<T> dev_state(mbt_env *e) {
+    DevState<T> st;
+    st.cash = (T *)e->col[0];
+    st.inv = (T *)e->col[1];
+    st.mid = (T *)e->col[2];
+    st.x0 = (T *)e->col[3];
+    st.x1 = (T *)e->col[4];
+    st.q0 = (T *)e->col[5];
+    return st;
+}
+
+static inline unsigned grid_for(long long n) { return (unsigned)((n + MBT_BLOCK - 1) / MBT_BLOCK); }
+
+static int timing_begin(mbt_env *e) {
+    if (!e->timing || e->timed >= MBT_TIMING_RING) return MBT_OK;
+    if ((int64_t)e->ev0.size() <= e->timed) {
+        cudaEvent_t a, b;
+        CU(cudaEventCreate(&a));
+        CU(cudaEventCreate(&b));
+        e->ev0.push_back(a);
+        e->ev1.push_back(b);
+    }
+    CU(cudaEventRecord(e->ev0[e->timed], e->stream));
+    return MBT_OK;
+}
+static int timing_end(mbt_env *e) {
+    if (!e->timing || e->timed >= MBT_TIMING_RING) return MBT_OK;
+    CU(cudaEventRecord(e->ev1[e->timed], e->stream));
+    e->timed += 1;
+    return MBT_OK;
+}
+
+/* is this host pointer page-locked (DMA-able without staging)? */
+static bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+/* parallel memcpy between pageable user memory and pinned staging (a single thread tops out well below PCIe) */
+static void par_memcpy(void *dst, const void *src, size_t bytes) {
+    const size_t chunk = 4u << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nthreads = std::min<size_t>(std::max(1u, std::min(hw, 8u)), (bytes + chunk - 1) / chunk);
+    if (nthreads <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    size_t per = (bytes / nthreads + 63) & ~(size_t)63;
+    for (size_t i = 0; i < nthreads; ++i) {
+        size_t off = i * per;
+        if (off >= bytes) break;
+        size_t len = std::min(per, bytes - off);
+        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    for (auto &t : th) t.join();
+}
+
+/* ------------------------------------------------------------------ launchers */
+template <typename T, class V>
+static void launch_step_v(mbt_env *e, const StepArgs<T> &g, bool vec) {
+    if (vec)
+        mbt_step_kernel<T, V, true><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
+    else
+        mbt_step_kernel<T, V, false><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
+}
+
+/* the BASELINE.json configurations get compile-time-specialised kernels, everything else the generic one */
+using VariantAS = Variant<MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, -1>;
+using VariantHawkes = Variant<MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, -1>;
+using VariantOE = Variant<MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, -1>;
+
+static int variant_of(const mbt_config &c) {
+    if (c.dynamics == MBT_DYN_LIMIT && c.midprice == MBT_MID_BM && c.impact == MBT_IMP_NONE) {
+        if (c.arrival == MBT_ARR_POISSON) return 1;
+        if (c.arrival == MBT_ARR_HAWKES) return 2;
+    }
+    if (c.dynamics == MBT_DYN_SPEED && c.midprice == MBT_MID_OU && c.impact == MBT_IMP_TEMP_PERM &&
+        c.arrival == MBT_ARR_NONE)
+        return 3;
+    return 0;
+}
+
+/* may the step kernel use whole-row vector accesses on the caller's buffers?  (see load_row / store_row:
+ * actions A=2 -> 2-element, A=4 -> 4-element vectors; observations D=4 -> 4-element, D=6 -> 2-element) */
+template <typename T>
+static bool rows_vector_aligned(const mbt_env *e, const void *actions, const void *obs) {
+    const size_t need_a = (size_t)(e->A == 2 ? 2 : e->A == 4 ? 4 : 1) * sizeof(T);
+    const size_t need_o = (size_t)(e->D == 4 ? 4 : e->D == 6 ? 2 : 1) * sizeof(T);
+    return ((uintptr_t)actions % need_a) == 0 && (!obs || ((uintptr_t)obs % need_o) == 0);
+}
+
+template <typename T>
+static int do_step_device(mbt_env *e, const void *actions, void *obs, void *rew, uint8_t *done_out) {
+    const mbt_config &c = e->cfg;
+    const double t_next = e->t + c.step_size; /* state[:, TIME] += step_size   TradingEnvironment.py:216 */
+    StepArgs<T> g;
+    g.p = mbt_make_params<T>(c, e->t0, e->q0_per_traj, e->q0_uniform);
+    g.ck = mbt_make_clock<T>(c, e->t, t_next);
+    g.st = dev_state<T>(e);
+    g.actions = (const T *)actions;
+    g.obs = (T *)obs;
+    g.rew = (T *)rew;
+    g.n = e->N;
+    g.seed = e->seed;
+    g.traj_offset = (unsigned long long)c.traj_offset;
+    g.n_step = (unsigned long long)e->n_step;
+    g.clipped = e->d_clipped;
+    const bool vec = rows_vector_aligned<T>(e, actions, obs);
+    int rc = timing_begin(e);
+    if (rc) return rc;
+    switch (variant_of(c)) {
+    case 1: launch_step_v<T, VariantAS>(e, g, vec); break;
+    case 2: launch_step_v<T, VariantHawkes>(e, g, vec); break;
+    case 3: launch_step_v<T, VariantOE>(e, g, vec); break;
+    default: launch_step_v<T, VariantGeneric>(e, g, vec); break;
+    }
+    CU(cudaGetLastError());
+    rc = timing_end(e);
+    if (rc) return rc;
+    e->launches += 1;
+    e->t = t_next;
+    e->k += 1;
+    e->n_step += 1;
+    if (done_out) *done_out = (uint8_t)g.ck.done;
+    return MBT_OK;
+}
+
+template <typename T>
+static int do_reset_device(mbt_env *e, const mbt_reset_args *args, void *obs) {
+    const mbt_config &c = e->cfg;
+    const double t0 = args ? args->start_time : c.start_time;
+    const int q0_mode = args ? args->q0_mode : c.q0_mode;
+    const double q0_const = args ? args->q0_const : c.q0_const;
+    const int64_t lo = args ? args->q0_lo : c.q0_lo, hi = args ? args->q0_hi : c.q0_hi;
+    if (q0_mode == MBT_Q0_UNIFORM_INT && !(hi > lo)) return fail(MBT_E_INVALID_ARG, "initial inventory range needs hi > lo");
+    if (!(t0 >= 0.0) || !(t0 < c.terminal_time))
+        return fail(MBT_E_INVALID_ARG, "Start time is not within (0, env.terminal_time)."); /* TradingEnvironment.py:267 */
+    ResetArgs<T> g;
+    g.p = mbt_make_params<T>(c, t0, q0_mode == MBT_Q0_UNIFORM_INT, q0_const);
+    g.st = dev_state<T>(e);
+    g.obs = (T *)obs;
+    g.n = e->N;
+    g.seed = e->seed;
+    g.traj_offset = (unsigned long long)c.traj_offset;
+    g.n_episode = (unsigned long long)e->n_episode;
+    g.cash0 = (T)c.initial_cash;
+    g.t0 = (T)t0;
+    g.mid0 = (T)c.mid_initial;
+    g.lam0[0] = (T)c.arr_rate[0];
+    g.lam0[1] = (T)c.arr_rate[1];
+    g.q0_mode = q0_mode;
+    g.q0_const = (T)q0_const;
+    g.q0_lo = lo;
+    g.q0_span = (unsigned long long)(hi - lo);
+    mbt_reset_kernel<T><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
+    CU(cudaGetLastError());
+    e->launches += 1;
+    e->t = t0;
+    e->t0 = t0;
+    e->k = 0;
+    e->n_episode += 1;
+    e->started = true;
+    e->q0_per_traj = (q0_mode == MBT_Q0_UNIFORM_INT);
+    e->q0_uniform = q0_const;
+    return MBT_OK;
+}
+
+/* ------------------------------------------------------------------ ABI */
+extern "C" {
+
+int mbt_abi_version(void) { return MBT_ABI_VERSION; }
+const char *mbt_last_error(void) { return g_err.c_str(); }
+
+int mbt_config_dims(const mbt_config *cfg, int32_t *action_dim, int32_t *obs_dim, int32_t *state_cols) {
+    if (!cfg) return fail(MBT_E_INVALID_ARG, "config is NULL");
+    int rc = mbt_dims(cfg, action_dim, obs_dim, state_cols);
+    if (rc) return fail(rc, "unknown dynamics kind");
+    return MBT_OK;
+}
+
+int mbt_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(MBT_E_INVALID_ARG, "out is NULL");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return MBT_OK;
+}
+int mbt_host_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return MBT_OK;
+}
+
+int mbt_destroy(mbt_env *e) {
+    if (!e) return MBT_OK;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->state_block);
+    cudaFree(e->d_clipped);
+    cudaFree(e->d_actions);
+    cudaFree(e->d_obs);
+    cudaFree(e->d_rew);
+    cudaFreeHost(e->h_actions);
+    cudaFreeHost(e->h_obs);
+    cudaFreeHost(e->h_rew);
+    cudaFree(e->d_times);
+    cudaFree(e->d_table);
+    cudaFree(e->d_block_sums);
+    cudaFreeHost(e->h_block_sums);
+    for (auto ev : e->ev0) cudaEventDestroy(ev);
+    for (auto ev : e->ev1) cudaEventDestroy(ev);
+    if (e->ev_h2d) cudaEventDestroy(e->ev_h2d);
+    if (e->ev_kernel) cudaEventDestroy(e->ev_kernel);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    cudaGetLastError();
+    delete e;
+    return MBT_OK;
+}
+
+int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
+    if (!out) return fail(MBT_E_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    std::string err;
+    int rc = mbt_validate_config(cfg, err);
+    if (rc) return fail(rc, err);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MBT_E_CUDA, std::string("no usable CUDA device (") + cudaGetErrorString(ce) +
+                                    "); libmbt_b200 has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return fail(MBT_E_INVALID_ARG, "device index out of range");
+    CU(cudaSetDevice(device));
+    mbt_env *e = new (std::nothrow) mbt_env();
+    if (!e) return fail(MBT_E_NOMEM, "out of host memory");
+    e->cfg = *cfg;
+    e->device = device;
+    e->N = cfg->num_trajectories;
+    mbt_dims(cfg, &e->A, &e->D, &e->S);
+    e->esz = cfg->precision == MBT_F64 ? 8 : 4;
+    auto bail = [&](int code) {
+        std::string keep = g_err;
+        mbt_destroy(e);
+        g_err = keep;
+        return code;
+    };
+#define CUB(expr)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess) {                                                                          \
+            fail(_e == cudaErrorMemoryAllocation ? MBT_E_NOMEM : MBT_E_CUDA,                              \
+                 std::string(#expr " failed: ") + cudaGetErrorString(_e));                                \
+            return bail(_e == cudaErrorMemoryAllocation ? MBT_E_NOMEM : MBT_E_CUDA);                      \
+        }                                                                                                 \
+    } while (0)
+    CUB(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    CUB(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&e->ev_kernel, cudaEventDisableTiming));
+    /* columns padded to 256 B so every column base is aligned for any vector width */
+    const size_t col_bytes = (((size_t)e->N * e->esz) + 255) & ~(size_t)255;
+    CUB(cudaMalloc(&e->state_block, col_bytes * 6));
+    CUB(cudaMemsetAsync(e->state_block, 0, col_bytes * 6, e->stream));
+    for (int i = 0; i < 6; ++i) e->col[i] = (char *)e->state_block + col_bytes * i;
+    CUB(cudaMalloc(&e->d_clipped, sizeof(unsigned long long)));
+    CUB(cudaMemsetAsync(e->d_clipped, 0, sizeof(unsigned long long), e->stream));
+    CUB(cudaStreamSynchronize(e->stream));
+#undef CUB
+    *out = e;
+    return MBT_OK;
+}
+
+int mbt_set_stream(mbt_env *e, void *cuda_stream) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return MBT_OK;
+}
+
+int mbt_sync(mbt_env *e) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return MBT_OK;
+}
+
+int mbt_seed(mbt_env *e, uint64_t seed) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    e->seed = seed;
+    e->n_step = 0;
+    e->n_episode = 0;
+    return MBT_OK;
+}
+
+/* lazily allocate the device + pinned staging used by MBT_MEM_HOST calls */
+static int ensure_staging(mbt_env *e) {
+    if (e->d_actions) return MBT_OK;
+    const size_t ab = (size_t)e->N * e->A * e->esz, ob = (size_t)e->N * e->D * e->esz, rb = (size_t)e->N * e->esz;
+    CU(cudaMalloc(&e->d_actions, ab));
+    CU(cudaMalloc(&e->d_obs, ob));
+    CU(cudaMalloc(&e->d_rew, rb));
+    CU(cudaHostAlloc(&e->h_actions, ab, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&e->h_obs, ob, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&e->h_rew, rb, cudaHostAllocDefault));
+    return MBT_OK;
+}
+
+/* device -> caller host buffer: direct DMA when the buffer is pinned, else through pinned staging */
+static int d2h(mbt_env *e, void *host_dst, const void *dev_src, void *pinned_stage, size_t bytes, bool *needs_unstage) {
+    *needs_unstage = false;
+    if (host_ptr_is_pinned(host_dst)) {
+        CU(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, e->stream));
+    } else {
+        CU(cudaMemcpyAsync(pinned_stage, dev_src, bytes, cudaMemcpyDeviceToHost, e->stream));
+        *needs_unstage = true;
+    }
+    return MBT_OK;
+}
+
+int mbt_reset(mbt_env *e, const mbt_reset_args *args, void *obs_out, int mem) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    if (mem != MBT_MEM_HOST && mem != MBT_MEM_DEVICE) return fail(MBT_E_INVALID_ARG, "mem must be MBT_MEM_HOST or MBT_MEM_DEVICE");
+    CU(cudaSetDevice(e->device));
+    void *dev_obs = obs_out;
+    if (obs_out && mem == MBT_MEM_HOST) {
+        int rc = ensure_staging(e);
+        if (rc) return rc;
+        dev_obs = e->d_obs;
+    }
+    int rc = e->cfg.precision == MBT_F64 ? do_reset_device<double>(e, args, dev_obs) : do_reset_device<float>(e, args, dev_obs);
+    if (rc) return rc;
+    if (obs_out && mem == MBT_MEM_HOST) {
+        const size_t ob = (size_t)e->N * e->D * e->esz;
+        bool unstage = false;
+        rc = d2h(e, obs_out, e->d_obs, e->h_obs, ob, &unstage);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(e->stream));
+        if (unstage) par_memcpy(obs_out, e->h_obs, ob);
+    }
+    return MBT_OK;
+}
+
+int mbt_step(mbt_env *e, const void *actions, void *obs_out, void *rew_out, uint8_t *done_out, int mem) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    if (!actions) return fail(MBT_E_INVALID_ARG, "actions is NULL");
+    if (mem != MBT_MEM_HOST && mem != MBT_MEM_DEVICE) return fail(MBT_E_INVALID_ARG, "mem must be MBT_MEM_HOST or MBT_MEM_DEVICE");
+    if (!e->started) return fail(MBT_E_STATE, "mbt_step called before mbt_reset");
+    CU(cudaSetDevice(e->device));
+    const bool f64 = e->cfg.precision == MBT_F64;
+    if (mem == MBT_MEM_DEVICE)
+        return f64 ? do_step_device<double>(e, actions, obs_out, rew_out, done_out)
+                   : do_step_device<float>(e, actions, obs_out, rew_out, done_out);
+
+    /* host buffers: H2D actions -> kernel -> D2H observations + rewards, all inside this call */
+    int rc = ensure_staging(e);
+    if (rc) return rc;
+    const size_t ab = (size_t)e->N * e->A * e->esz, ob = (size_t)e->N * e->D * e->esz, rb = (size_t)e->N * e->esz;
+    const void *src = actions;
+    if (!host_ptr_is_pinned(actions)) {
+        par_memcpy(e->h_actions, actions, ab);
+        src = e->h_actions;
+    }
+    CU(cudaMemcpyAsync(e->d_actions, src, ab, cudaMemcpyHostToDevice, e->stream));
+    rc = f64 ? do_step_device<double>(e, e->d_actions, obs_out ? e->d_obs : nullptr, rew_out ? e->d_rew : nullptr, done_out)
+             : do_step_device<float>(e, e->d_actions, obs_out ? e->d_obs : nullptr, rew_out ? e->d_rew : nullptr, done_out);
+    if (rc) return rc;
+    bool un_obs = false, un_rew = false;
+    if (obs_out) {
+        rc = d2h(e, obs_out, e->d_obs, e->h_obs, ob, &un_obs);
+        if (rc) return rc;
+    }
+    if (rew_out) {
+        rc = d2h(e, rew_out, e->d_rew, e->h_rew, rb, &un_rew);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    if (un_obs) par_memcpy(obs_out, e->h_obs, ob);
+    if (un_rew) par_memcpy(rew_out, e->h_rew, rb);
+    return MBT_OK;
+}
+
+int mbt_get_state(mbt_env *e, void *state_out, int mem) {
+    if (!e || !state_out) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    CU(cudaSetDevice(e->device));
+    void *dev = state_out;
+    if (mem == MBT_MEM_HOST) {
+        int rc = ensure_staging(e);
+        if (rc) return rc;
+        dev = e->d_obs;
+    }
+    if (e->cfg.precision == MBT_F64) {
+        auto p = mbt_make_params<double>(e->cfg, e->t0, e->q0_per_traj, e->q0_uniform);
+        mbt_gather_state_kernel<double><<<grid_for(e->N), MBT_BLOCK, 0, e->stream>>>(p, dev_state<double>(e), e->t, (double *)dev, e->N);
+    } else {
+        auto p = mbt_make_params<float>(e->cfg, e->t0, e->q0_per_traj, e->q0_uniform);
+        mbt_gather_state_kernel<float><<<grid_for(e->N), MBT_BLOCK, 0, e->stream>>>(p, dev_state<float>(e), (float)e->t, (float *)dev, e->N);
+    }
+    CU(cudaGetLastError());
+    e->launches += 1;
+    if (mem == MBT_MEM_HOST) {
+        CU(cudaMemcpyAsync(state_out, dev, (size_t)e->N * e->D * e->esz, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    return MBT_OK;
+}
+
+int mbt_set_state(mbt_env *e, const void *state_in, int mem) {
+    if (!e || !state_in) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    CU(cudaSetDevice(e->device));
+    const void *dev = state_in;
+    const size_t ob = (size_t)e->N * e->D * e->esz;
+    if (mem == MBT_MEM_HOST) {
+        int rc = ensure_staging(e);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(e->d_obs, state_in, ob, cudaMemcpyHostToDevice, e->stream));
+        dev = e->d_obs;
+        /* the clock is the TIME column of row 0 (uniform)   TradingEnvironment.py:219 */
+        e->t = e->cfg.precision == MBT_F64 ? ((const double *)state_in)[2] : (double)((const float *)state_in)[2];
+    } else {
+        char buf[8];
+        CU(cudaMemcpyAsync(buf, (const char *)state_in + 2 * e->esz, e->esz, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        e->t = e->cfg.precision == MBT_F64 ? *(double *)buf : (double)*(float *)buf;
+    }
+    if (e->cfg.precision == MBT_F64) {
+        auto p = mbt_make_params<double>(e->cfg, e->t0, e->q0_per_traj, e->q0_uniform);
+        mbt_scatter_state_kernel<double><<<grid_for(e->N), MBT_BLOCK, 0, e->stream>>>(p, dev_state<double>(e), (const double *)dev, e->N);
+    } else {
+        auto p = mbt_make_params<float>(e->cfg, e->t0, e->q0_per_traj, e->q0_uniform);
+        mbt_scatter_state_kernel<float><<<grid_for(e->N), MBT_BLOCK, 0, e->stream>>>(p, dev_state<float>(e), (const float *)dev, e->N);
+    }
+    CU(cudaGetLastError());
+    e->launches += 1;
+    e->started = true;
+    if (mem == MBT_MEM_HOST) CU(cudaStreamSynchronize(e->stream));
+    return MBT_OK;
+}
+
+int mbt_get_clock(mbt_env *e, double *time, int64_t *steps_this_episode, int64_t *steps_since_seed, int64_t *episodes_since_seed) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    if (time) *time = e->t;
+    if (steps_this_episode) *steps_this_episode = e->k;
+    if (steps_since_seed) *steps_since_seed = e->n_step;
+    if (episodes_since_seed) *episodes_since_seed = e->n_episode;
+    return MBT_OK;
+}
+
+int mbt_get_clip_count(mbt_env *e, int64_t *count) {
+    if (!e || !count) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    CU(cudaSetDevice(e->device));
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, e->d_clipped, sizeof v, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    *count = (int64_t)v;
+    return MBT_OK;
+}
+
+int mbt_reward_eval(mbt_env *e, int64_t n, const void *current_state, const void *action, const void *next_state, int is_terminal,
+                    void *rew_out, int mem) {
+    if (!e || !current_state || !action || !next_state || !rew_out) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    if (n <= 0) return fail(MBT_E_INVALID_ARG, "n must be > 0");
+    CU(cudaSetDevice(e->device));
+    const size_t sb = (size_t)n * e->D * e->esz, ab = (size_t)n * e->A * e->esz, rb = (size_t)n * e->esz;
+    const void *dc = current_state, *da = action, *dn = next_state;
+    void *dr = rew_out;
+    void *tmp = nullptr;
+    if (mem == MBT_MEM_HOST) {
+        CU(cudaMalloc(&tmp, 2 * sb + ab + rb));
+        char *b = (char *)tmp;
+        CU(cudaMemcpyAsync(b, current_state, sb, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(b + sb, next_state, sb, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(b + 2 * sb, action, ab, cudaMemcpyHostToDevice, e->stream));
+        dc = b; dn = b + sb; da = b + 2 * sb; dr = b + 2 * sb + ab;
+    }
+    if (e->cfg.precision == MBT_F64) {
+        auto p = mbt_make_params<double>(e->cfg, e->t0, 0, e->q0_uniform);
+        mbt_reward_kernel<double><<<grid_for(n), MBT_BLOCK, 0, e->stream>>>(p, is_terminal, (const double *)dc, (const double *)da, (const double *)dn, (double *)dr, n);
+    } else {
+        auto p = mbt_make_params<float>(e->cfg, e->t0, 0, e->q0_uniform);
+        mbt_reward_kernel<float><<<grid_for(n), MBT_BLOCK, 0, e->stream>>>(p, is_terminal, (const float *)dc, (const float *)da, (const float *)dn, (float *)dr, n);
+    }
+    cudaError_t le = cudaGetLastError();
+    e->launches += 1;
+    if (mem == MBT_MEM_HOST) {
+        if (le == cudaSuccess) le = cudaMemcpyAsync(rew_out, dr, rb, cudaMemcpyDeviceToHost, e->stream);
+        cudaError_t se = cudaStreamSynchronize(e->stream);
+        cudaFree(tmp);
+        if (le == cudaSuccess) le = se;
+    }
+    if (le != cudaSuccess) return fail(MBT_E_CUDA, std::string("mbt_reward_eval: ") + cudaGetErrorString(le));
+    return MBT_OK;
+}
+
+} /* extern "C" */
+
+template <typename T>
+static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, void *returns, void *term_q) {
+    const mbt_config &c = e->cfg;
+    /* the clock exactly as repeated `state[:, TIME] += step_size` produces it   TradingEnvironment.py:216 */
+    std::vector<double> times;
+    times.push_back(e->t);
+    int steps = 0;
+    {
+        double t = e->t;
+        const int cap = 1 << 24;
+        while (steps < cap) {
+            t = t + c.step_size;
+            times.push_back(t);
+            steps += 1;
+            if (t >= c.terminal_time - c.step_size / 2) break;
+        }
+    }
+    if ((int)times.size() > e->times_cap) {
+        cudaFree(e->d_times);
+        e->d_times = nullptr;
+        CU(cudaMalloc(&e->d_times, times.size() * sizeof(double)));
+        e->times_cap = (int)times.size();
+    }
+    CU(cudaMemcpyAsync(e->d_times, times.data(), times.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+
+    RolloutArgs<T> g;
+    memset(&g, 0, sizeof g);
+    g.p = mbt_make_params<T>(c, e->t0, e->q0_per_traj, e->q0_uniform);
+    g.st = dev_state<T>(e);
+    g.n = e->N;
+    g.seed = e->seed;
+    g.traj_offset = (unsigned long long)c.traj_offset;
+    g.n_step0 = (unsigned long long)e->n_step;
+    g.steps = steps;
+    g.times = e->d_times;
+    g.terminal_time = c.terminal_time;
+    g.step_size = c.step_size;
+    g.pol_kind = pol->kind;
+    g.table_rows = pol->table_rows;
+    g.table_cols = pol->table_cols;
+    g.inv_offset = pol->inv_offset;
+    for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j) g.fixed[j] = (T)pol->fixed[j];
+    g.as_gamma = (T)pol->as_gamma;
+    g.as_sigma_sq = (T)pol->as_sigma_sq;
+    g.as_fill_comp = (T)pol->as_fill_comp;
+    g.as_terminal_time = (T)pol->as_terminal_time;
+    std::vector<T> host_table;
+    if (pol->kind == MBT_POL_CJ_MM_TABLE || pol->kind == MBT_POL_SCHEDULE) {
+        if (!pol->table) return fail(MBT_E_INVALID_ARG, "policy table is NULL");
+        if (pol->table_rows < steps) return fail(MBT_E_INVALID_ARG, "policy table has fewer rows than the steps left in the episode");
+        size_t count = pol->kind == MBT_POL_CJ_MM_TABLE ? (size_t)pol->table_rows * pol->table_cols * 2 : (size_t)pol->table_rows * e->A;
+        if (pol->kind == MBT_POL_CJ_MM_TABLE && (pol->table_cols != 2 * pol->inv_offset + 1 || pol->inv_offset < 0))
+            return fail(MBT_E_INVALID_ARG, "CJ_MM_TABLE needs table_cols == 2*inv_offset+1");
+        host_table.resize(count);
+        for (size_t i = 0; i < count; ++i) host_table[i] = (T)pol->table[i];
+        if (count * sizeof(T) > e->table_cap) {
+            cudaFree(e->d_table);
+            e->d_table = nullptr;
+            CU(cudaMalloc(&e->d_table, count * sizeof(T)));
+            e->table_cap = count * sizeof(T);
+        }
+        CU(cudaMemcpyAsync(e->d_table, host_table.data(), count * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+        g.table = (const T *)e->d_table;
+    } else if (pol->kind != MBT_POL_FIXED && pol->kind != MBT_POL_AVELLANEDA_STOIKOV) {
+        return fail(MBT_E_UNSUPPORTED, "unknown policy kind");
+    }
+    if (pol->kind == MBT_POL_AVELLANEDA_STOIKOV && e->A != 2) return fail(MBT_E_UNSUPPORTED, "Avellaneda-Stoikov policy needs a 2-d action");
+    g.returns = (T *)returns;
+    g.term_q = (T *)term_q;
+    const int blocks = (int)grid_for(g.n);
+    if (blocks > e->block_sums_cap) {
+        cudaFree(e->d_block_sums);
+        cudaFreeHost(e->h_block_sums);
+        e->d_block_sums = e->h_block_sums = nullptr;
+        CU(cudaMalloc(&e->d_block_sums, (size_t)blocks * MBT_SUMMARY_DOUBLES * sizeof(double)));
+        CU(cudaHostAlloc(&e->h_block_sums, (size_t)blocks * MBT_SUMMARY_DOUBLES * sizeof(double), cudaHostAllocDefault));
+        e->block_sums_cap = blocks;
+    }
+    g.block_sums = e->d_block_sums;
+    g.clipped = e->d_clipped;
+    unsigned long long clip_before = 0, clip_after = 0;
+    CU(cudaMemcpyAsync(&clip_before, e->d_clipped, sizeof clip_before, cudaMemcpyDeviceToHost, e->stream));
+    int rc = timing_begin(e);
+    if (rc) return rc;
+    switch (variant_of(c)) {
+    case 1: mbt_rollout_kernel<T, VariantAS><<<blocks, MBT_BLOCK, 0, e->stream>>>(g); break;
+    case 2: mbt_rollout_kernel<T, VariantHawkes><<<blocks, MBT_BLOCK, 0, e->stream>>>(g); break;
+    case 3: mbt_rollout_kernel<T, VariantOE><<<blocks, MBT_BLOCK, 0, e->stream>>>(g); break;
+    default: mbt_rollout_kernel<T, VariantGeneric><<<blocks, MBT_BLOCK, 0, e->stream>>>(g); break;
+    }
+    CU(cudaGetLastError());
+    rc = timing_end(e);
+    if (rc) return rc;
+    e->launches += 1;
+    CU(cudaMemcpyAsync(e->h_block_sums, e->d_block_sums, (size_t)blocks * MBT_SUMMARY_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(&clip_after, e->d_clipped, sizeof clip_after, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    double tot[MBT_SUMMARY_DOUBLES] = {0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < blocks; ++b)
+        for (int m = 0; m < MBT_SUMMARY_DOUBLES; ++m) tot[m] += e->h_block_sums[(size_t)b * MBT_SUMMARY_DOUBLES + m];
+    if (summary) {
+        summary->count = e->N;
+        summary->steps = steps;
+        summary->sum_return = tot[0];
+        summary->sum_return_sq = tot[1];
+        summary->sum_q = tot[2];
+        summary->sum_q_sq = tot[3];
+        summary->sum_action = tot[4];
+        summary->sum_reward_sq = tot[5];
+        summary->clipped = (int64_t)(clip_after - clip_before);
+    }
+    e->t = times.back();
+    e->k += steps;
+    e->n_step += steps;
+    return MBT_OK;
+}
+
+extern "C" {
+
+int mbt_rollout(mbt_env *e, const mbt_policy *policy, mbt_summary *summary_out, void *returns_out, void *terminal_q_out, int mem) {
+    if (!e || !policy) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    if (!e->started) return fail(MBT_E_STATE, "mbt_rollout called before mbt_reset");
+    if (e->t >= e->cfg.terminal_time - e->cfg.step_size / 2) return fail(MBT_E_STATE, "episode already finished; call mbt_reset");
+    CU(cudaSetDevice(e->device));
+    void *d_ret = returns_out, *d_q = terminal_q_out;
+    const size_t rb = (size_t)e->N * e->esz;
+    if (mem == MBT_MEM_HOST && (returns_out || terminal_q_out)) {
+        int rc = ensure_staging(e);
+        if (rc) return rc;
+        d_ret = returns_out ? e->d_rew : nullptr;
+        d_q = terminal_q_out ? e->d_obs : nullptr; /* d_obs holds >= N elements */
+    }
+    int rc = e->cfg.precision == MBT_F64 ? do_rollout<double>(e, policy, summary_out, d_ret, d_q)
+                                         : do_rollout<float>(e, policy, summary_out, d_ret, d_q);
+    if (rc) return rc;
+    if (mem == MBT_MEM_HOST) {
+        if (returns_out) CU(cudaMemcpyAsync(returns_out, d_ret, rb, cudaMemcpyDeviceToHost, e->stream));
+        if (terminal_q_out) CU(cudaMemcpyAsync(terminal_q_out, d_q, rb, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    return MBT_OK;
+}
+
+int mbt_get_launch_count(mbt_env *e, int64_t *launches) {
+    if (!e || !launches) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    *launches = e->launches;
+    return MBT_OK;
+}
+
+int mbt_enable_timing(mbt_env *e, int enable) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    e->timing = enable != 0;
+    e->timed = 0;
+    return MBT_OK;
+}
+
+int mbt_get_kernel_times(mbt_env *e, float *ms_out, int64_t capacity, int64_t *count) {
+    if (!e || !count) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    int64_t n = std::min<int64_t>(e->timed, capacity);
+    for (int64_t i = 0; i < n && ms_out; ++i) CU(cudaEventElapsedTime(&ms_out[i], e->ev0[i], e->ev1[i]));
+    *count = e->timed;
+    return MBT_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,124 @@
+/*
+ * mbt_host_params.h -- host-side (no CUDA) helpers: config validation, dims, and the per-launch
+ * StepParams<T> built from mbt_config.  Derived constants are formed in float64 exactly the way the
+ * reference's Python floats form them, then cast once to the arithmetic type.
+ */
+#ifndef MBT_HOST_PARAMS_H
+#define MBT_HOST_PARAMS_H
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "mbt_step_core.cuh"
+
+/* action dim A (ModelDynamics.get_action_space), obs dim D = 3 + sum(process dims)
+ * (TradingEnvironment.py:232-241,311-318), persistent state columns S = D - 1 (time is a uniform scalar). */
+static inline int mbt_dims(const mbt_config *c, int32_t *A, int32_t *D, int32_t *S) {
+    int a, d = 4;
+    switch (c->dynamics) {
+    case MBT_DYN_LIMIT: a = 2; break;
+    case MBT_DYN_AT_TOUCH: a = 2; break;
+    case MBT_DYN_LIMIT_AND_MARKET: a = 4; break;
+    case MBT_DYN_SPEED: a = 1; break;
+    default: return MBT_E_UNSUPPORTED;
+    }
+    if (c->arrival == MBT_ARR_HAWKES) d += 2;
+    if (c->impact == MBT_IMP_TEMP_PERM) d += 1;
+    if (A) *A = a;
+    if (D) *D = d;
+    if (S) *S = d - 1;
+    return MBT_OK;
+}
+
+static inline int mbt_validate_config(const mbt_config *c, std::string &err) {
+    char buf[256];
+    if (!c) { err = "config is NULL"; return MBT_E_INVALID_ARG; }
+    if (c->struct_size != (int32_t)sizeof(mbt_config)) {
+        snprintf(buf, sizeof buf, "mbt_config.struct_size=%d, library expects %zu (ABI mismatch)", c->struct_size,
+                 sizeof(mbt_config));
+        err = buf;
+        return MBT_E_INVALID_ARG;
+    }
+    if (c->precision != MBT_F64 && c->precision != MBT_F32) { err = "precision must be MBT_F64 or MBT_F32"; return MBT_E_INVALID_ARG; }
+    if (c->num_trajectories <= 0) { err = "num_trajectories must be > 0"; return MBT_E_INVALID_ARG; }
+    if (c->traj_offset < 0) { err = "traj_offset must be >= 0"; return MBT_E_INVALID_ARG; }
+    if (c->n_steps <= 0 || !(c->step_size > 0) || !(c->terminal_time > 0)) {
+        err = "n_steps, step_size and terminal_time must be > 0";
+        return MBT_E_INVALID_ARG;
+    }
+    if (mbt_dims(c, nullptr, nullptr, nullptr) != MBT_OK) { err = "unknown dynamics kind"; return MBT_E_UNSUPPORTED; }
+    if (c->midprice < MBT_MID_CONSTANT || c->midprice > MBT_MID_OU) { err = "unknown midprice model"; return MBT_E_UNSUPPORTED; }
+    if (c->reward < MBT_REW_PNL || c->reward > MBT_REW_EXP_UTILITY) { err = "unknown reward function"; return MBT_E_UNSUPPORTED; }
+    if (c->dynamics == MBT_DYN_SPEED) {
+        /* ModelDynamics.py:273-275: required_processes = ["price_impact_model"] */
+        if (c->impact != MBT_IMP_TEMP_PERM && c->impact != MBT_IMP_TEMP_POWER) {
+            err = "speed dynamics needs a price impact model (temp_perm or temp_power)";
+            return MBT_E_UNSUPPORTED;
+        }
+        if (c->arrival == MBT_ARR_HAWKES) { err = "speed dynamics with a Hawkes arrival model is not supported"; return MBT_E_UNSUPPORTED; }
+    } else {
+        /* ModelDynamics.py:123-125,163-165,234-236: arrival (+ fill) models required */
+        if (c->arrival < MBT_ARR_POISSON || c->arrival > MBT_ARR_HAWKES) { err = "limit-order dynamics need an arrival model"; return MBT_E_UNSUPPORTED; }
+        if (c->dynamics != MBT_DYN_AT_TOUCH && c->fill != MBT_FILL_EXPONENTIAL) {
+            err = "limit-order dynamics need the exponential fill model";
+            return MBT_E_UNSUPPORTED;
+        }
+        if (c->impact != MBT_IMP_NONE) { err = "price impact models only combine with speed dynamics"; return MBT_E_UNSUPPORTED; }
+        if (c->reward == MBT_REW_CJ_OE) { err = "CjOeCriterion needs a 1-d action (reference fails too, RewardFunctions.py:66)"; return MBT_E_UNSUPPORTED; }
+    }
+    if (c->q0_mode == MBT_Q0_UNIFORM_INT && !(c->q0_hi > c->q0_lo)) { err = "initial inventory range needs hi > lo"; return MBT_E_INVALID_ARG; }
+    if (c->q0_mode != MBT_Q0_UNIFORM_INT && c->q0_mode != MBT_Q0_CONST) { err = "unknown q0_mode"; return MBT_E_INVALID_ARG; }
+    return MBT_OK;
+}
+
+/* The uniform clock of the step that moves time from t_cur to t_next. */
+template <typename T>
+static inline StepClock<T> mbt_make_clock(const mbt_config &c, double t_cur, double t_next) {
+    StepClock<T> ck;
+    ck.t_next = (T)t_next;
+    ck.dt_r = (T)(t_next - t_cur);
+    ck.done = t_next >= c.terminal_time - c.step_size / 2; /* TradingEnvironment.py:218-220 */
+    return ck;
+}
+
+/* Uniform per-episode parameters (t0 = start time of the running episode). */
+template <typename T>
+static inline StepParams<T> mbt_make_params(const mbt_config &c, double t0, int q0_per_traj, double q0_uniform) {
+    StepParams<T> p;
+    memset(&p, 0, sizeof p);
+    int32_t A, D, S;
+    mbt_dims(&c, &A, &D, &S);
+    p.dyn = c.dynamics; p.mid = c.midprice; p.arr = c.arrival; p.imp = c.impact; p.rew = c.reward;
+    p.action_dim = A; p.obs_dim = D;
+    p.normalise_action = c.normalise_action; p.normalise_obs = c.normalise_obs; p.normalise_rewards = c.normalise_rewards;
+    p.q0_per_traj = q0_per_traj;
+    p.ep_len = (T)(c.rew_terminal_time - t0);
+    p.q0_uniform = (T)q0_uniform;
+    p.qmax = (T)c.max_inventory; p.cmax = (T)c.max_cash;
+    if (c.arrival == MBT_ARR_POISSON) {
+        p.p_arr[0] = (T)(c.arr_rate[0] * c.arr_step);
+        p.p_arr[1] = (T)(c.arr_rate[1] * c.arr_step);
+    } else if (c.arrival == MBT_ARR_POISSON_NONLINEAR) {
+        p.p_arr[0] = (T)(1.0 - mbt_exp_f64(-c.arr_rate[0] * c.arr_step));
+        p.p_arr[1] = (T)(1.0 - mbt_exp_f64(-c.arr_rate[1] * c.arr_step));
+    }
+    p.arr_step = (T)c.arr_step; p.arr_rate[0] = (T)c.arr_rate[0]; p.arr_rate[1] = (T)c.arr_rate[1];
+    p.hawkes_speed = (T)c.hawkes_speed; p.hawkes_jump = (T)c.hawkes_jump;
+    p.neg_kappa = -(T)c.fill_exponent;
+    p.drift_dt = (T)(c.mid_drift * c.mid_step);
+    p.vol_sqdt = (T)(c.mid_vol * std::sqrt(c.mid_step));
+    p.sqdt = (T)std::sqrt(c.mid_step);
+    p.mid_drift = (T)c.mid_drift; p.mid_vol = (T)c.mid_vol; p.mid_step = (T)c.mid_step;
+    p.ou_neg_speed = -(T)c.ou_speed; p.ou_level = (T)c.ou_level;
+    p.imp_temp = (T)c.imp_temp; p.imp_perm = (T)c.imp_perm; p.imp_exp = (T)c.imp_exponent; p.imp_step = (T)c.imp_step;
+    p.half_spread = (T)c.half_spread;
+    p.phi = (T)c.rew_phi; p.alpha = (T)c.rew_alpha; p.pexp = (T)c.rew_exponent; p.risk_aversion = (T)c.rew_risk_aversion;
+    p.reward_scaling = (T)c.reward_scaling;
+    for (int i = 0; i < MBT_MAX_ACTION_DIM; ++i) { p.act_low[i] = (T)c.act_low[i]; p.act_grad[i] = (T)c.act_grad[i]; }
+    for (int i = 0; i < MBT_MAX_OBS_DIM; ++i) { p.obs_low[i] = (T)c.obs_low[i]; p.obs_grad[i] = (T)c.obs_grad[i]; }
+    return p;
+}
+
+#endif /* MBT_HOST_PARAMS_H */

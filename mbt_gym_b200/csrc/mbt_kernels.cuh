@@ -1,0 +1,383 @@
+/*
+ * mbt_kernels.cuh -- the sm_100a kernels of the hot path.
+ *
+ *   mbt_step_kernel     one env-step for all trajectories        (TradingEnvironment.step,  :103-110)
+ *   mbt_reset_kernel    start an episode                         (TradingEnvironment.reset, :96-101)
+ *   mbt_rollout_kernel  whole episode, policy on device, state in registers
+ *                                                                (generate_trajectory, helpers/generate_trajectory.py:8-38)
+ *   gather/scatter      (N,D) row-major <-> structure-of-arrays  (env.state property)
+ *   mbt_reward_kernel   RewardFunction.calculate on caller rows  (RewardFunctions.py:8-13)
+ *
+ * Data layout in HBM (DESIGN.md "Layout"): the persistent per-trajectory state is structure-of-arrays,
+ * one contiguous column per scalar (cash, inventory, midprice, then model columns), so a warp's access to
+ * a column is one fully-coalesced 128 B (float) / 256 B (double) transaction.  Time is NOT stored per
+ * trajectory: the reference's clock is uniform over the batch (TradingEnvironment.py:216-220), so it lives
+ * in the kernel arguments.  Caller-facing buffers keep the reference's layouts: actions (N,A), observations
+ * (N,D) row-major; each thread reads/writes its row with the widest aligned vector access (128-bit, or the
+ * sm_100 256-bit LDG/STG for a 4-double row).
+ *
+ * No tensor cores: the path is elementwise + counter-based RNG, bound by HBM bytes and INT32/FP issue.
+ */
+#ifndef MBT_KERNELS_CUH
+#define MBT_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "mbt_step_core.cuh"
+
+constexpr int MBT_BLOCK = 256;
+
+template <typename T>
+struct DevState {
+    T *cash, *inv, *mid, *x0, *x1, *q0;
+};
+
+template <typename T>
+struct StepArgs {
+    StepParams<T> p;
+    StepClock<T> ck;
+    DevState<T> st;
+    const T *actions; /* (N, A) */
+    T *obs;           /* (N, D) or NULL */
+    T *rew;           /* (N,)   or NULL */
+    long long n;
+    unsigned long long seed, traj_offset, n_step;
+    unsigned long long *clipped;
+};
+
+/* ------------------------------------------------------------------ row access helpers */
+template <typename T, int W>
+struct RowIO; /* W = row width known at compile time (0 = runtime width, scalar accesses) */
+
+__device__ __forceinline__ void st_v4_f64(double *ptr, double a, double b, double c, double d) {
+    /* sm_100: 256-bit global store (SASS STG.E.ENL2.256), 32-byte aligned */
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(ptr), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld_v4_f64(const double *ptr, double &a, double &b, double &c, double &d) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(ptr));
+}
+
+template <typename T>
+__device__ __forceinline__ void load_row(const T *__restrict__ base, long long i, int w, T *out, bool vec_ok) {
+    const T *row = base + i * w;
+    if (vec_ok && w == 2) {
+        if constexpr (sizeof(T) == 4) {
+            float2 v = __ldg(reinterpret_cast<const float2 *>(row));
+            out[0] = v.x; out[1] = v.y;
+        } else {
+            double2 v = __ldg(reinterpret_cast<const double2 *>(row));
+            out[0] = v.x; out[1] = v.y;
+        }
+    } else if (vec_ok && w == 4) {
+        if constexpr (sizeof(T) == 4) {
+            float4 v = __ldg(reinterpret_cast<const float4 *>(row));
+            out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+        } else {
+            double a, b, c, d;
+            ld_v4_f64(reinterpret_cast<const double *>(row), a, b, c, d);
+            out[0] = a; out[1] = b; out[2] = c; out[3] = d;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < MBT_MAX_OBS_DIM; ++j)
+            if (j < w) out[j] = __ldg(row + j);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_row(T *__restrict__ base, long long i, int w, const T *v, bool vec_ok) {
+    T *row = base + i * w;
+    if (vec_ok && w == 4) {
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float4 *>(row) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            st_v4_f64(reinterpret_cast<double *>(row), v[0], v[1], v[2], v[3]);
+        }
+    } else if (vec_ok && w == 6) {
+        if constexpr (sizeof(T) == 4) {
+            float2 *r2 = reinterpret_cast<float2 *>(row);
+            r2[0] = make_float2(v[0], v[1]); r2[1] = make_float2(v[2], v[3]); r2[2] = make_float2(v[4], v[5]);
+        } else {
+            double2 *r2 = reinterpret_cast<double2 *>(row);
+            r2[0] = make_double2(v[0], v[1]); r2[1] = make_double2(v[2], v[3]); r2[2] = make_double2(v[4], v[5]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < MBT_MAX_OBS_DIM; ++j)
+            if (j < w) row[j] = v[j];
+    }
+}
+
+/* observation row of one trajectory: [cash, inventory, time, midprice | arrival cols | impact col]
+ * (TradingEnvironment.py:131-140,303-318), normalised on the way out (:112-118). */
+template <typename T, class V>
+__device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T> &s, T t, T *row) {
+    const int arr = pick<V::arr>(p.arr), imp = pick<V::imp>(p.imp);
+    int d = 0;
+    row[d] = norm_obs(p, s.cash, d); ++d;
+    row[d] = norm_obs(p, s.inv, d); ++d;
+    row[d] = norm_obs(p, t, d); ++d;
+    row[d] = norm_obs(p, s.mid, d); ++d;
+    if (arr == MBT_ARR_HAWKES) {
+        row[d] = norm_obs(p, s.x0, d); ++d;
+        row[d] = norm_obs(p, s.x1, d); ++d;
+    }
+    if (imp == MBT_IMP_TEMP_PERM) { row[d] = norm_obs(p, s.x0, d); ++d; }
+    return d;
+}
+
+template <typename T, class V>
+__device__ __forceinline__ void load_traj(const StepParams<T> &p, const DevState<T> &st, long long i, Traj<T> &s) {
+    const int arr = pick<V::arr>(p.arr), imp = pick<V::imp>(p.imp);
+    s.cash = st.cash[i];
+    s.inv = st.inv[i];
+    s.mid = st.mid[i];
+    s.x0 = (T)0;
+    s.x1 = (T)0;
+    if (arr == MBT_ARR_HAWKES) { s.x0 = st.x0[i]; s.x1 = st.x1[i]; }
+    if (imp == MBT_IMP_TEMP_PERM) s.x0 = st.x0[i];
+}
+
+template <typename T, class V>
+__device__ __forceinline__ void store_traj(const StepParams<T> &p, const DevState<T> &st, long long i, const Traj<T> &s) {
+    const int arr = pick<V::arr>(p.arr), imp = pick<V::imp>(p.imp), mid = pick<V::mid>(p.mid);
+    st.cash[i] = s.cash;
+    st.inv[i] = s.inv;
+    if (mid != MBT_MID_CONSTANT) st.mid[i] = s.mid;
+    if (arr == MBT_ARR_HAWKES) { st.x0[i] = s.x0; st.x1[i] = s.x1; }
+    if (imp == MBT_IMP_TEMP_PERM) st.x0[i] = s.x0;
+}
+
+/* ------------------------------------------------------------------ step */
+/* VEC: the caller's action/obs pointers are aligned for whole-row vector access. */
+template <typename T, class V, bool VEC>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_constant__ StepArgs<T> g) {
+    const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
+    if (i >= g.n) return;
+    const StepParams<T> &p = g.p;
+
+    T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
+    load_row<T>(g.actions, i, p.action_dim, a, VEC);
+#pragma unroll
+    for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j)
+        if (j < p.action_dim) a[j] = denorm_action(p, a[j], j);
+
+    Traj<T> s;
+    load_traj<T, V>(p, g.st, i, s);
+    const T q_init = p.q0_per_traj ? g.st.q0[i] : p.q0_uniform;
+
+    const mbt_u32x4 r = mbt_draw(g.seed, g.traj_offset + (unsigned long long)i, g.n_step, MBT_STREAM_STEP);
+    int clipped = 0;
+    const T rwd = step_one<T, V>(p, g.ck, s, a, r, q_init, &clipped);
+
+    store_traj<T, V>(p, g.st, i, s);
+    if (g.obs) {
+        T row[MBT_MAX_OBS_DIM];
+        const int d = make_obs_row<T, V>(p, s, g.ck.t_next, row);
+        store_row<T>(g.obs, i, d, row, VEC);
+    }
+    if (g.rew) g.rew[i] = rwd;
+    if (clipped) atomicAdd(g.clipped, 1ull);
+}
+
+/* ------------------------------------------------------------------ reset */
+template <typename T>
+struct ResetArgs {
+    StepParams<T> p; /* for normalisation + model kinds */
+    DevState<T> st;
+    T *obs;
+    long long n;
+    unsigned long long seed, traj_offset, n_episode;
+    T cash0, t0, mid0, lam0[2];
+    int q0_mode;
+    T q0_const;
+    long long q0_lo;
+    unsigned long long q0_span;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_reset_kernel(const __grid_constant__ ResetArgs<T> g) {
+    const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
+    if (i >= g.n) return;
+    const StepParams<T> &p = g.p;
+    Traj<T> s;
+    s.cash = g.cash0;
+    if (g.q0_mode == MBT_Q0_UNIFORM_INT) { /* rng.integers(lo, hi)   TradingEnvironment.py:271-272 */
+        const mbt_u32x4 r = mbt_draw(g.seed, g.traj_offset + (unsigned long long)i, g.n_episode, MBT_STREAM_RESET);
+        s.inv = (T)(g.q0_lo + (long long)(((unsigned long long)r.x * g.q0_span) >> 32));
+    } else {
+        s.inv = g.q0_const;
+    }
+    s.mid = g.mid0;
+    s.x0 = (T)0;
+    s.x1 = (T)0;
+    if (p.arr == MBT_ARR_HAWKES) { s.x0 = g.lam0[0]; s.x1 = g.lam0[1]; }
+    g.st.cash[i] = s.cash;
+    g.st.inv[i] = s.inv;
+    g.st.mid[i] = s.mid;
+    if (p.arr == MBT_ARR_HAWKES) { g.st.x0[i] = s.x0; g.st.x1[i] = s.x1; }
+    if (p.imp == MBT_IMP_TEMP_PERM) g.st.x0[i] = s.x0;
+    if (g.q0_mode == MBT_Q0_UNIFORM_INT) g.st.q0[i] = s.inv; /* reward_function.reset  RewardFunctions.py:72,111 */
+    if (g.obs) {
+        T row[MBT_MAX_OBS_DIM];
+        const int d = make_obs_row<T, VariantGeneric>(p, s, g.t0, row);
+        store_row<T>(g.obs, i, d, row, false);
+    }
+}
+
+/* ------------------------------------------------------------------ state gather / scatter */
+template <typename T>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_gather_state_kernel(StepParams<T> p, DevState<T> st, T t, T *out, long long n) {
+    const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    Traj<T> s;
+    load_traj<T, VariantGeneric>(p, st, i, s);
+    StepParams<T> raw = p;
+    raw.normalise_obs = 0;
+    T row[MBT_MAX_OBS_DIM];
+    const int d = make_obs_row<T, VariantGeneric>(raw, s, t, row);
+    store_row<T>(out, i, d, row, false);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_scatter_state_kernel(StepParams<T> p, DevState<T> st, const T *in, long long n) {
+    const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const T *row = in + i * p.obs_dim;
+    st.cash[i] = row[0];
+    st.inv[i] = row[1];
+    st.mid[i] = row[3];
+    int d = 4;
+    if (p.arr == MBT_ARR_HAWKES) { st.x0[i] = row[d]; st.x1[i] = row[d + 1]; d += 2; }
+    if (p.imp == MBT_IMP_TEMP_PERM) st.x0[i] = row[d];
+}
+
+/* ------------------------------------------------------------------ reward on caller rows */
+template <typename T>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_reward_kernel(StepParams<T> p, int is_terminal, const T *cur, const T *act, const T *nxt,
+                                                               T *out, long long n) {
+    const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const T *c = cur + i * p.obs_dim, *x = nxt + i * p.obs_dim;
+    T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
+    for (int j = 0; j < p.action_dim; ++j) a[j] = act[i * p.action_dim + j];
+    Traj<T> s;
+    s.cash = x[0]; s.inv = x[1]; s.mid = x[3]; s.x0 = 0; s.x1 = 0;
+    StepClock<T> ck;
+    ck.t_next = x[2];
+    ck.dt_r = x[2] - c[2];
+    ck.done = is_terminal;
+    out[i] = reward_one<T, VariantGeneric>(p, ck, c[0], c[1], c[3], s, a, p.q0_uniform);
+}
+
+/* ------------------------------------------------------------------ fused rollout */
+constexpr int MBT_SUMMARY_DOUBLES = 6; /* sum R, sum R^2, sum q, sum q^2, sum action, sum r^2 */
+
+template <typename T>
+struct RolloutArgs {
+    StepParams<T> p;
+    DevState<T> st;
+    long long n;
+    unsigned long long seed, traj_offset, n_step0;
+    int steps;            /* env-steps to run (until the episode ends) */
+    const double *times;  /* device, steps+1 entries: the clock as the host accumulates it (t += dt) */
+    double terminal_time, step_size;
+    /* policy */
+    int pol_kind, table_rows, table_cols, inv_offset;
+    T fixed[MBT_MAX_ACTION_DIM];
+    T as_gamma, as_sigma_sq, as_fill_comp, as_terminal_time;
+    const T *table; /* device */
+    /* outputs */
+    T *returns; /* (N,) or NULL */
+    T *term_q;  /* (N,) or NULL */
+    double *block_sums; /* (gridDim.x, MBT_SUMMARY_DOUBLES) */
+    unsigned long long *clipped;
+};
+
+template <typename T>
+__device__ __forceinline__ void policy_action(const RolloutArgs<T> &g, int k, T t, const Traj<T> &s, T *a) {
+    const int A = g.p.action_dim;
+    if (g.pol_kind == MBT_POL_AVELLANEDA_STOIKOV) { /* BaselineAgents.py:62-83 */
+        const T tau = g.as_terminal_time - t;
+        const T adj = ((s.inv * g.as_gamma) * g.as_sigma_sq) * tau;
+        const T spread = (g.as_gamma == (T)0) ? g.as_fill_comp : (g.as_gamma * g.as_sigma_sq) * tau + g.as_fill_comp;
+        a[0] = adj + spread / (T)2;
+        a[1] = -adj + spread / (T)2;
+    } else if (g.pol_kind == MBT_POL_CJ_MM_TABLE) { /* BaselineAgents.py:116-137 */
+        T fi = (T)g.inv_offset + s.inv;
+        const T hi = (T)(2 * g.inv_offset);
+        fi = fi < (T)0 ? (T)0 : fi;
+        fi = fi > hi ? hi : fi;
+        const int idx = (int)fi; /* .astype(int) truncates */
+        const T *e = g.table + ((long long)k * g.table_cols + idx) * 2;
+        a[0] = e[0];
+        a[1] = e[1];
+    } else if (g.pol_kind == MBT_POL_SCHEDULE) {
+        for (int j = 0; j < A; ++j) a[j] = g.table[(long long)k * A + j];
+    } else { /* MBT_POL_FIXED  BaselineAgents.py:25-42 */
+        for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j) a[j] = g.fixed[j];
+    }
+}
+
+template <typename T, class V>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_constant__ RolloutArgs<T> g) {
+    const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
+    const bool live = i < g.n;
+    const StepParams<T> &p = g.p;
+    double acc[MBT_SUMMARY_DOUBLES] = {0, 0, 0, 0, 0, 0};
+    if (live) {
+        Traj<T> s;
+        load_traj<T, V>(p, g.st, i, s);
+        const T q_init = p.q0_per_traj ? g.st.q0[i] : p.q0_uniform;
+        T ret = (T)0;
+        int clipped = 0;
+        double t_cur = g.times[0];
+        for (int k = 0; k < g.steps; ++k) {
+            const double t_next = g.times[k + 1];
+            StepClock<T> ck;
+            ck.t_next = (T)t_next;
+            ck.dt_r = (T)(t_next - t_cur);
+            ck.done = t_next >= g.terminal_time - g.step_size / 2;
+            T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
+            policy_action<T>(g, k, (T)t_cur, s, a);
+#pragma unroll
+            for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j)
+                if (j < p.action_dim) {
+                    acc[4] += (double)a[j];
+                    a[j] = denorm_action(p, a[j], j);
+                }
+            const mbt_u32x4 r = mbt_draw(g.seed, g.traj_offset + (unsigned long long)i, g.n_step0 + (unsigned long long)k, MBT_STREAM_STEP);
+            const T rwd = step_one<T, V>(p, ck, s, a, r, q_init, &clipped);
+            ret = ret + rwd;
+            acc[5] += (double)rwd * (double)rwd;
+            t_cur = t_next;
+        }
+        store_traj<T, V>(p, g.st, i, s);
+        if (g.returns) g.returns[i] = ret;
+        if (g.term_q) g.term_q[i] = s.inv;
+        acc[0] = (double)ret;
+        acc[1] = (double)ret * (double)ret;
+        acc[2] = (double)s.inv;
+        acc[3] = (double)s.inv * (double)s.inv;
+        if (clipped) atomicAdd(g.clipped, 1ull);
+    }
+    /* episode-return summaries: warp shuffle -> shared -> one row per block (summed on the host in
+     * block order, so the result is deterministic).  This is the only cross-thread step of the path. */
+    __shared__ double sm[MBT_BLOCK / 32][MBT_SUMMARY_DOUBLES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int m = 0; m < MBT_SUMMARY_DOUBLES; ++m) {
+        double v = acc[m];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) sm[warp][m] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < MBT_SUMMARY_DOUBLES) {
+        double v = 0;
+        for (int w = 0; w < MBT_BLOCK / 32; ++w) v += sm[w][threadIdx.x];
+        g.block_sums[(long long)blockIdx.x * MBT_SUMMARY_DOUBLES + threadIdx.x] = v;
+    }
+}
+
+#endif /* MBT_KERNELS_CUH */

@@ -1,0 +1,205 @@
+/*
+ * mbt_step_core.cuh -- one env-step of ONE trajectory, state in registers.
+ *
+ * This is the arithmetic of the reference's TradingEnvironment.step() call tree
+ * (mbt_gym/gym/TradingEnvironment.py:103-110,198-220,283-297,323-327 and the model classes it calls)
+ * collapsed into a single function over scalars: no (N,2) temporaries, no state copies.  It is used by
+ * the step kernel (one call per launch) and by the fused rollout kernel (one call per time step, state
+ * never leaving registers).
+ *
+ * Exactness rules (DESIGN.md "Numerics"): the expression trees below are the reference's, operation
+ * for operation, so in float64 every intermediate rounds like numpy's.  The build uses -fmad=false; the
+ * only fused operations are the explicit fma() calls inside include/mbt_math.h.
+ *
+ * The `V` template argument fixes model kinds at compile time (V::dyn etc. >= 0) or leaves them to the
+ * runtime config (-1): the BASELINE configurations get specialised kernels, everything else the generic one.
+ */
+#ifndef MBT_STEP_CORE_CUH
+#define MBT_STEP_CORE_CUH
+
+#include "../../include/mbt_b200.h"
+#include "../../include/mbt_math.h"
+#include "../../include/mbt_philox.h"
+
+template <int DYN, int MID, int ARR, int IMP, int REW>
+struct Variant {
+    static constexpr int dyn = DYN, mid = MID, arr = ARR, imp = IMP, rew = REW;
+};
+using VariantGeneric = Variant<-1, -1, -1, -1, -1>;
+
+/* math dispatch on the arithmetic type */
+MBT_HD float mbt_exp_t(float x) { return mbt_exp_f32(x); }
+MBT_HD double mbt_exp_t(double x) { return mbt_exp_f64(x); }
+MBT_HD float mbt_pow_t(float x, float p) { return mbt_pow_f32(x, p); }
+MBT_HD double mbt_pow_t(double x, double p) { return mbt_pow_f64(x, p); }
+MBT_HD void mbt_normal_t(uint32_t bits, float *z) { *z = mbt_normal_from_bits_f32(bits); }
+MBT_HD void mbt_normal_t(uint32_t bits, double *z) { *z = mbt_normal_from_bits_f64(bits); }
+
+/*
+ * Uniform (per-launch) quantities, already in the arithmetic type T.  Built on the host by
+ * make_params() in mbt_capi.cu from mbt_config, forming each derived constant the way the reference's
+ * Python floats do (e.g. volatility * sqrt(step_size) in float64, then cast).
+ */
+template <typename T>
+struct StepParams {
+    /* model selectors (runtime copies; compile-time Variant wins when >= 0) */
+    int dyn, mid, arr, imp, rew;
+    int action_dim, obs_dim;
+    int normalise_action, normalise_obs, normalise_rewards;
+    int q0_per_traj; /* 1: read q0 column (random initial inventories), 0: q0_uniform */
+
+    T ep_len;    /* reward_function.episode_length = T - t0              RewardFunctions.py:73,112 */
+    T q0_uniform;
+    T qmax, cmax;
+
+    T p_arr[2];  /* Poisson: intensity*step_size ; NonLinear: 1-exp(-intensity*step_size) */
+    T arr_step, arr_rate[2], hawkes_speed, hawkes_jump;
+    T neg_kappa; /* -fill_exponent */
+    T drift_dt, vol_sqdt, sqdt, mid_drift, mid_vol, mid_step, ou_neg_speed, ou_level;
+    T imp_temp, imp_perm, imp_exp, imp_step, half_spread;
+    T phi, alpha, pexp, risk_aversion, reward_scaling;
+    T act_low[MBT_MAX_ACTION_DIM], act_grad[MBT_MAX_ACTION_DIM];
+    T obs_low[MBT_MAX_OBS_DIM], obs_grad[MBT_MAX_OBS_DIM];
+};
+
+/* The uniform clock of ONE step (every trajectory shares it, TradingEnvironment.py:216-220). */
+template <typename T>
+struct StepClock {
+    T t_next; /* time column after the step                           TradingEnvironment.py:216 */
+    T dt_r;   /* next[TIME] - current[TIME] as the rewards read it    RewardFunctions.py:58,99,131 */
+    int done; /* this step is the terminal one                        TradingEnvironment.py:218-220 */
+};
+
+/* Per-trajectory state carried between steps (the SoA columns of DESIGN.md "Layout"). */
+template <typename T>
+struct Traj {
+    T cash, inv, mid;
+    T x0, x1; /* Hawkes: (lambda_bid, lambda_ask);  Temp+Perm impact: x0 = accumulated permanent impact */
+};
+
+template <int CT>
+MBT_HD int pick(int runtime) { return CT >= 0 ? CT : runtime; }
+
+/* reward_function.calculate for one row; (c0,q0s,S0) = current_state, s = next_state. */
+template <typename T, class V>
+MBT_HD T reward_one(const StepParams<T> &p, const StepClock<T> &ck, T c0, T q_cur, T S0, const Traj<T> &s, const T *a, T q_init) {
+    const int rew = pick<V::rew>(p.rew);
+    T pnl = (s.cash + s.inv * s.mid) - (c0 + q_cur * S0); /* PnL  RewardFunctions.py:26-33 */
+    if (rew == MBT_REW_PNL) return pnl;
+    if (rew == MBT_REW_EXP_UTILITY) /* RewardFunctions.py:156-163 */
+        return ck.done ? -mbt_exp_t(-p.risk_aversion * (s.cash + s.inv * s.mid)) : (T)0;
+    T qp = mbt_pow_t(s.inv, p.pexp);
+    T base = pnl - (ck.dt_r * p.phi) * qp;
+    if (rew == MBT_REW_RUNNING_INVENTORY_PENALTY) /* RewardFunctions.py:128-138 */
+        return base - (p.alpha * (T)ck.done) * qp;
+    if (rew == MBT_REW_CJ_MM) /* RewardFunctions.py:96-109 */
+        return base - p.alpha * ((qp - mbt_pow_t(q_cur, p.pexp)) + (ck.dt_r / p.ep_len) * mbt_pow_t(q_init, p.pexp));
+    /* MBT_REW_CJ_OE  RewardFunctions.py:55-70 */
+    return base - (ck.dt_r * p.alpha) *
+                      ((p.pexp * a[0]) * mbt_pow_t(q_cur, p.pexp - (T)1) + mbt_pow_t(q_init, p.pexp) * p.ep_len);
+}
+
+/*
+ * Advance one trajectory by one step.
+ *   s       in/out  state
+ *   a       raw (de-normalised) action, p.action_dim values
+ *   r       the 128 random bits of this (trajectory, step)   include/mbt_philox.h draw contract
+ *   q_init  initial inventory of the episode (for CjMm / CjOe)
+ * returns the (scaled) reward; *clipped is set when inventory or cash hit their bounds.
+ */
+template <typename T, class V>
+MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, const T *a, mbt_u32x4 r, T q_init, int *clipped) {
+    const int dyn = pick<V::dyn>(p.dyn), mid = pick<V::mid>(p.mid), arr_kind = pick<V::arr>(p.arr),
+              imp = pick<V::imp>(p.imp);
+    const T c0 = s.cash, q_cur = s.inv, S = s.mid; /* current_state = state.copy()   TradingEnvironment.py:105 */
+    const T two_m24 = (T)5.9604644775390625e-08;
+    T arr_b = 0, arr_a = 0;
+
+    if (dyn != MBT_DYN_SPEED) {
+        /* get_arrivals_and_fills                                    ModelDynamics.py:127-131,169-172 */
+        T pb, pa;
+        if (arr_kind == MBT_ARR_HAWKES) { /* unif < lambda_t * step   arrival_models.py:121-123 */
+            pb = s.x0 * p.arr_step;
+            pa = s.x1 * p.arr_step;
+        } else { /* arrival_models.py:54-56,81-83 */
+            pb = p.p_arr[0];
+            pa = p.p_arr[1];
+        }
+        arr_b = ((T)mbt_uniform_bits24(r.x) * two_m24 < pb) ? (T)1 : (T)0;
+        arr_a = ((T)mbt_uniform_bits24(r.y) * two_m24 < pa) ? (T)1 : (T)0;
+        T fil_b, fil_a, off_b, off_a;
+        if (dyn == MBT_DYN_AT_TOUCH) { /* fills = action[:, 0:2]      ModelDynamics.py:157-158,171 */
+            fil_b = a[0];
+            fil_a = a[1];
+            off_b = p.half_spread;
+            off_a = p.half_spread;
+        } else { /* unif < exp(-kappa*depth)   fill_probability_models.py:28-34,57-58 */
+            fil_b = ((T)mbt_uniform_bits24(r.z) * two_m24 < mbt_exp_t(p.neg_kappa * a[0])) ? (T)1 : (T)0;
+            fil_a = ((T)mbt_uniform_bits24(r.w) * two_m24 < mbt_exp_t(p.neg_kappa * a[1])) ? (T)1 : (T)0;
+            off_b = a[0];
+            off_a = a[1];
+        }
+        /* _remove_max_inventory_fills, on the pre-step inventory     TradingEnvironment.py:146-152,323-327 */
+        fil_b = (q_cur >= p.qmax) ? (T)0 * fil_b : fil_b;
+        fil_a = (q_cur <= -p.qmax) ? (T)0 * fil_a : fil_a;
+        if (dyn == MBT_DYN_LIMIT_AND_MARKET) { /* market orders first   ModelDynamics.py:208-215 */
+            T mo_buy = (a[2] > (T)0.5) ? (T)1 : (T)0, mo_sell = (a[3] > (T)0.5) ? (T)1 : (T)0;
+            s.cash = s.cash + (mo_sell * (S - p.half_spread) - mo_buy * (S + p.half_spread));
+            s.inv = s.inv + (mo_buy - mo_sell);
+        }
+        /* update_state with fill_multiplier (-1,+1)                   ModelDynamics.py:71-73,108-116 */
+        T b = arr_b * fil_b, k = arr_a * fil_a;
+        s.inv = s.inv + (b - k);
+        s.cash = s.cash + (k * (S + off_a) - b * (S - off_b));
+    } else { /* TradinghWithSpeedModelDynamics.update_state            ModelDynamics.py:262-267 */
+        T nu = a[0];
+        T impact = (imp == MBT_IMP_TEMP_PERM) ? p.imp_temp * nu + s.x0              /* price_impact_models.py:91-92 */
+                                              : p.imp_temp * mbt_pow_t(nu, p.imp_exp); /* :55-56 */
+        T vol = nu * p.mid_step;
+        s.cash = s.cash - vol * (S + impact);
+        s.inv = s.inv + vol;
+    }
+    /* _clip_inventory_and_cash                                        TradingEnvironment.py:283-297 */
+    T qc = s.inv < -p.qmax ? -p.qmax : s.inv;
+    qc = qc > p.qmax ? p.qmax : qc;
+    T cc = s.cash < -p.cmax ? -p.cmax : s.cash;
+    cc = cc > p.cmax ? p.cmax : cc;
+    if (qc != s.inv || cc != s.cash) *clipped = 1;
+    s.inv = qc;
+    s.cash = cc;
+
+    /* _update_market_state: midprice, arrival, fill, impact            TradingEnvironment.py:206-211 */
+    if (mid != MBT_MID_CONSTANT) {
+        T z;
+        mbt_normal_t(mbt_normal_bits(r), &z);
+        if (mid == MBT_MID_BM) /* midprice_models.py:60-65 */
+            s.mid = (S + p.drift_dt) + p.vol_sqdt * z;
+        else if (mid == MBT_MID_GBM) /* midprice_models.py:97-105 */
+            s.mid = (S + (p.mid_drift * S) * p.mid_step) + (((p.mid_vol * S) * p.sqdt) * z);
+        else /* MBT_MID_OU  midprice_models.py:140-143: drift not scaled by dt, as written there */
+            s.mid = S + (p.ou_neg_speed * (S - p.ou_level) + p.vol_sqdt * z);
+    }
+    if (arr_kind == MBT_ARR_HAWKES) { /* arrival_models.py:110-119 (jump on arrival, not on fill) */
+        s.x0 = (s.x0 + ((p.hawkes_speed * (p.arr_rate[0] - s.x0)) * p.arr_step)) + p.hawkes_jump * arr_b;
+        s.x1 = (s.x1 + ((p.hawkes_speed * (p.arr_rate[1] - s.x1)) * p.arr_step)) + p.hawkes_jump * arr_a;
+    }
+    if (imp == MBT_IMP_TEMP_PERM) /* price_impact_models.py:88-89 */
+        s.x0 = s.x0 + (p.imp_perm * a[0]) * p.imp_step;
+
+    /* rewards = reward_function.calculate(current_state, action, next_state, dones[0])   :108 */
+    T rwd = reward_one<T, V>(p, ck, c0, q_cur, S, s, a, q_init);
+    return p.normalise_rewards ? p.reward_scaling * rwd : rwd; /* :128-129 */
+}
+
+/* normalise_action(inverse=True)                                       TradingEnvironment.py:120-126 */
+template <typename T>
+MBT_HD T denorm_action(const StepParams<T> &p, T x, int j) {
+    return p.normalise_action ? (x + (T)1) * p.act_grad[j] + p.act_low[j] : x;
+}
+/* normalise_observation                                                 TradingEnvironment.py:112-118 */
+template <typename T>
+MBT_HD T norm_obs(const StepParams<T> &p, T x, int d) {
+    return p.normalise_obs ? (x - p.obs_low[d]) / p.obs_grad[d] - (T)1 : x;
+}
+
+#endif /* MBT_STEP_CORE_CUH */

@@ -1,0 +1,78 @@
+/*
+ * hostsim.cpp -- TEST-ONLY host compile of the kernel's per-trajectory core (mbt_step_core.cuh).
+ *
+ * The build container has no GPU; compiling step_one<T,V>() for the host lets tests/test_hostsim.py check
+ * the exact expression trees the kernels execute against the oracle before any GPU time is spent.  This is
+ * NOT a CPU path of the product: it lives under tests/, is built only by the test, and nothing in
+ * mbt_gym_b200/ can reach it.
+ */
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../mbt_gym_b200/csrc/mbt_host_params.h"
+
+using VariantAS = Variant<MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, -1>;
+using VariantHawkes = Variant<MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, -1>;
+using VariantOE = Variant<MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, -1>;
+
+template <typename T, class V>
+static void run(const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, double t_start, int q0_per_traj,
+                double q0_uniform, T *state, const T *q0, int steps, const T *actions, T *obs, T *rew,
+                uint8_t *dones) {
+    int32_t A, D, S;
+    mbt_dims(&c, &A, &D, &S);
+    const int64_t N = c.num_trajectories;
+    StepParams<T> p = mbt_make_params<T>(c, t0, q0_per_traj, q0_uniform);
+    double t = t_start;
+    for (int k = 0; k < steps; ++k) {
+        const double t_next = t + c.step_size;
+        StepClock<T> ck = mbt_make_clock<T>(c, t, t_next);
+        for (int64_t i = 0; i < N; ++i) {
+            T *row = state + i * D;
+            Traj<T> s;
+            s.cash = row[0]; s.inv = row[1]; s.mid = row[3]; s.x0 = 0; s.x1 = 0;
+            if (c.arrival == MBT_ARR_HAWKES) { s.x0 = row[4]; s.x1 = row[5]; }
+            if (c.impact == MBT_IMP_TEMP_PERM) s.x0 = row[4];
+            T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
+            for (int j = 0; j < A; ++j) a[j] = denorm_action(p, actions[((int64_t)k * N + i) * A + j], j);
+            mbt_u32x4 r = mbt_draw(seed, (uint64_t)(c.traj_offset + i), (uint64_t)(n_step0 + k), MBT_STREAM_STEP);
+            int clipped = 0;
+            T rw = step_one<T, V>(p, ck, s, a, r, q0_per_traj ? q0[i] : (T)q0_uniform, &clipped);
+            row[0] = s.cash; row[1] = s.inv; row[2] = ck.t_next; row[3] = s.mid;
+            if (c.arrival == MBT_ARR_HAWKES) { row[4] = s.x0; row[5] = s.x1; }
+            if (c.impact == MBT_IMP_TEMP_PERM) row[4] = s.x0;
+            for (int d = 0; d < D; ++d) obs[((int64_t)k * N + i) * D + d] = norm_obs(p, row[d], d);
+            rew[(int64_t)k * N + i] = rw;
+        }
+        dones[k] = (uint8_t)ck.done;
+        t = t_next;
+    }
+}
+
+template <typename T>
+static void dispatch(int variant, const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, double t_start,
+                     int q0_per_traj, double q0_uniform, void *state, const void *q0, int steps, const void *actions,
+                     void *obs, void *rew, uint8_t *dones) {
+#define GO(V) run<T, V>(c, seed, n_step0, t0, t_start, q0_per_traj, q0_uniform, (T *)state, (const T *)q0, steps, (const T *)actions, (T *)obs, (T *)rew, dones)
+    switch (variant) {
+    case 1: GO(VariantAS); break;
+    case 2: GO(VariantHawkes); break;
+    case 3: GO(VariantOE); break;
+    default: GO(VariantGeneric); break;
+    }
+#undef GO
+}
+
+extern "C" int hostsim_run(const mbt_config *c, int variant, uint64_t seed, int64_t n_step0, double t0, double t_start,
+                           int q0_per_traj, double q0_uniform, void *state, const void *q0, int steps,
+                           const void *actions, void *obs, void *rew, uint8_t *dones) {
+    std::string err;
+    int rc = mbt_validate_config(c, err);
+    if (rc) return rc;
+    if (c->precision == MBT_F64)
+        dispatch<double>(variant, *c, seed, n_step0, t0, t_start, q0_per_traj, q0_uniform, state, q0, steps, actions, obs, rew, dones);
+    else
+        dispatch<float>(variant, *c, seed, n_step0, t0, t_start, q0_per_traj, q0_uniform, state, q0, steps, actions, obs, rew, dones);
+    return 0;
+}

@@ -1,0 +1,278 @@
+"""GPU parity (-m gpu): the CUDA kernels, called through the C ABI, against
+  (a) the committed REFERENCE fixtures (tests/golden, float64, bit-for-bit),
+  (b) the CPU oracle on the same seeds (float32 bit-for-bit; float64 again),
+  (c) size-independent properties at BASELINE.json's full size (2^20 trajectories).
+
+Tolerances: float64 and float32 are compared BIT-EXACT (`np.array_equal`), except the two fixtures that reach
+libm pow/exp in the reference (`rip_cubic`, `exputil`), compared at rtol=atol=1e-11.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from mbt_gym_b200 import _abi, _lib
+from oracle import oracle as O
+from tests.helpers import Golden, assert_same, copy_config, golden_names
+
+pytestmark = pytest.mark.gpu
+
+
+def run_native(g, precision, mem="host", n_shards=1):
+    """Step the fixture's action sequence through libmbt_b200; returns (reset_obs, obs, rew, done, final_state)."""
+    dt = np.float64 if precision == _abi.MBT_F64 else np.float32
+    N_total = int(g.cfg.num_trajectories)
+    bounds = np.linspace(0, N_total, n_shards + 1).astype(int)
+    envs = []
+    for s in range(n_shards):
+        cfg = g.config(precision, num_trajectories=int(bounds[s + 1] - bounds[s]), traj_offset=int(bounds[s]))
+        e = _lib.NativeEnv(cfg)
+        e.seed(g.seed)
+        envs.append(e)
+    A, D = envs[0].A, envs[0].D
+    spe = g.steps_per_episode
+    reset_obs, obs_all, rew_all, done_all = [], [], [], []
+    if mem == "device":
+        import torch
+    for ep in range(g.n_episodes):
+        ro = np.empty((N_total, D), dt)
+        for s, e in enumerate(envs):
+            sl = slice(bounds[s], bounds[s + 1])
+            buf = np.empty((e.N, D), dt)
+            e.reset(buf)
+            ro[sl] = buf
+        reset_obs.append(ro)
+        for k in range(ep * spe, (ep + 1) * spe):
+            o = np.empty((N_total, D), dt)
+            r = np.empty((N_total,), dt)
+            dones = []
+            for s, e in enumerate(envs):
+                sl = slice(bounds[s], bounds[s + 1])
+                a = np.ascontiguousarray(g.actions[k, sl], dtype=dt)
+                if mem == "host":
+                    ob = np.empty((e.N, D), dt)
+                    rb = np.empty((e.N,), dt)
+                    dones.append(e.step(a, ob, rb))
+                else:
+                    tdt = torch.float64 if precision == _abi.MBT_F64 else torch.float32
+                    ta = torch.from_numpy(a).cuda()
+                    to = torch.empty((e.N, D), dtype=tdt, device="cuda")
+                    tr = torch.empty((e.N,), dtype=tdt, device="cuda")
+                    torch.cuda.synchronize()
+                    dones.append(e.step(ta, to, tr, mem=_abi.MBT_MEM_DEVICE))
+                    e.sync()
+                    ob, rb = to.cpu().numpy(), tr.cpu().numpy()
+                o[sl], r[sl] = ob, rb
+            assert len(set(dones)) == 1
+            obs_all.append(o); rew_all.append(r); done_all.append(dones[0])
+    final = np.concatenate([e.get_state() for e in envs])
+    for e in envs:
+        e.close()
+    return np.stack(reset_obs), np.stack(obs_all), np.stack(rew_all), np.array(done_all), final
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_f64_matches_reference_fixture(name):
+    g = Golden(name)
+    reset_obs, obs, rew, done, final = run_native(g, _abi.MBT_F64)
+    assert_same(reset_obs, g.reset_obs, exact=True, what=f"{name} reset obs")
+    assert_same(obs, g.obs, exact=g.exact, what=f"{name} obs")
+    assert_same(rew, g.rew, exact=g.exact, what=f"{name} rewards")
+    assert np.array_equal(done, g.done)
+    assert_same(final, g.final_state, exact=g.exact, what=f"{name} final state")
+
+
+def oracle_run(g, precision):
+    cfg = g.config(precision)
+    orc = O.OracleEnv(cfg)
+    orc.seed(g.seed)
+    spe = g.steps_per_episode
+    reset_obs, obs, rew, done = [], [], [], []
+    for ep in range(g.n_episodes):
+        reset_obs.append(orc.reset())
+        for k in range(ep * spe, (ep + 1) * spe):
+            o, r, d = orc.step(g.actions[k])
+            obs.append(o); rew.append(r); done.append(d)
+    return np.stack(reset_obs), np.stack(obs), np.stack(rew), np.array(done), orc.state
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_f32_matches_oracle_bitwise(name):
+    g = Golden(name)
+    got = run_native(g, _abi.MBT_F32)
+    want = oracle_run(g, _abi.MBT_F32)
+    for a, b, what in zip(got, want, ("reset obs", "obs", "rewards", "done", "final state")):
+        assert_same(a, b, exact=True, what=f"{name} f32 {what}")
+
+
+@pytest.mark.parametrize("name", ["as_pnl", "hawkes_normalised", "oe_ou_cjoe", "limit_and_market"])
+@pytest.mark.parametrize("precision", [_abi.MBT_F64, _abi.MBT_F32])
+def test_device_pointer_mode_equals_host_mode(name, precision):
+    g = Golden(name)
+    host = run_native(g, precision, mem="host")
+    dev = run_native(g, precision, mem="device")
+    for a, b, what in zip(host, dev, ("reset obs", "obs", "rewards", "done", "final state")):
+        assert_same(a, b, exact=True, what=f"{name} {what}")
+
+
+@pytest.mark.parametrize("name", ["as_pnl", "cjmm", "hawkes_pnl", "oe_ou_cjoe", "two_episodes"])
+def test_results_do_not_depend_on_sharding(name):
+    """Global trajectory ids in the Philox counter: 1, 2 or 3 handles give the same trajectories."""
+    g = Golden(name)
+    one = run_native(g, _abi.MBT_F64, n_shards=1)
+    for shards in (2, 3):
+        many = run_native(g, _abi.MBT_F64, n_shards=shards)
+        for a, b, what in zip(one, many, ("reset obs", "obs", "rewards", "done", "final state")):
+            assert_same(a, b, exact=True, what=f"{name} shards={shards} {what}")
+
+
+def test_edge_sizes_and_errors():
+    g = Golden("as_pnl")
+    for n in (1, 2, 31, 33, 255, 257):
+        cfg = g.config(_abi.MBT_F64, num_trajectories=n)
+        e = _lib.NativeEnv(cfg)
+        e.seed(3)
+        orc = O.OracleEnv(cfg)
+        orc.seed(3)
+        ob = np.empty((n, 4)); rb = np.empty((n,))
+        e.reset(ob)
+        assert_same(ob, orc.reset(), what=f"n={n} reset")
+        a = np.full((n, 2), 0.7)
+        for _ in range(3):
+            e.step(a, ob, rb)
+            o, r, _d = orc.step(a)
+            assert_same(ob, o, what=f"n={n} obs"); assert_same(rb, r, what=f"n={n} rew")
+        e.close()
+    # step before reset -> MBT_E_STATE ; bad config -> MBT_E_INVALID_ARG / UNSUPPORTED
+    e = _lib.NativeEnv(g.config(_abi.MBT_F64))
+    with pytest.raises(_lib.MbtError) as ei:
+        e.step(np.zeros((e.N, 2)))
+    assert ei.value.code == _abi.MBT_E_STATE
+    e.close()
+    with pytest.raises(_lib.MbtError) as ei:
+        _lib.NativeEnv(g.config(_abi.MBT_F64, num_trajectories=0))
+    assert ei.value.code == _abi.MBT_E_INVALID_ARG
+    with pytest.raises(_lib.MbtError) as ei:
+        _lib.NativeEnv(g.config(_abi.MBT_F64, dynamics=17))
+    assert ei.value.code == _abi.MBT_E_UNSUPPORTED
+
+
+def test_set_get_state_roundtrip_and_unaligned_buffers():
+    g = Golden("hawkes_pnl")
+    e = _lib.NativeEnv(g.config(_abi.MBT_F64))
+    e.seed(9)
+    e.reset()
+    rng = np.random.default_rng(0)
+    st = rng.normal(size=(e.N, e.D))
+    st[:, 2] = 0.25
+    e.set_state(st)
+    assert_same(e.get_state(), st, what="state roundtrip")
+    assert e.clock()["time"] == 0.25
+    # deliberately misaligned host views (offset by one element) must still be handled
+    big_a = np.zeros(e.N * e.A + 1); big_o = np.zeros(e.N * e.D + 1); big_r = np.zeros(e.N + 1)
+    a = big_a[1:].reshape(e.N, e.A); a[:] = 0.5
+    ob = big_o[1:].reshape(e.N, e.D); rb = big_r[1:]
+    e.step(a, ob, rb)
+    e2 = _lib.NativeEnv(g.config(_abi.MBT_F64))
+    e2.seed(9); e2.reset(); e2.set_state(st)
+    ob2 = np.empty((e.N, e.D)); rb2 = np.empty(e.N)
+    e2.step(np.full((e.N, e.A), 0.5), ob2, rb2)
+    assert_same(ob, ob2, what="misaligned obs"); assert_same(rb, rb2, what="misaligned rew")
+    e.close(); e2.close()
+
+
+# --------------------------------------------------------------------------- fused rollout
+def as_policy_numpy(state, gamma, sigma, kappa, T, dtype):
+    """AvellanedaStoikovAgent.get_action (BaselineAgents.py:62-83), same evaluation order as the kernel."""
+    q = state[:, 1].astype(dtype)
+    t = state[:, 2].astype(dtype)
+    g, s2 = dtype(gamma), dtype(sigma ** 2)
+    fill = dtype(2 / gamma * np.log(1 + gamma / kappa))
+    tau = dtype(T) - t
+    adj = ((q * g) * s2) * tau
+    spread = (g * s2) * tau + fill
+    return np.stack([adj + spread / dtype(2), -adj + spread / dtype(2)], axis=1)
+
+
+@pytest.mark.parametrize("precision", [_abi.MBT_F64, _abi.MBT_F32])
+def test_fused_rollout_matches_stepwise_oracle(precision):
+    g = Golden("as_pnl")
+    dt = np.float64 if precision == _abi.MBT_F64 else np.float32
+    cfg = g.config(precision, num_trajectories=1000)
+    gamma = 0.1
+    e = _lib.NativeEnv(cfg)
+    e.seed(50)
+    e.reset()
+    pol = _abi.mbt_policy()
+    pol.kind = _abi.MBT_POL_AVELLANEDA_STOIKOV
+    pol.as_gamma, pol.as_sigma_sq = gamma, cfg.mid_vol ** 2
+    pol.as_fill_comp = 2 / gamma * np.log(1 + gamma / cfg.fill_exponent)
+    pol.as_terminal_time = cfg.terminal_time
+    ret = np.empty(e.N, dt); qT = np.empty(e.N, dt)
+    summ = e.rollout(pol, ret, qT)
+    # oracle, stepped with the numpy policy, returns accumulated sequentially like the kernel does
+    orc = O.OracleEnv(cfg)
+    orc.seed(50)
+    orc.reset()
+    R = np.zeros(e.N, dt); act_sum = 0.0; r2 = 0.0
+    done = False
+    steps = 0
+    while not done:
+        a = as_policy_numpy(orc.state, gamma, cfg.mid_vol, cfg.fill_exponent, cfg.terminal_time, dt)
+        act_sum += float(a.astype(np.float64).sum())
+        _o, r, done = orc.step(a)
+        R = R + r
+        r2 += float((r.astype(np.float64) ** 2).sum())
+        steps += 1
+    assert summ.steps == steps == cfg.n_steps
+    assert_same(ret, R, exact=True, what="per-trajectory returns")
+    assert_same(qT, orc.state[:, 1], exact=True, what="terminal inventories")
+    assert_same(e.get_state(), orc.state, exact=True, what="terminal state")
+    R64 = R.astype(np.float64); q64 = orc.state[:, 1].astype(np.float64)
+    np.testing.assert_allclose(summ.sum_return, R64.sum(), rtol=1e-12)
+    np.testing.assert_allclose(summ.sum_return_sq, (R64 ** 2).sum(), rtol=1e-12)
+    np.testing.assert_allclose(summ.sum_q, q64.sum(), rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(summ.sum_q_sq, (q64 ** 2).sum(), rtol=1e-12)
+    np.testing.assert_allclose(summ.sum_action, act_sum, rtol=1e-9)
+    np.testing.assert_allclose(summ.sum_reward_sq, r2, rtol=1e-9)
+    e.close()
+
+
+# --------------------------------------------------------------------------- full size (BASELINE configs[1])
+def test_full_size_properties_2pow20():
+    """N = 2^20: determinism, sharding invariance on a slice, and the AS-2008 statistics of the reference notebook
+    (Test_1: mean PnL 64.872, std 6.69, mean q_T 0.201, std q_T 2.89 at N=1000, seed 50) within 4 standard errors."""
+    g = Golden("as_pnl")
+    N = 1 << 20
+    cfg = g.config(_abi.MBT_F64, num_trajectories=N)
+    gamma = 0.1
+    pol = _abi.mbt_policy()
+    pol.kind = _abi.MBT_POL_AVELLANEDA_STOIKOV
+    pol.as_gamma, pol.as_sigma_sq = gamma, cfg.mid_vol ** 2
+    pol.as_fill_comp = 2 / gamma * np.log(1 + gamma / cfg.fill_exponent)
+    pol.as_terminal_time = cfg.terminal_time
+
+    def run(cfg_):
+        e = _lib.NativeEnv(cfg_)
+        e.seed(50)
+        e.reset()
+        ret = np.empty(e.N); qT = np.empty(e.N)
+        s = e.rollout(pol, ret, qT)
+        e.close()
+        return ret, qT, s
+
+    ret, qT, s = run(cfg)
+    ret2, qT2, _ = run(cfg)
+    assert np.array_equal(ret, ret2) and np.array_equal(qT, qT2), "same seed must give identical trajectories"
+    # a shard holding global ids [N/2, N/2 + 4096) reproduces that slice
+    part = g.config(_abi.MBT_F64, num_trajectories=4096, traj_offset=N // 2)
+    ret3, qT3, _ = run(part)
+    assert np.array_equal(ret3, ret[N // 2:N // 2 + 4096]) and np.array_equal(qT3, qT[N // 2:N // 2 + 4096])
+    # statistics vs the reference notebook goldens (SE of the notebook's N=1000 sample dominates)
+    mean_pnl, std_pnl = ret.mean(), ret.std()
+    assert abs(mean_pnl - 64.872139) < 4 * 6.692567 / np.sqrt(1000)
+    assert abs(std_pnl - 6.692567) < 4 * 6.692567 / np.sqrt(2 * 1000)
+    assert abs(qT.mean() - 0.201) < 4 * 2.893544 / np.sqrt(1000)
+    assert abs(qT.std() - 2.893544) < 4 * 2.893544 / np.sqrt(2 * 1000)
+    np.testing.assert_allclose(s.sum_return / N, mean_pnl, rtol=1e-10)
+    assert np.all(qT == np.round(qT))

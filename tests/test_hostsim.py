@@ -1,0 +1,92 @@
+"""The kernels' per-trajectory core (mbt_gym_b200/csrc/mbt_step_core.cuh), compiled for the HOST by this test,
+must reproduce the reference fixtures bit-for-bit in float64 and the oracle bit-for-bit in float32.
+
+This is a build-container safety net (no GPU here); the same comparison through the real CUDA kernels and the
+C ABI is tests/test_gpu_parity.py.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from mbt_gym_b200 import _abi
+from oracle import oracle as O
+from tests.helpers import Golden, ROOT, assert_same, golden_names
+
+SRC = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+SO = os.path.join(ROOT, "tests", "hostsim", "_build", "libhostsim.so")
+
+
+@pytest.fixture(scope="module")
+def hostsim():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-march=x86-64-v3", "-x", "c++",
+                    SRC, "-o", SO], check=True)
+    lib = C.CDLL(SO)
+    vp = C.c_void_p
+    lib.hostsim_run.argtypes = [C.POINTER(_abi.mbt_config), C.c_int, C.c_uint64, C.c_int64, C.c_double, C.c_double,
+                                C.c_int, C.c_double, vp, vp, C.c_int, vp, vp, vp, vp]
+    return lib
+
+
+def variant_of(cfg):
+    if cfg.dynamics == _abi.MBT_DYN_LIMIT and cfg.midprice == _abi.MBT_MID_BM and cfg.impact == _abi.MBT_IMP_NONE:
+        if cfg.arrival == _abi.MBT_ARR_POISSON:
+            return 1
+        if cfg.arrival == _abi.MBT_ARR_HAWKES:
+            return 2
+    if (cfg.dynamics == _abi.MBT_DYN_SPEED and cfg.midprice == _abi.MBT_MID_OU and cfg.impact == _abi.MBT_IMP_TEMP_PERM
+            and cfg.arrival == _abi.MBT_ARR_NONE):
+        return 3
+    return 0
+
+
+def run_hostsim(lib, g, precision, variant):
+    """Oracle does the resets (state injection), the host-compiled kernel core does the steps."""
+    cfg = g.config(precision)
+    dt = np.float64 if precision == _abi.MBT_F64 else np.float32
+    orc = O.OracleEnv(cfg)
+    orc.seed(g.seed)
+    N, A, D = orc.N, orc.A, orc.D
+    spe = g.steps_per_episode
+    obs_all, rew_all, done_all, oobs_all, orew_all = [], [], [], [], []
+    for ep in range(g.n_episodes):
+        orc.reset()
+        state = orc.state.copy()
+        q0 = np.ascontiguousarray(state[:, 1].copy())
+        acts = np.ascontiguousarray(g.actions[ep * spe:(ep + 1) * spe], dtype=dt)
+        obs = np.empty((spe, N, D), dt)
+        rew = np.empty((spe, N), dt)
+        dones = np.zeros(spe, np.uint8)
+        per_traj = int(cfg.q0_mode == _abi.MBT_Q0_UNIFORM_INT)
+        rc = lib.hostsim_run(C.byref(cfg), variant, g.seed, ep * spe, cfg.start_time, cfg.start_time, per_traj,
+                             cfg.q0_const, state.ctypes.data, q0.ctypes.data, spe, acts.ctypes.data, obs.ctypes.data,
+                             rew.ctypes.data, dones.ctypes.data)
+        assert rc == 0
+        obs_all.append(obs); rew_all.append(rew); done_all.append(dones.astype(bool))
+        for k in range(spe):  # advance the oracle in lock-step (also gives the f32 comparison target)
+            o, r, _ = orc.step(acts[k])
+            oobs_all.append(o); orew_all.append(r)
+    return (np.concatenate(obs_all), np.concatenate(rew_all), np.concatenate(done_all), np.stack(oobs_all),
+            np.stack(orew_all))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_kernel_core_f64_matches_reference_fixture(hostsim, name):
+    g = Golden(name)
+    for variant in sorted({0, variant_of(g.cfg)}):
+        obs, rew, done, _, _ = run_hostsim(hostsim, g, _abi.MBT_F64, variant)
+        assert_same(obs, g.obs, exact=g.exact, what=f"{name} obs (variant {variant})")
+        assert_same(rew, g.rew, exact=g.exact, what=f"{name} rew (variant {variant})")
+        assert np.array_equal(done, g.done)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_kernel_core_f32_matches_oracle_f32(hostsim, name):
+    g = Golden(name)
+    for variant in sorted({0, variant_of(g.cfg)}):
+        obs, rew, done, oobs, orew = run_hostsim(hostsim, g, _abi.MBT_F32, variant)
+        assert_same(obs, oobs, exact=True, what=f"{name} f32 obs (variant {variant})")
+        assert_same(rew, orew, exact=True, what=f"{name} f32 rew (variant {variant})")
