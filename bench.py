@@ -215,7 +215,8 @@ def main():
     env = _lib.NativeEnv(cfg, device=local_rank)
     N, A, D = env.N, env.A, env.D
     env.seed(1234)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-default) stream: the env's kernels and the timing events share it
+    torch.cuda.set_stream(stream)
     env.set_stream(stream.cuda_stream)
 
     # rotating buffer sets so that the bytes touched between two uses of a buffer exceed L2 (126 MB)
@@ -258,6 +259,7 @@ def main():
     ktimes = env.kernel_times_ms()
     env.enable_timing(False)
 
+    env.set_stream(None)  # back to the handle's own stream for the host-buffer path
     # ---- e2e: host buffers through the call a user makes (pinned action array in, pinned obs/rew out)
     e2e_steps = args.e2e_steps or max(10, min(args.steps, 50))
     h_act = _lib.PinnedArray((N, A), env.dtype)

@@ -224,7 +224,10 @@ int mbt_config_dims(const mbt_config *cfg, int32_t *action_dim, int32_t *obs_dim
 int mbt_create(const mbt_config *cfg, int device, mbt_env **out);
 int mbt_destroy(mbt_env *env);
 
-/* Use an external stream (e.g. torch's current stream) for all subsequent work; NULL = own stream. */
+/* Use an external stream for all subsequent work.  The value is a cudaStream_t taken literally, so NULL is the
+ * CUDA legacy default stream (what torch's default stream is); MBT_OWN_STREAM switches back to the handle's own
+ * non-blocking stream (the initial state). */
+#define MBT_OWN_STREAM ((void *)(intptr_t)-1)
 int mbt_set_stream(mbt_env *env, void *cuda_stream);
 int mbt_sync(mbt_env *env);
 

@@ -150,7 +150,8 @@ class NativeEnv:
         _check(load().mbt_sync(self._h))
 
     def set_stream(self, stream_ptr):
-        _check(load().mbt_set_stream(self._h, C.c_void_p(stream_ptr or 0)))
+        """cudaStream_t as an int (0 = legacy default stream, torch's default); None = the handle's own stream."""
+        _check(load().mbt_set_stream(self._h, C.c_void_p(-1 if stream_ptr is None else int(stream_ptr))))
 
     # -- hot path
     def reset(self, obs_out=None, args=None, mem=_abi.MBT_MEM_HOST):

@@ -365,7 +365,7 @@ int mbt_set_stream(mbt_env *e, void *cuda_stream) {
     if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
-    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    e->stream = cuda_stream == MBT_OWN_STREAM ? e->own_stream : (cudaStream_t)cuda_stream;
     return MBT_OK;
 }
 

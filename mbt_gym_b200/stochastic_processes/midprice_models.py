@@ -1,0 +1,84 @@
+"""Midprice model descriptors (reference: mbt_gym/stochastic_processes/midprice_models.py).
+
+Supported on the device: Constant (:12-33), BrownianMotion (:36-68), GeometricBrownianMotion (:71-111), Ou (:114-146).
+The reference's alpha / jump / Heston / CEV models are outside the BASELINE hot path --
+several of them do not run for num_trajectories > 1 in the reference itself.
+"""
+from math import sqrt
+
+import numpy as np
+
+from .. import _abi
+from .StochasticProcessModel import StochasticProcessModel
+
+MidpriceModel = StochasticProcessModel
+
+
+class _SymmetricBoundsMidprice(StochasticProcessModel):
+    """Common ctor: observation bounds are initial_price -/+ (max - initial_price)."""
+
+    def _finish(self, initial_price, terminal_time, step_size, num_trajectories, seed):
+        hi = self._get_max_value(initial_price, terminal_time)
+        super().__init__([[initial_price - (hi - initial_price)]], [[hi]], step_size, terminal_time, [[initial_price]],
+                         num_trajectories, seed)
+
+    def _flatten(self, cfg):
+        cfg.midprice = self.KIND
+        cfg.mid_initial = float(self.initial_state[0, 0])
+        cfg.mid_step = float(self.step_size)
+        cfg.mid_drift = float(getattr(self, "drift", 0.0))
+        cfg.mid_vol = float(getattr(self, "volatility", 0.0))
+        cfg.ou_level = float(getattr(self, "mean_reversion_level", 0.0))
+        cfg.ou_speed = float(getattr(self, "mean_reversion_speed", 0.0))
+
+
+class ConstantMidpriceModel(_SymmetricBoundsMidprice):
+    KIND = _abi.MBT_MID_CONSTANT
+
+    def __init__(self, initial_price=100, terminal_time=1.0, step_size=0.01, num_trajectories=1, seed=None):
+        self._finish(initial_price, terminal_time, step_size, num_trajectories, seed)
+
+    def _get_max_value(self, initial_price, terminal_time):
+        return initial_price
+
+
+class BrownianMotionMidpriceModel(_SymmetricBoundsMidprice):
+    """dS = drift dt + volatility dW; bounds S0 +/- 4 volatility sqrt(T)."""
+    KIND = _abi.MBT_MID_BM
+
+    def __init__(self, drift=0.0, volatility=2.0, initial_price=100, terminal_time=1.0, step_size=0.01,
+                 num_trajectories=1, seed=None):
+        self.drift, self.volatility = drift, volatility
+        self._finish(initial_price, terminal_time, step_size, num_trajectories, seed)
+
+    def _get_max_value(self, initial_price, terminal_time):
+        return initial_price + 4 * self.volatility * np.sqrt(terminal_time)
+
+
+class GeometricBrownianMotionMidpriceModel(_SymmetricBoundsMidprice):
+    """dS = drift S dt + volatility S dW; bounds mean + 4 standard deviations of S_T."""
+    KIND = _abi.MBT_MID_GBM
+
+    def __init__(self, drift=0.0, volatility=0.1, initial_price=100, terminal_time=1.0, step_size=0.01,
+                 num_trajectories=1, seed=None):
+        self.drift, self.volatility = drift, volatility
+        self._finish(initial_price, terminal_time, step_size, num_trajectories, seed)
+
+    def _get_max_value(self, initial_price, terminal_time):
+        var = initial_price ** 2 * np.exp(2 * self.drift * terminal_time) * (np.exp(self.volatility ** 2 * terminal_time) - 1)
+        return initial_price * np.exp(self.drift * terminal_time) + 4 * sqrt(var)
+
+
+class OuMidpriceModel(_SymmetricBoundsMidprice):
+    """Ornstein-Uhlenbeck midprice.  NB the reference's Euler step adds -speed*(S-level) WITHOUT a dt factor
+    (midprice_models.py:140-143); the kernel reproduces that literally."""
+    KIND = _abi.MBT_MID_OU
+
+    def __init__(self, mean_reversion_level=0.0, mean_reversion_speed=1.0, volatility=2.0, initial_price=100.0,
+                 terminal_time=1.0, step_size=0.01, num_trajectories=1, seed=None):
+        self.mean_reversion_level, self.mean_reversion_speed, self.volatility = (mean_reversion_level,
+                                                                                 mean_reversion_speed, volatility)
+        self._finish(initial_price, terminal_time, step_size, num_trajectories, seed)
+
+    def _get_max_value(self, initial_price, terminal_time):
+        return initial_price + 4 * self.volatility * terminal_time

@@ -70,3 +70,76 @@ def assert_same(a, b, exact=True, rtol=1e-11, atol=1e-11, what=""):
             raise AssertionError(f"{what}: {len(bad)} of {a.size} values differ; first at {i}: {a[i]!r} vs {b[i]!r}")
     else:
         np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=what)
+
+
+def build_facade_env(spec, **extra):
+    """The mbt_gym_b200 environment for a fixture spec, built with the same keyword arguments the reference takes
+    (mirror of oracle/ref_shim.build_reference_env)."""
+    from mbt_gym_b200.gym import ModelDynamics as MD
+    from mbt_gym_b200.gym.TradingEnvironment import TradingEnvironment
+    from mbt_gym_b200.rewards import RewardFunctions as RF
+    from mbt_gym_b200.stochastic_processes import arrival_models as AM, fill_probability_models as FM
+    from mbt_gym_b200.stochastic_processes import midprice_models as MM, price_impact_models as PM
+
+    N, n_steps, T = spec["N"], spec["n_steps"], spec["terminal_time"]
+    dt = T / n_steps
+    m = spec["midprice"]
+    kw = dict(initial_price=m["initial_price"], terminal_time=T, step_size=dt, num_trajectories=N)
+    if m["kind"] == "bm":
+        mid = MM.BrownianMotionMidpriceModel(drift=m.get("drift", 0.0), volatility=m["volatility"], **kw)
+    elif m["kind"] == "gbm":
+        mid = MM.GeometricBrownianMotionMidpriceModel(drift=m.get("drift", 0.0), volatility=m["volatility"], **kw)
+    elif m["kind"] == "ou":
+        mid = MM.OuMidpriceModel(mean_reversion_level=m["level"], mean_reversion_speed=m["speed"],
+                                 volatility=m["volatility"], **kw)
+    else:
+        mid = MM.ConstantMidpriceModel(**kw)
+    arr = fill = imp = None
+    a = spec.get("arrival")
+    if a:
+        if a["kind"] == "poisson":
+            arr = AM.PoissonArrivalModel(intensity=np.array(a["intensity"], float), step_size=dt, num_trajectories=N)
+        elif a["kind"] == "poisson_nonlinear":
+            arr = AM.PoissonArrivalNonLinearModel(intensity=np.array(a["intensity"], float), step_size=dt, num_trajectories=N)
+        else:
+            arr = AM.HawkesArrivalModel(baseline_arrival_rate=np.array([a["baseline"]], float), step_size=dt,
+                                        jump_size=a["jump"], mean_reversion_speed=a["speed"], terminal_time=T,
+                                        num_trajectories=N)
+    if spec.get("fill"):
+        fill = FM.ExponentialFillFunction(fill_exponent=spec["fill"]["fill_exponent"], step_size=dt, num_trajectories=N)
+    p = spec.get("impact")
+    if p:
+        if p["kind"] == "temp_perm":
+            imp = PM.TemporaryAndPermanentPriceImpact(temporary_impact_coefficient=p["temp"],
+                                                      permanent_impact_coefficient=p["perm"], n_steps=n_steps,
+                                                      terminal_time=T, num_trajectories=N)
+        else:
+            imp = PM.TemporaryPowerPriceImpact(temporary_impact_coefficient=p["temp"],
+                                               temporary_impact_exponent=p["exponent"], num_trajectories=N)
+    kind = spec["dynamics"]
+    if kind == "limit":
+        dyn = MD.LimitOrderModelDynamics(midprice_model=mid, arrival_model=arr, fill_probability_model=fill, num_trajectories=N)
+    elif kind == "touch":
+        dyn = MD.AtTheTouchModelDynamics(midprice_model=mid, arrival_model=arr, num_trajectories=N,
+                                         fixed_market_half_spread=spec.get("half_spread", 0.5))
+    elif kind == "limit_and_market":
+        dyn = MD.LimitAndMarketOrderModelDynamics(midprice_model=mid, arrival_model=arr, fill_probability_model=fill,
+                                                  num_trajectories=N, fixed_market_half_spread=spec.get("half_spread", 0.5))
+    else:
+        dyn = MD.TradinghWithSpeedModelDynamics(midprice_model=mid, price_impact_model=imp, num_trajectories=N)
+    r = spec["reward"]
+    rew = {"pnl": lambda: RF.PnL(),
+           "rip": lambda: RF.RunningInventoryPenalty(r["phi"], r["alpha"], r.get("exponent", 2.0)),
+           "cjmm": lambda: RF.CjMmCriterion(r["phi"], r["alpha"], r.get("exponent", 2.0), T),
+           "cjoe": lambda: RF.CjOeCriterion(r["phi"], r["alpha"], r.get("exponent", 2.0), T),
+           "exputil": lambda: RF.ExponentialUtility(r["risk_aversion"])}[r["kind"]]()
+    q0 = spec.get("initial_inventory", 0)
+    if isinstance(q0, list):
+        q0 = tuple(q0)
+    return TradingEnvironment(terminal_time=T, n_steps=n_steps, reward_function=rew, model_dynamics=dyn,
+                              initial_cash=spec.get("initial_cash", 0.0), initial_inventory=q0,
+                              max_inventory=spec.get("max_inventory", 10_000), max_cash=spec.get("max_cash"),
+                              start_time=spec.get("start_time", 0.0), seed=spec["seed"], num_trajectories=N,
+                              normalise_action_space=spec.get("normalise_action", False),
+                              normalise_observation_space=spec.get("normalise_obs", False), normalise_rewards=False,
+                              **extra)

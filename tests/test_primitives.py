@@ -1,0 +1,76 @@
+"""RNG / math primitives shared by the kernels and the oracle (include/mbt_philox.h, include/mbt_math.h)."""
+import numpy as np
+from scipy import special
+
+from oracle import oracle as O
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+        ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+        ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+         [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+    ]
+    for ctr, key, want in kat:
+        assert [int(x) for x in O.philox(ctr, key)] == want
+
+
+def _ulp_err(got, want, eps):
+    return np.max(np.abs(got.astype(np.float64) - want) / np.abs(want)) / eps
+
+
+def test_exp_log_accuracy_vs_libm():
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-86, 88, 400_000).astype(np.float32)
+    assert _ulp_err(O.vec("exp_f32", x), np.exp(x.astype(np.float64)), 2.0 ** -24) < 2.0
+    x = np.exp(rng.uniform(-80, 80, 400_000)).astype(np.float32)
+    assert _ulp_err(O.vec("log_f32", x), np.log(x.astype(np.float64)), 2.0 ** -24) < 2.0
+    x = rng.uniform(-700, 700, 400_000)
+    assert _ulp_err(O.vec("exp_f64", x), np.exp(x), 2.0 ** -53) < 4.0
+    x = np.exp(rng.uniform(-700, 700, 400_000))
+    assert _ulp_err(O.vec("log_f64", x), np.log(x), 2.0 ** -53) < 4.0
+    # range ends
+    assert O.vec("exp_f32", np.array([-100.0, 100.0], np.float32)).tolist() == [0.0, np.finfo(np.float32).max]
+    assert O.vec("exp_f64", np.array([-1000.0]))[0] == 0.0
+
+
+def test_pow_matches_numpy_fast_paths():
+    x = np.array([-3.0, -1.0, 0.0, 0.5, 2.0, 17.0])
+    assert np.array_equal(O.vec("pow_f64", x, 2.0), x ** 2.0)
+    assert np.array_equal(O.vec("pow_f64", x, 1.0), x ** 1.0)
+    np.testing.assert_allclose(O.vec("pow_f64", x, 4.0), x ** 4.0, rtol=1e-13)
+    np.testing.assert_allclose(O.vec("pow_f64", x, 3.0), x ** 3.0, rtol=1e-13)
+
+
+def test_normal_from_bits_is_the_normal_quantile():
+    rng = np.random.default_rng(1)
+    bits = rng.integers(0, 2 ** 32, 1_000_000, dtype=np.uint64).astype(np.uint32)
+    ks = np.arange(1, 32.01, 0.01)
+    mc = np.clip(np.round(2.0 ** -ks * 2 ** 31 - 0.5), 0, 2 ** 31 - 1).astype(np.uint64)
+    bits = np.concatenate([bits, (0x7FFFFFFF - mc).astype(np.uint32), np.array([0, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF], np.uint32)])
+    t = ((0x7FFFFFFF - (bits & 0x7FFFFFFF)).astype(np.float64) + 0.5) / 2 ** 31
+    want = np.where(bits >> 31, 1.0, -1.0) * special.ndtri(t / 2)
+    z64 = O.vec("normal_f64", bits)
+    z32 = O.vec("normal_f32", bits).astype(np.float64)
+    assert np.max(np.abs(z64 - want) / np.maximum(np.abs(want), 1e-9)) < 1e-13
+    assert np.max(np.abs(z32 - want)) < 3e-6
+    assert np.max(np.abs(z64)) < 6.34 and np.all(np.isfinite(z32))
+    main = z64[:1_000_000]
+    assert abs(main.mean()) < 5e-3 and abs(main.var() - 1) < 5e-3 and abs((main ** 4).mean() - 3) < 0.05
+
+
+def test_draws_are_uniform_and_independent_across_trajectories_and_steps():
+    from mbt_gym_b200 import _abi
+    u0, z0 = O.draws(_abi.MBT_F64, 123, 0, 50_000, 0)
+    u1, z1 = O.draws(_abi.MBT_F64, 123, 0, 50_000, 1)
+    assert u0.min() >= 0 and u0.max() < 1
+    assert np.all(np.abs(u0.mean(axis=0) - 0.5) < 0.01)
+    assert abs(np.corrcoef(z0, z1)[0, 1]) < 0.02 and abs(np.corrcoef(u0[:, 0], u0[:, 2])[0, 1]) < 0.02
+    # global trajectory ids: a shard at offset 1000 sees the same numbers as rows 1000.. of the full batch
+    u_part, z_part = O.draws(_abi.MBT_F64, 123, 1000, 100, 0)
+    assert np.array_equal(u_part, u0[1000:1100]) and np.array_equal(z_part, z0[1000:1100])
+    # float32 uniforms are the same grid points
+    u32, _ = O.draws(_abi.MBT_F32, 123, 0, 1000, 0)
+    assert np.array_equal(u32.astype(np.float64), u0[:1000])

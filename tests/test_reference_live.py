@@ -1,0 +1,73 @@
+"""Checks that need the UNMODIFIED reference at /root/reference (build container only; skipped on the GPU box).
+
+  * the oracle equals the reference step-for-step under injected draws (the generator of tests/golden, re-run live);
+  * the committed fixtures are what the reference produces today;
+  * the facade's host agents return exactly what the reference's agents return;
+  * the NumPy port used as CPU baseline reproduces the reference's notebook golden (Test_1, seed 50).
+"""
+import numpy as np
+import pytest
+
+from oracle import ref_shim as R
+from tests.helpers import Golden, build_facade_env, golden_specs
+
+pytestmark = pytest.mark.reference
+SPECS = golden_specs()
+
+
+@pytest.mark.parametrize("name", ["as_pnl_tight", "cjmm", "hawkes_normalised", "oe_ou_cjoe", "limit_and_market", "two_episodes"])
+def test_oracle_equals_live_reference_and_fixture_is_current(name):
+    spec = SPECS[name]
+    out = R.run_pair(spec, n_episodes=spec.get("n_episodes", 1))
+    assert np.array_equal(out["ref_obs"], out["orc_obs"]) and np.array_equal(out["ref_rew"], out["orc_rew"])
+    assert out["ref_done"] == out["orc_done"] and np.array_equal(out["ref_reset"], out["orc_reset"])
+    g = Golden(name)
+    assert np.array_equal(out["ref_obs"], g.obs) and np.array_equal(out["ref_rew"], g.rew)
+    assert bytes(out["cfg"]) == bytes(g.cfg)
+
+
+def test_host_agents_equal_reference_agents():
+    R.import_reference()
+    from mbt_gym.agents import BaselineAgents as RefAgents
+
+    from mbt_gym_b200.agents import BaselineAgents as Agents
+
+    rng = np.random.default_rng(0)
+    for name, make_ref, make_mine in [
+        ("as_pnl", lambda e: RefAgents.AvellanedaStoikovAgent(0.1, e), lambda e: Agents.AvellanedaStoikovAgent(0.1, e)),
+        ("cjmm", lambda e: RefAgents.CarteaJaimungalMmAgent(e), lambda e: Agents.CarteaJaimungalMmAgent(e)),
+        ("oe_ou_cjoe", lambda e: RefAgents.CarteaJaimungalOeAgent(env=e), lambda e: Agents.CarteaJaimungalOeAgent(env=e)),
+    ]:
+        spec = SPECS[name]
+        ref_env, my_env = R.build_reference_env(spec), build_facade_env(spec)
+        ref_agent, my_agent = make_ref(ref_env), make_mine(my_env)
+        n, d = spec["N"], ref_env.observation_space.shape[0]
+        for t in (0.0, 0.25, 0.995):
+            state = np.zeros((n, d))
+            state[:, 1] = rng.integers(-12, 13, size=n)
+            state[:, 2] = t
+            state[:, 3] = 100.0
+            np.testing.assert_array_equal(my_agent.get_action(state), ref_agent.get_action(state), err_msg=f"{name} t={t}")
+        if name == "cjmm":
+            np.testing.assert_array_equal(np.asarray(my_agent.calculate_true_value_function(state)).reshape(-1),
+                                          np.asarray(ref_agent.calculate_true_value_function(state)).reshape(-1))
+
+
+def test_numpy_port_reproduces_notebook_golden():
+    """Test_1 notebook, gamma=0.1 (notebooks/Test_1_-_replicate_AS_original_results.ipynb:219-231): second rollout."""
+    from oracle import numpy_port as P
+
+    env = P.NumpyPortEnv("as", N=1000, seed=50)
+    for _ in range(2):
+        obs = env.reset()
+        R_ = np.zeros(1000)
+        acts = []
+        while True:
+            a = P.as_agent_action(obs, 0.1, 2.0, 1.5, 1.0)
+            acts.append(a)
+            obs, r, d, _ = env.step(a)
+            R_ += r
+            if d[0]:
+                break
+    got = [2 * np.mean(acts), R_.mean(), R_.std(), obs[:, 1].mean(), obs[:, 1].std()]
+    np.testing.assert_allclose(got, [1.49177, 64.872139, 6.692567, 0.201, 2.893544], rtol=0, atol=6e-7)
