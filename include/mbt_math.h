@@ -126,6 +126,26 @@ MBT_HD float mbt_log_f32(float x) {
 }
 
 /* ------------------------------------------------------------------ exp, double */
+/* Polynomial coefficients live in a table: on the device a __constant__ array, so every DFMA takes its
+ * coefficient straight from the constant bank (a 64-bit literal would cost two UMOVs each). */
+#if defined(__CUDACC__)
+#define MBT_TABLE(name, n, ...)                         \
+    static const double name##_h[n] = {__VA_ARGS__};    \
+    static __constant__ double name##_d[n] = {__VA_ARGS__};
+#else
+#define MBT_TABLE(name, n, ...) static const double name##_h[n] = {__VA_ARGS__};
+#endif
+#if defined(__CUDA_ARCH__)
+#define MBT_T(name) name##_d
+#else
+#define MBT_T(name) name##_h
+#endif
+
+/* Taylor coefficients 1/13! ... 1/2! : truncation < 5e-18 on |r| <= ln2/2 */
+MBT_TABLE(mbt_exp64_c, 12, 1.6059043836821614599e-10, 2.0876756987868098979e-9, 2.5052108385441718775e-8,
+          2.7557319223985890653e-7, 2.7557319223985890653e-6, 2.4801587301587301587e-5, 1.9841269841269841270e-4,
+          1.3888888888888888889e-3, 8.3333333333333333333e-3, 4.1666666666666666667e-2, 1.6666666666666666667e-1, 0.5)
+
 MBT_HD double mbt_exp_f64(double x) {
     if (!(x > -700.0)) return (x != x) ? x : 0.0;
     if (x > 700.0) return 1.7976931348623157e308;
@@ -134,23 +154,16 @@ MBT_HD double mbt_exp_f64(double x) {
     double n = t - magic;
     double r = fma(n, -6.93147180369123816490e-01, x); /* ln2 high part (fdlibm split) */
     r = fma(n, -1.90821492927058770002e-10, r);        /* ln2 low part               */
-    /* Taylor series to r^13: truncation < 5e-18 on |r| <= 0.3466 */
-    double p = 1.6059043836821614599e-10; /* 1/13! */
-    p = fma(p, r, 2.0876756987868098979e-9);  /* 1/12! */
-    p = fma(p, r, 2.5052108385441718775e-8);  /* 1/11! */
-    p = fma(p, r, 2.7557319223985890653e-7);  /* 1/10! */
-    p = fma(p, r, 2.7557319223985890653e-6);  /* 1/9!  */
-    p = fma(p, r, 2.4801587301587301587e-5);  /* 1/8!  */
-    p = fma(p, r, 1.9841269841269841270e-4);  /* 1/7!  */
-    p = fma(p, r, 1.3888888888888888889e-3);  /* 1/6!  */
-    p = fma(p, r, 8.3333333333333333333e-3);  /* 1/5!  */
-    p = fma(p, r, 4.1666666666666666667e-2);  /* 1/4!  */
-    p = fma(p, r, 1.6666666666666666667e-1);  /* 1/3!  */
-    p = fma(p, r, 0.5);
+    double p = MBT_T(mbt_exp64_c)[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 1; k < 12; ++k) p = fma(p, r, MBT_T(mbt_exp64_c)[k]);
     double r2 = r * r;
     double y = fma(p, r2, r) + 1.0;
-    int64_t ni = (int64_t)n;
-    return mbt_bits_f64(mbt_f64_bits(y) + ((uint64_t)ni << 52));
+    /* n is an integer in [-1010, 1010]: the low word of t holds it in two's complement */
+    int32_t ni = (int32_t)(uint32_t)mbt_f64_bits(t);
+    return mbt_bits_f64(mbt_f64_bits(y) + ((uint64_t)(int64_t)ni << 52));
 }
 
 /* ------------------------------------------------------------------ log, double */
@@ -324,6 +337,17 @@ MBT_HD double mbt_normal_from_bits_f64(uint32_t bits) {
     }
     double z = (1.41421356237309504880 * v) * p;
     return (bits >> 31) ? -z : z;
+}
+
+/* 24-bit integer -> the uniform k * 2^-24 in [0,1), exactly, in either precision.  On the device the double
+ * version avoids the slow I2F.F64 unit: OR the integer into the mantissa of 2^52 and subtract 2^52. */
+MBT_HD float mbt_u24_to_unit_f32(uint32_t k) { return (float)k * 5.9604644775390625e-08f; }
+MBT_HD double mbt_u24_to_unit_f64(uint32_t k) {
+#if defined(__CUDA_ARCH__)
+    return (__hiloint2double(0x43300000, (int)k) - 4503599627370496.0) * 5.9604644775390625e-08;
+#else
+    return (double)k * 5.9604644775390625e-08;
+#endif
 }
 
 /* x^p for the inventory penalties (reference: RewardFunctions.py:60-67,100-107,133-137,

@@ -43,15 +43,58 @@ typedef struct mbt_u32x4 {
 } mbt_u32x4;
 
 MBT_HD void mbt_mulhilo32(uint32_t a, uint32_t b, uint32_t *hi, uint32_t *lo) {
-#if defined(__CUDA_ARCH__)
-    *lo = a * b;
-    *hi = __umulhi(a, b);
-#else
-    uint64_t p = (uint64_t)a * (uint64_t)b;
+    uint64_t p = (uint64_t)a * (uint64_t)b; /* one IMAD.WIDE.U32 on the device */
     *lo = (uint32_t)p;
     *hi = (uint32_t)(p >> 32);
-#endif
 }
+
+/* The ten round keys of a seed (key bumped by the Weyl constants each round).  The step kernels get them
+ * precomputed from the host in their argument block (constant bank) instead of re-deriving them per thread. */
+typedef struct mbt_philox_keys {
+    uint32_t k0[10], k1[10];
+} mbt_philox_keys;
+
+MBT_HD mbt_philox_keys mbt_philox_expand(uint64_t seed) {
+    mbt_philox_keys K;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.k0[r] = k0;
+        K.k1[r] = k1;
+        k0 += MBT_PHILOX_W0;
+        k1 += MBT_PHILOX_W1;
+    }
+    return K;
+}
+
+#if defined(__cplusplus)
+MBT_HD mbt_u32x4 mbt_philox4x32_10_keyed(mbt_u32x4 c, const mbt_philox_keys &K) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mbt_mulhilo32(MBT_PHILOX_M0, c.x, &hi0, &lo0);
+        mbt_mulhilo32(MBT_PHILOX_M1, c.z, &hi1, &lo1);
+        mbt_u32x4 n;
+        n.x = hi1 ^ c.y ^ K.k0[r];
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ K.k1[r];
+        n.w = lo0;
+        c = n;
+    }
+    return c;
+}
+
+/* mbt_draw with pre-expanded keys: identical output. */
+MBT_HD mbt_u32x4 mbt_draw_keyed(const mbt_philox_keys &K, uint64_t traj, uint64_t n, uint32_t stream) {
+    mbt_u32x4 c;
+    c.x = (uint32_t)traj;
+    c.y = (uint32_t)(traj >> 32);
+    c.z = (uint32_t)n;
+    c.w = (stream << 24) | ((uint32_t)(n >> 32) & 0x00FFFFFFu);
+    return mbt_philox4x32_10_keyed(c, K);
+}
+#endif
 
 MBT_HD mbt_u32x4 mbt_philox4x32_10(mbt_u32x4 c, uint32_t k0, uint32_t k1) {
 #if defined(__CUDA_ARCH__)
@@ -89,7 +132,9 @@ MBT_HD mbt_u32x4 mbt_draw(uint64_t seed, uint64_t traj, uint64_t n, uint32_t str
  *       (x: bid arrival, y: ask arrival, z: bid fill, w: ask fill -- the consumption
  *        order of the reference, arrival_models.py:55 then fill_probability_models.py:33);
  *   low 8 bits of the four words, concatenated -> 32 bits for the midprice normal
- *       (midprice_models.py:64,143), mapped through mbt_normal_from_bits (mbt_math.h).
+ *       (midprice_models.py:64,143), mapped through mbt_normal_from_bits_f32 (mbt_math.h) in BOTH
+ *       precisions: the float64 path widens that float (the draw is a definition, its 24-bit resolution
+ *       is far below any statistical resolution; state arithmetic stays float64).
  * All 128 output bits of a Philox block are independent, so the five values are too.
  */
 MBT_HD uint32_t mbt_uniform_bits24(uint32_t word) { return word >> 8; }

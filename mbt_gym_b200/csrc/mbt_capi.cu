@@ -40,6 +40,7 @@ static int fail(int code, const std::string &msg) {
 
 /* ------------------------------------------------------------------ handle */
 constexpr int MBT_TIMING_RING = 8192;
+constexpr int MBT_PIPE_CHUNKS = 8;
 
 struct mbt_env {
     mbt_config cfg;
@@ -57,8 +58,8 @@ struct mbt_env {
     /* device + pinned staging for MBT_MEM_HOST calls */
     void *d_actions = nullptr, *d_obs = nullptr, *d_rew = nullptr;
     void *h_actions = nullptr, *h_obs = nullptr, *h_rew = nullptr;
-    cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr;
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr; /* H2D / D2H copy engines for the pipelined host path */
+    cudaEvent_t ev_in[MBT_PIPE_CHUNKS] = {}, ev_k[MBT_PIPE_CHUNKS] = {};
 
     /* rollout scratch */
     double *d_times = nullptr;
@@ -155,19 +156,41 @@ static void launch_step_v(mbt_env *e, const StepArgs<T> &g, bool vec) {
         mbt_step_kernel<T, V, false><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
 }
 
-/* the BASELINE.json configurations get compile-time-specialised kernels, everything else the generic one */
-using VariantAS = Variant<MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, -1>;
-using VariantHawkes = Variant<MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, -1>;
-using VariantOE = Variant<MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, -1>;
+/*
+ * Kernel variants.  The BASELINE.json configurations (and the reference's default-constructor market) get
+ * instantiations with model kinds, row widths, reward kind and "no normalisation" fixed at compile time;
+ * everything else runs the generic kernel with runtime switches (warp-uniform branches).
+ */
+#define V_(d, m, a, i, r, n) Variant<d, m, a, i, r, n>
+#define MBT_FOR_EACH_VARIANT(X)                                                                                     \
+    X(0, VariantGeneric)                                                                                            \
+    X(1, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_PNL, 0))                              \
+    X(2, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_CJ_MM, 0))                            \
+    X(3, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_RUNNING_INVENTORY_PENALTY, 0))        \
+    X(4, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, -1, -1))                                      \
+    X(5, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, MBT_REW_PNL, 0))                               \
+    X(6, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, -1, -1))                                       \
+    X(7, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, MBT_REW_CJ_OE, 0))                          \
+    X(8, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, MBT_REW_PNL, 0))                            \
+    X(9, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, -1, -1))
 
 static int variant_of(const mbt_config &c) {
+    const bool plain = !c.normalise_action && !c.normalise_obs && !c.normalise_rewards;
     if (c.dynamics == MBT_DYN_LIMIT && c.midprice == MBT_MID_BM && c.impact == MBT_IMP_NONE) {
-        if (c.arrival == MBT_ARR_POISSON) return 1;
-        if (c.arrival == MBT_ARR_HAWKES) return 2;
+        if (c.arrival == MBT_ARR_POISSON) {
+            if (plain && c.reward == MBT_REW_PNL) return 1;
+            if (plain && c.reward == MBT_REW_CJ_MM) return 2;
+            if (plain && c.reward == MBT_REW_RUNNING_INVENTORY_PENALTY) return 3;
+            return 4;
+        }
+        if (c.arrival == MBT_ARR_HAWKES) return (plain && c.reward == MBT_REW_PNL) ? 5 : 6;
     }
     if (c.dynamics == MBT_DYN_SPEED && c.midprice == MBT_MID_OU && c.impact == MBT_IMP_TEMP_PERM &&
-        c.arrival == MBT_ARR_NONE)
-        return 3;
+        c.arrival == MBT_ARR_NONE) {
+        if (plain && c.reward == MBT_REW_CJ_OE) return 7;
+        if (plain && c.reward == MBT_REW_PNL) return 8;
+        return 9;
+    }
     return 0;
 }
 
@@ -180,39 +203,97 @@ static bool rows_vector_aligned(const mbt_env *e, const void *actions, const voi
     return ((uintptr_t)actions % need_a) == 0 && (!obs || ((uintptr_t)obs % need_o) == 0);
 }
 
+/* launch the step kernel on rows [r0, r0+n) of the batch (base pointers address row 0) */
+template <typename T>
+static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<T> &ck, const void *actions, void *obs,
+                            void *rew, long long r0, long long n) {
+    const mbt_config &c = e->cfg;
+    StepArgs<T> g;
+    g.p = p;
+    g.ck = ck;
+    g.st = dev_state<T>(e);
+    g.st.cash += r0; g.st.inv += r0; g.st.mid += r0; g.st.x0 += r0; g.st.x1 += r0; g.st.q0 += r0;
+    g.actions = (const T *)actions + r0 * e->A;
+    g.obs = obs ? (T *)obs + r0 * e->D : nullptr;
+    g.rew = rew ? (T *)rew + r0 : nullptr;
+    g.n = n;
+    g.keys = mbt_philox_expand(e->seed);
+    g.traj_offset = (unsigned long long)c.traj_offset + (unsigned long long)r0;
+    g.n_step = (unsigned long long)e->n_step;
+    g.clipped = e->d_clipped;
+    const bool vec = rows_vector_aligned<T>(e, g.actions, g.obs);
+    switch (variant_of(c)) {
+#define X(id, ...) case id: launch_step_v<T, __VA_ARGS__>(e, g, vec); break;
+        MBT_FOR_EACH_VARIANT(X)
+#undef X
+    }
+    CU(cudaGetLastError());
+    e->launches += 1;
+    return MBT_OK;
+}
+
+static void advance_clock(mbt_env *e, double t_next) {
+    e->t = t_next;
+    e->k += 1;
+    e->n_step += 1;
+}
+
 template <typename T>
 static int do_step_device(mbt_env *e, const void *actions, void *obs, void *rew, uint8_t *done_out) {
     const mbt_config &c = e->cfg;
     const double t_next = e->t + c.step_size; /* state[:, TIME] += step_size   TradingEnvironment.py:216 */
-    StepArgs<T> g;
-    g.p = mbt_make_params<T>(c, e->t0, e->q0_per_traj, e->q0_uniform);
-    g.ck = mbt_make_clock<T>(c, e->t, t_next);
-    g.st = dev_state<T>(e);
-    g.actions = (const T *)actions;
-    g.obs = (T *)obs;
-    g.rew = (T *)rew;
-    g.n = e->N;
-    g.seed = e->seed;
-    g.traj_offset = (unsigned long long)c.traj_offset;
-    g.n_step = (unsigned long long)e->n_step;
-    g.clipped = e->d_clipped;
-    const bool vec = rows_vector_aligned<T>(e, actions, obs);
+    const StepParams<T> p = mbt_make_params<T>(c, e->t0, e->q0_per_traj, e->q0_uniform);
+    const StepClock<T> ck = mbt_make_clock<T>(c, e->t, t_next);
     int rc = timing_begin(e);
     if (rc) return rc;
-    switch (variant_of(c)) {
-    case 1: launch_step_v<T, VariantAS>(e, g, vec); break;
-    case 2: launch_step_v<T, VariantHawkes>(e, g, vec); break;
-    case 3: launch_step_v<T, VariantOE>(e, g, vec); break;
-    default: launch_step_v<T, VariantGeneric>(e, g, vec); break;
-    }
-    CU(cudaGetLastError());
+    rc = launch_step_rows<T>(e, p, ck, actions, obs, rew, 0, e->N);
+    if (rc) return rc;
     rc = timing_end(e);
     if (rc) return rc;
-    e->launches += 1;
-    e->t = t_next;
-    e->k += 1;
-    e->n_step += 1;
-    if (done_out) *done_out = (uint8_t)g.ck.done;
+    advance_clock(e, t_next);
+    if (done_out) *done_out = (uint8_t)ck.done;
+    return MBT_OK;
+}
+
+/*
+ * Host-buffer step: the batch is cut into row chunks and each chunk flows H2D(actions) -> kernel -> D2H(obs, rewards)
+ * on three streams, so the two copy engines (PCIe is full duplex) and the SMs overlap; the call returns when the last
+ * chunk's results are in the caller's buffers.  `act_src`, `obs_dst`, `rew_dst` are pinned (caller's own pinned
+ * buffers, or the handle's staging).
+ */
+template <typename T>
+static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst, void *rew_dst, uint8_t *done_out) {
+    const mbt_config &c = e->cfg;
+    const double t_next = e->t + c.step_size;
+    const StepParams<T> p = mbt_make_params<T>(c, e->t0, e->q0_per_traj, e->q0_uniform);
+    const StepClock<T> ck = mbt_make_clock<T>(c, e->t, t_next);
+    const long long N = e->N;
+    int chunks = N >= (1 << 17) ? MBT_PIPE_CHUNKS : 1;
+    long long rows = ((N + chunks - 1) / chunks + 255) & ~255ll;
+    const size_t arow = (size_t)e->A * sizeof(T), orow = (size_t)e->D * sizeof(T);
+    for (int k = 0; k < chunks; ++k) {
+        const long long r0 = (long long)k * rows;
+        if (r0 >= N) break;
+        const long long n = std::min(rows, N - r0);
+        CU(cudaMemcpyAsync((char *)e->d_actions + r0 * arow, (const char *)act_src + r0 * arow, n * arow,
+                           cudaMemcpyHostToDevice, e->copy_in));
+        CU(cudaEventRecord(e->ev_in[k], e->copy_in));
+        CU(cudaStreamWaitEvent(e->stream, e->ev_in[k], 0));
+        int rc = launch_step_rows<T>(e, p, ck, e->d_actions, obs_dst ? e->d_obs : nullptr, rew_dst ? e->d_rew : nullptr, r0, n);
+        if (rc) return rc;
+        CU(cudaEventRecord(e->ev_k[k], e->stream));
+        CU(cudaStreamWaitEvent(e->copy_out, e->ev_k[k], 0));
+        if (obs_dst)
+            CU(cudaMemcpyAsync((char *)obs_dst + r0 * orow, (const char *)e->d_obs + r0 * orow, n * orow,
+                               cudaMemcpyDeviceToHost, e->copy_out));
+        if (rew_dst)
+            CU(cudaMemcpyAsync((char *)rew_dst + r0 * sizeof(T), (const char *)e->d_rew + r0 * sizeof(T), n * sizeof(T),
+                               cudaMemcpyDeviceToHost, e->copy_out));
+    }
+    CU(cudaStreamSynchronize(e->copy_out));
+    CU(cudaStreamSynchronize(e->stream));
+    advance_clock(e, t_next);
+    if (done_out) *done_out = (uint8_t)ck.done;
     return MBT_OK;
 }
 
@@ -297,9 +378,12 @@ int mbt_destroy(mbt_env *e) {
     cudaFreeHost(e->h_block_sums);
     for (auto ev : e->ev0) cudaEventDestroy(ev);
     for (auto ev : e->ev1) cudaEventDestroy(ev);
-    if (e->ev_h2d) cudaEventDestroy(e->ev_h2d);
-    if (e->ev_kernel) cudaEventDestroy(e->ev_kernel);
-    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (int i = 0; i < MBT_PIPE_CHUNKS; ++i) {
+        if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+        if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]);
+    }
+    if (e->copy_in) cudaStreamDestroy(e->copy_in);
+    if (e->copy_out) cudaStreamDestroy(e->copy_out);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     cudaGetLastError();
     delete e;
@@ -345,9 +429,12 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     } while (0)
     CUB(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
-    CUB(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    CUB(cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming));
-    CUB(cudaEventCreateWithFlags(&e->ev_kernel, cudaEventDisableTiming));
+    CUB(cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < MBT_PIPE_CHUNKS; ++i) {
+        CUB(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming));
+    }
     /* columns padded to 256 B so every column base is aligned for any vector width */
     const size_t col_bytes = (((size_t)e->N * e->esz) + 255) & ~(size_t)255;
     CUB(cudaMalloc(&e->state_block, col_bytes * 6));
@@ -443,29 +530,21 @@ int mbt_step(mbt_env *e, const void *actions, void *obs_out, void *rew_out, uint
         return f64 ? do_step_device<double>(e, actions, obs_out, rew_out, done_out)
                    : do_step_device<float>(e, actions, obs_out, rew_out, done_out);
 
-    /* host buffers: H2D actions -> kernel -> D2H observations + rewards, all inside this call */
+    /* host buffers: H2D actions -> kernel -> D2H observations + rewards, pipelined, all inside this call */
     int rc = ensure_staging(e);
     if (rc) return rc;
     const size_t ab = (size_t)e->N * e->A * e->esz, ob = (size_t)e->N * e->D * e->esz, rb = (size_t)e->N * e->esz;
     const void *src = actions;
-    if (!host_ptr_is_pinned(actions)) {
+    if (!host_ptr_is_pinned(actions)) { /* pageable caller memory: stage through the handle's pinned buffer */
         par_memcpy(e->h_actions, actions, ab);
         src = e->h_actions;
     }
-    CU(cudaMemcpyAsync(e->d_actions, src, ab, cudaMemcpyHostToDevice, e->stream));
-    rc = f64 ? do_step_device<double>(e, e->d_actions, obs_out ? e->d_obs : nullptr, rew_out ? e->d_rew : nullptr, done_out)
-             : do_step_device<float>(e, e->d_actions, obs_out ? e->d_obs : nullptr, rew_out ? e->d_rew : nullptr, done_out);
+    const bool un_obs = obs_out && !host_ptr_is_pinned(obs_out), un_rew = rew_out && !host_ptr_is_pinned(rew_out);
+    void *obs_dst = obs_out ? (un_obs ? e->h_obs : obs_out) : nullptr;
+    void *rew_dst = rew_out ? (un_rew ? e->h_rew : rew_out) : nullptr;
+    rc = f64 ? do_step_host_pipelined<double>(e, src, obs_dst, rew_dst, done_out)
+             : do_step_host_pipelined<float>(e, src, obs_dst, rew_dst, done_out);
     if (rc) return rc;
-    bool un_obs = false, un_rew = false;
-    if (obs_out) {
-        rc = d2h(e, obs_out, e->d_obs, e->h_obs, ob, &un_obs);
-        if (rc) return rc;
-    }
-    if (rew_out) {
-        rc = d2h(e, rew_out, e->d_rew, e->h_rew, rb, &un_rew);
-        if (rc) return rc;
-    }
-    CU(cudaStreamSynchronize(e->stream));
     if (un_obs) par_memcpy(obs_out, e->h_obs, ob);
     if (un_rew) par_memcpy(rew_out, e->h_rew, rb);
     return MBT_OK;
@@ -615,7 +694,7 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
     g.p = mbt_make_params<T>(c, e->t0, e->q0_per_traj, e->q0_uniform);
     g.st = dev_state<T>(e);
     g.n = e->N;
-    g.seed = e->seed;
+    g.keys = mbt_philox_expand(e->seed);
     g.traj_offset = (unsigned long long)c.traj_offset;
     g.n_step0 = (unsigned long long)e->n_step;
     g.steps = steps;
@@ -670,10 +749,9 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
     int rc = timing_begin(e);
     if (rc) return rc;
     switch (variant_of(c)) {
-    case 1: mbt_rollout_kernel<T, VariantAS><<<blocks, MBT_BLOCK, 0, e->stream>>>(g); break;
-    case 2: mbt_rollout_kernel<T, VariantHawkes><<<blocks, MBT_BLOCK, 0, e->stream>>>(g); break;
-    case 3: mbt_rollout_kernel<T, VariantOE><<<blocks, MBT_BLOCK, 0, e->stream>>>(g); break;
-    default: mbt_rollout_kernel<T, VariantGeneric><<<blocks, MBT_BLOCK, 0, e->stream>>>(g); break;
+#define X(id, ...) case id: mbt_rollout_kernel<T, __VA_ARGS__><<<blocks, MBT_BLOCK, 0, e->stream>>>(g); break;
+        MBT_FOR_EACH_VARIANT(X)
+#undef X
     }
     CU(cudaGetLastError());
     rc = timing_end(e);

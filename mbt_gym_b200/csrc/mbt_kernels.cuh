@@ -41,9 +41,16 @@ struct StepArgs {
     T *obs;           /* (N, D) or NULL */
     T *rew;           /* (N,)   or NULL */
     long long n;
-    unsigned long long seed, traj_offset, n_step;
+    mbt_philox_keys keys; /* the ten Philox round keys of the seed, expanded on the host */
+    unsigned long long traj_offset, n_step;
     unsigned long long *clipped;
 };
+
+/* the specialised variants know the row widths at compile time */
+template <typename T, class V>
+__device__ __forceinline__ int action_width(const StepParams<T> &p) { return V::A ? V::A : p.action_dim; }
+template <typename T, class V>
+__device__ __forceinline__ int obs_width(const StepParams<T> &p) { return V::D ? V::D : p.obs_dim; }
 
 /* ------------------------------------------------------------------ row access helpers */
 template <typename T, int W>
@@ -114,15 +121,15 @@ template <typename T, class V>
 __device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T> &s, T t, T *row) {
     const int arr = pick<V::arr>(p.arr), imp = pick<V::imp>(p.imp);
     int d = 0;
-    row[d] = norm_obs(p, s.cash, d); ++d;
-    row[d] = norm_obs(p, s.inv, d); ++d;
-    row[d] = norm_obs(p, t, d); ++d;
-    row[d] = norm_obs(p, s.mid, d); ++d;
+    row[d] = norm_obs<T, V>(p, s.cash, d); ++d;
+    row[d] = norm_obs<T, V>(p, s.inv, d); ++d;
+    row[d] = norm_obs<T, V>(p, t, d); ++d;
+    row[d] = norm_obs<T, V>(p, s.mid, d); ++d;
     if (arr == MBT_ARR_HAWKES) {
-        row[d] = norm_obs(p, s.x0, d); ++d;
-        row[d] = norm_obs(p, s.x1, d); ++d;
+        row[d] = norm_obs<T, V>(p, s.x0, d); ++d;
+        row[d] = norm_obs<T, V>(p, s.x1, d); ++d;
     }
-    if (imp == MBT_IMP_TEMP_PERM) { row[d] = norm_obs(p, s.x0, d); ++d; }
+    if (imp == MBT_IMP_TEMP_PERM) { row[d] = norm_obs<T, V>(p, s.x0, d); ++d; }
     return d;
 }
 
@@ -156,25 +163,28 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_consta
     if (i >= g.n) return;
     const StepParams<T> &p = g.p;
 
+    const int A = action_width<T, V>(p);
     T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
-    load_row<T>(g.actions, i, p.action_dim, a, VEC);
+    load_row<T>(g.actions, i, A, a, VEC);
 #pragma unroll
     for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j)
-        if (j < p.action_dim) a[j] = denorm_action(p, a[j], j);
+        if (j < A) a[j] = denorm_action<T, V>(p, a[j], j);
 
     Traj<T> s;
     load_traj<T, V>(p, g.st, i, s);
-    const T q_init = p.q0_per_traj ? g.st.q0[i] : p.q0_uniform;
+    const int rew_kind = pick<V::rew>(p.rew);
+    T q_init = p.q0_uniform;
+    if ((rew_kind == MBT_REW_CJ_MM || rew_kind == MBT_REW_CJ_OE) && p.q0_per_traj) q_init = g.st.q0[i];
 
-    const mbt_u32x4 r = mbt_draw(g.seed, g.traj_offset + (unsigned long long)i, g.n_step, MBT_STREAM_STEP);
+    const mbt_u32x4 r = mbt_draw_keyed(g.keys, g.traj_offset + (unsigned long long)i, g.n_step, MBT_STREAM_STEP);
     int clipped = 0;
     const T rwd = step_one<T, V>(p, g.ck, s, a, r, q_init, &clipped);
 
     store_traj<T, V>(p, g.st, i, s);
     if (g.obs) {
         T row[MBT_MAX_OBS_DIM];
-        const int d = make_obs_row<T, V>(p, s, g.ck.t_next, row);
-        store_row<T>(g.obs, i, d, row, VEC);
+        make_obs_row<T, V>(p, s, g.ck.t_next, row);
+        store_row<T>(g.obs, i, obs_width<T, V>(p), row, VEC);
     }
     if (g.rew) g.rew[i] = rwd;
     if (clipped) atomicAdd(g.clipped, 1ull);
@@ -278,7 +288,8 @@ struct RolloutArgs {
     StepParams<T> p;
     DevState<T> st;
     long long n;
-    unsigned long long seed, traj_offset, n_step0;
+    mbt_philox_keys keys;
+    unsigned long long traj_offset, n_step0;
     int steps;            /* env-steps to run (until the episode ends) */
     const double *times;  /* device, steps+1 entries: the clock as the host accumulates it (t += dt) */
     double terminal_time, step_size;
@@ -328,7 +339,10 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
     if (live) {
         Traj<T> s;
         load_traj<T, V>(p, g.st, i, s);
-        const T q_init = p.q0_per_traj ? g.st.q0[i] : p.q0_uniform;
+        const int rew_kind = pick<V::rew>(p.rew);
+        T q_init = p.q0_uniform;
+        if ((rew_kind == MBT_REW_CJ_MM || rew_kind == MBT_REW_CJ_OE) && p.q0_per_traj) q_init = g.st.q0[i];
+        const int A = action_width<T, V>(p);
         T ret = (T)0;
         int clipped = 0;
         double t_cur = g.times[0];
@@ -342,11 +356,11 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
             policy_action<T>(g, k, (T)t_cur, s, a);
 #pragma unroll
             for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j)
-                if (j < p.action_dim) {
+                if (j < A) {
                     acc[4] += (double)a[j];
-                    a[j] = denorm_action(p, a[j], j);
+                    a[j] = denorm_action<T, V>(p, a[j], j);
                 }
-            const mbt_u32x4 r = mbt_draw(g.seed, g.traj_offset + (unsigned long long)i, g.n_step0 + (unsigned long long)k, MBT_STREAM_STEP);
+            const mbt_u32x4 r = mbt_draw_keyed(g.keys, g.traj_offset + (unsigned long long)i, g.n_step0 + (unsigned long long)k, MBT_STREAM_STEP);
             const T rwd = step_one<T, V>(p, ck, s, a, r, q_init, &clipped);
             ret = ret + rwd;
             acc[5] += (double)rwd * (double)rwd;

@@ -12,7 +12,9 @@
  * only fused operations are the explicit fma() calls inside include/mbt_math.h.
  *
  * The `V` template argument fixes model kinds at compile time (V::dyn etc. >= 0) or leaves them to the
- * runtime config (-1): the BASELINE configurations get specialised kernels, everything else the generic one.
+ * runtime config (-1).  The kernels are issue-bound (profiles/), so the BASELINE configurations get fully
+ * specialised instantiations -- action/observation widths, reward kind and "no normalisation" known to
+ * the compiler -- and everything else runs the generic one.
  */
 #ifndef MBT_STEP_CORE_CUH
 #define MBT_STEP_CORE_CUH
@@ -21,24 +23,28 @@
 #include "../../include/mbt_math.h"
 #include "../../include/mbt_philox.h"
 
-template <int DYN, int MID, int ARR, int IMP, int REW>
+/* NORM: 0 = no action/observation/reward normalisation compiled in; -1 = decided by runtime flags. */
+template <int DYN, int MID, int ARR, int IMP, int REW, int NORM>
 struct Variant {
-    static constexpr int dyn = DYN, mid = MID, arr = ARR, imp = IMP, rew = REW;
+    static constexpr int dyn = DYN, mid = MID, arr = ARR, imp = IMP, rew = REW, norm = NORM;
+    /* action / observation widths when the model kinds are fixed (0 = runtime) */
+    static constexpr int A = DYN < 0 ? 0 : (DYN == MBT_DYN_SPEED ? 1 : (DYN == MBT_DYN_LIMIT_AND_MARKET ? 4 : 2));
+    static constexpr int D = (DYN < 0 || ARR < 0 || IMP < 0) ? 0 : 4 + (ARR == MBT_ARR_HAWKES ? 2 : 0) + (IMP == MBT_IMP_TEMP_PERM ? 1 : 0);
 };
-using VariantGeneric = Variant<-1, -1, -1, -1, -1>;
+using VariantGeneric = Variant<-1, -1, -1, -1, -1, -1>;
 
 /* math dispatch on the arithmetic type */
 MBT_HD float mbt_exp_t(float x) { return mbt_exp_f32(x); }
 MBT_HD double mbt_exp_t(double x) { return mbt_exp_f64(x); }
 MBT_HD float mbt_pow_t(float x, float p) { return mbt_pow_f32(x, p); }
 MBT_HD double mbt_pow_t(double x, double p) { return mbt_pow_f64(x, p); }
-MBT_HD void mbt_normal_t(uint32_t bits, float *z) { *z = mbt_normal_from_bits_f32(bits); }
-MBT_HD void mbt_normal_t(uint32_t bits, double *z) { *z = mbt_normal_from_bits_f64(bits); }
+MBT_HD void mbt_unit_t(uint32_t k, float *u) { *u = mbt_u24_to_unit_f32(k); }
+MBT_HD void mbt_unit_t(uint32_t k, double *u) { *u = mbt_u24_to_unit_f64(k); }
 
 /*
- * Uniform (per-launch) quantities, already in the arithmetic type T.  Built on the host by
- * make_params() in mbt_capi.cu from mbt_config, forming each derived constant the way the reference's
- * Python floats do (e.g. volatility * sqrt(step_size) in float64, then cast).
+ * Uniform (per-episode) quantities, already in the arithmetic type T.  Built on the host by
+ * mbt_make_params() from mbt_config, forming each derived constant the way the reference's Python floats
+ * do (e.g. volatility * sqrt(step_size) in float64, then cast).
  */
 template <typename T>
 struct StepParams {
@@ -80,7 +86,7 @@ struct Traj {
 template <int CT>
 MBT_HD int pick(int runtime) { return CT >= 0 ? CT : runtime; }
 
-/* reward_function.calculate for one row; (c0,q0s,S0) = current_state, s = next_state. */
+/* reward_function.calculate for one row; (c0, q_cur, S0) = current_state, s = next_state. */
 template <typename T, class V>
 MBT_HD T reward_one(const StepParams<T> &p, const StepClock<T> &ck, T c0, T q_cur, T S0, const Traj<T> &s, const T *a, T q_init) {
     const int rew = pick<V::rew>(p.rew);
@@ -112,12 +118,11 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
     const int dyn = pick<V::dyn>(p.dyn), mid = pick<V::mid>(p.mid), arr_kind = pick<V::arr>(p.arr),
               imp = pick<V::imp>(p.imp);
     const T c0 = s.cash, q_cur = s.inv, S = s.mid; /* current_state = state.copy()   TradingEnvironment.py:105 */
-    const T two_m24 = (T)5.9604644775390625e-08;
     T arr_b = 0, arr_a = 0;
 
     if (dyn != MBT_DYN_SPEED) {
         /* get_arrivals_and_fills                                    ModelDynamics.py:127-131,169-172 */
-        T pb, pa;
+        T pb, pa, ub, ua;
         if (arr_kind == MBT_ARR_HAWKES) { /* unif < lambda_t * step   arrival_models.py:121-123 */
             pb = s.x0 * p.arr_step;
             pa = s.x1 * p.arr_step;
@@ -125,8 +130,10 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
             pb = p.p_arr[0];
             pa = p.p_arr[1];
         }
-        arr_b = ((T)mbt_uniform_bits24(r.x) * two_m24 < pb) ? (T)1 : (T)0;
-        arr_a = ((T)mbt_uniform_bits24(r.y) * two_m24 < pa) ? (T)1 : (T)0;
+        mbt_unit_t(mbt_uniform_bits24(r.x), &ub);
+        mbt_unit_t(mbt_uniform_bits24(r.y), &ua);
+        arr_b = (ub < pb) ? (T)1 : (T)0;
+        arr_a = (ua < pa) ? (T)1 : (T)0;
         T fil_b, fil_a, off_b, off_a;
         if (dyn == MBT_DYN_AT_TOUCH) { /* fills = action[:, 0:2]      ModelDynamics.py:157-158,171 */
             fil_b = a[0];
@@ -134,8 +141,11 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
             off_b = p.half_spread;
             off_a = p.half_spread;
         } else { /* unif < exp(-kappa*depth)   fill_probability_models.py:28-34,57-58 */
-            fil_b = ((T)mbt_uniform_bits24(r.z) * two_m24 < mbt_exp_t(p.neg_kappa * a[0])) ? (T)1 : (T)0;
-            fil_a = ((T)mbt_uniform_bits24(r.w) * two_m24 < mbt_exp_t(p.neg_kappa * a[1])) ? (T)1 : (T)0;
+            T vb, va;
+            mbt_unit_t(mbt_uniform_bits24(r.z), &vb);
+            mbt_unit_t(mbt_uniform_bits24(r.w), &va);
+            fil_b = (vb < mbt_exp_t(p.neg_kappa * a[0])) ? (T)1 : (T)0;
+            fil_a = (va < mbt_exp_t(p.neg_kappa * a[1])) ? (T)1 : (T)0;
             off_b = a[0];
             off_a = a[1];
         }
@@ -170,8 +180,7 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
 
     /* _update_market_state: midprice, arrival, fill, impact            TradingEnvironment.py:206-211 */
     if (mid != MBT_MID_CONSTANT) {
-        T z;
-        mbt_normal_t(mbt_normal_bits(r), &z);
+        const T z = (T)mbt_normal_from_bits_f32(mbt_normal_bits(r)); /* draw contract: float quantile, widened */
         if (mid == MBT_MID_BM) /* midprice_models.py:60-65 */
             s.mid = (S + p.drift_dt) + p.vol_sqdt * z;
         else if (mid == MBT_MID_GBM) /* midprice_models.py:97-105 */
@@ -188,17 +197,20 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
 
     /* rewards = reward_function.calculate(current_state, action, next_state, dones[0])   :108 */
     T rwd = reward_one<T, V>(p, ck, c0, q_cur, S, s, a, q_init);
+    if (V::norm == 0) return rwd;
     return p.normalise_rewards ? p.reward_scaling * rwd : rwd; /* :128-129 */
 }
 
 /* normalise_action(inverse=True)                                       TradingEnvironment.py:120-126 */
-template <typename T>
+template <typename T, class V>
 MBT_HD T denorm_action(const StepParams<T> &p, T x, int j) {
+    if (V::norm == 0) return x;
     return p.normalise_action ? (x + (T)1) * p.act_grad[j] + p.act_low[j] : x;
 }
 /* normalise_observation                                                 TradingEnvironment.py:112-118 */
-template <typename T>
+template <typename T, class V>
 MBT_HD T norm_obs(const StepParams<T> &p, T x, int d) {
+    if (V::norm == 0) return x;
     return p.normalise_obs ? (x - p.obs_low[d]) / p.obs_grad[d] - (T)1 : x;
 }
 

@@ -45,11 +45,8 @@ static REAL FN(orc_exp)(REAL x) {
 #endif
 }
 static REAL FN(orc_normal)(uint32_t bits) {
-#if ORC_IS_F64
-    return mbt_normal_from_bits_f64(bits);
-#else
-    return mbt_normal_from_bits_f32(bits);
-#endif
+    /* draw contract (include/mbt_philox.h): the float quantile in both precisions, widened for float64 */
+    return (REAL)mbt_normal_from_bits_f32(bits);
 }
 static REAL FN(orc_clip)(REAL x, REAL lo, REAL hi) { /* np.clip = minimum(maximum(x, lo), hi) */
     REAL y = x < lo ? lo : x;

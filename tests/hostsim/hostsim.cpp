@@ -12,9 +12,19 @@
 
 #include "../../mbt_gym_b200/csrc/mbt_host_params.h"
 
-using VariantAS = Variant<MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, -1>;
-using VariantHawkes = Variant<MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, -1>;
-using VariantOE = Variant<MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, -1>;
+/* the same specialisations mbt_capi.cu instantiates (MBT_FOR_EACH_VARIANT) */
+#define V_(d, m, a, i, r, n) Variant<d, m, a, i, r, n>
+#define HOSTSIM_VARIANTS(X)                                                                                  \
+    X(0, VariantGeneric)                                                                                     \
+    X(1, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_PNL, 0))                       \
+    X(2, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_CJ_MM, 0))                     \
+    X(3, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_RUNNING_INVENTORY_PENALTY, 0)) \
+    X(4, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, -1, -1))                               \
+    X(5, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, MBT_REW_PNL, 0))                        \
+    X(6, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, -1, -1))                                \
+    X(7, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, MBT_REW_CJ_OE, 0))                   \
+    X(8, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, MBT_REW_PNL, 0))                     \
+    X(9, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, -1, -1))
 
 template <typename T, class V>
 static void run(const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, double t_start, int q0_per_traj,
@@ -24,6 +34,7 @@ static void run(const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, 
     mbt_dims(&c, &A, &D, &S);
     const int64_t N = c.num_trajectories;
     StepParams<T> p = mbt_make_params<T>(c, t0, q0_per_traj, q0_uniform);
+    const mbt_philox_keys keys = mbt_philox_expand(seed);
     double t = t_start;
     for (int k = 0; k < steps; ++k) {
         const double t_next = t + c.step_size;
@@ -35,14 +46,14 @@ static void run(const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, 
             if (c.arrival == MBT_ARR_HAWKES) { s.x0 = row[4]; s.x1 = row[5]; }
             if (c.impact == MBT_IMP_TEMP_PERM) s.x0 = row[4];
             T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
-            for (int j = 0; j < A; ++j) a[j] = denorm_action(p, actions[((int64_t)k * N + i) * A + j], j);
-            mbt_u32x4 r = mbt_draw(seed, (uint64_t)(c.traj_offset + i), (uint64_t)(n_step0 + k), MBT_STREAM_STEP);
+            for (int j = 0; j < A; ++j) a[j] = denorm_action<T, V>(p, actions[((int64_t)k * N + i) * A + j], j);
+            mbt_u32x4 r = mbt_draw_keyed(keys, (uint64_t)(c.traj_offset + i), (uint64_t)(n_step0 + k), MBT_STREAM_STEP);
             int clipped = 0;
             T rw = step_one<T, V>(p, ck, s, a, r, q0_per_traj ? q0[i] : (T)q0_uniform, &clipped);
             row[0] = s.cash; row[1] = s.inv; row[2] = ck.t_next; row[3] = s.mid;
             if (c.arrival == MBT_ARR_HAWKES) { row[4] = s.x0; row[5] = s.x1; }
             if (c.impact == MBT_IMP_TEMP_PERM) row[4] = s.x0;
-            for (int d = 0; d < D; ++d) obs[((int64_t)k * N + i) * D + d] = norm_obs(p, row[d], d);
+            for (int d = 0; d < D; ++d) obs[((int64_t)k * N + i) * D + d] = norm_obs<T, V>(p, row[d], d);
             rew[(int64_t)k * N + i] = rw;
         }
         dones[k] = (uint8_t)ck.done;
@@ -54,11 +65,11 @@ template <typename T>
 static void dispatch(int variant, const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, double t_start,
                      int q0_per_traj, double q0_uniform, void *state, const void *q0, int steps, const void *actions,
                      void *obs, void *rew, uint8_t *dones) {
-#define GO(V) run<T, V>(c, seed, n_step0, t0, t_start, q0_per_traj, q0_uniform, (T *)state, (const T *)q0, steps, (const T *)actions, (T *)obs, (T *)rew, dones)
+#define GO(...) run<T, __VA_ARGS__>(c, seed, n_step0, t0, t_start, q0_per_traj, q0_uniform, (T *)state, (const T *)q0, steps, (const T *)actions, (T *)obs, (T *)rew, dones)
     switch (variant) {
-    case 1: GO(VariantAS); break;
-    case 2: GO(VariantHawkes); break;
-    case 3: GO(VariantOE); break;
+#define X(id, ...) case id: GO(__VA_ARGS__); break;
+        HOSTSIM_VARIANTS(X)
+#undef X
     default: GO(VariantGeneric); break;
     }
 #undef GO

@@ -32,14 +32,27 @@ def hostsim():
 
 
 def variant_of(cfg):
-    if cfg.dynamics == _abi.MBT_DYN_LIMIT and cfg.midprice == _abi.MBT_MID_BM and cfg.impact == _abi.MBT_IMP_NONE:
-        if cfg.arrival == _abi.MBT_ARR_POISSON:
-            return 1
-        if cfg.arrival == _abi.MBT_ARR_HAWKES:
-            return 2
-    if (cfg.dynamics == _abi.MBT_DYN_SPEED and cfg.midprice == _abi.MBT_MID_OU and cfg.impact == _abi.MBT_IMP_TEMP_PERM
-            and cfg.arrival == _abi.MBT_ARR_NONE):
-        return 3
+    """Mirror of variant_of() in mbt_gym_b200/csrc/mbt_capi.cu."""
+    A = _abi
+    plain = not (cfg.normalise_action or cfg.normalise_obs or cfg.normalise_rewards)
+    if cfg.dynamics == A.MBT_DYN_LIMIT and cfg.midprice == A.MBT_MID_BM and cfg.impact == A.MBT_IMP_NONE:
+        if cfg.arrival == A.MBT_ARR_POISSON:
+            if plain and cfg.reward == A.MBT_REW_PNL:
+                return 1
+            if plain and cfg.reward == A.MBT_REW_CJ_MM:
+                return 2
+            if plain and cfg.reward == A.MBT_REW_RUNNING_INVENTORY_PENALTY:
+                return 3
+            return 4
+        if cfg.arrival == A.MBT_ARR_HAWKES:
+            return 5 if (plain and cfg.reward == A.MBT_REW_PNL) else 6
+    if (cfg.dynamics == A.MBT_DYN_SPEED and cfg.midprice == A.MBT_MID_OU and cfg.impact == A.MBT_IMP_TEMP_PERM
+            and cfg.arrival == A.MBT_ARR_NONE):
+        if plain and cfg.reward == A.MBT_REW_CJ_OE:
+            return 7
+        if plain and cfg.reward == A.MBT_REW_PNL:
+            return 8
+        return 9
     return 0
 
 
