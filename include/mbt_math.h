@@ -67,9 +67,11 @@ MBT_HD double mbt_bits_f64(uint64_t u) {
 /* ------------------------------------------------------------------ exp, float */
 /* Cody-Waite reduction x = n*ln2 + r, |r| <= ln2/2, degree-5 minimax tail (the classic
  * Cephes single-precision coefficient set), scaled by 2^n through the exponent field. */
-MBT_HD float mbt_exp_f32(float x) {
-    if (!(x > -86.0f)) return (x != x) ? x : 0.0f;
-    if (x > 88.0f) return 3.402823466e38f;
+/* exp(x) * 2^k, k a small non-negative integer folded into the exponent add (free).  Branch-free: x is
+ * clamped to [-87, 88 - 0.7k] (exp(-87) = 1.6e-38 is the smallest value returned, the upper clamp keeps the
+ * scaled result finite; NaN is treated as -87). */
+MBT_HD float mbt_exp2k_f32(float x, int k) {
+    x = fminf(fmaxf(x, -87.0f), 88.0f - 0.7f * (float)k); /* upper clamp keeps exp(x)*2^k finite */
     const float magic = 12582912.0f; /* 1.5 * 2^23: adding it rounds to nearest integer */
     float t = fmaf(x, 1.44269504088896341f, magic);
     float n = t - magic;
@@ -83,9 +85,11 @@ MBT_HD float mbt_exp_f32(float x) {
     p = fmaf(p, r, 5.0000001201e-1f);
     float r2 = r * r;
     float y = fmaf(p, r2, r) + 1.0f;
-    int32_t ni = (int32_t)n;
-    return mbt_bits_f32(mbt_f32_bits(y) + ((uint32_t)ni << 23));
+    /* n is an integer in [-126, 127]: the low bits of t hold it (t = 1.5*2^23 + n exactly) */
+    int32_t ni = (int32_t)(mbt_f32_bits(t) & 0x007FFFFFu) - 0x00400000;
+    return mbt_bits_f32(mbt_f32_bits(y) + ((uint32_t)(ni + k) << 23));
 }
+MBT_HD float mbt_exp_f32(float x) { return mbt_exp2k_f32(x, 0); }
 
 /* ------------------------------------------------------------------ log, float */
 /* x = m * 2^e, m in [sqrt(1/2), sqrt(2)); log(m) by the Cephes degree-8 polynomial in
@@ -99,6 +103,37 @@ MBT_HD float mbt_log_f32(float x) {
         b = mbt_f32_bits(x * 8388608.0f);
         e = (int32_t)(b >> 23) - 126 - 23;
     }
+    float m = mbt_bits_f32((b & 0x007FFFFFu) | 0x3F000000u); /* [0.5, 1) */
+    float f;
+    if (m < 0.707106781186547524f) {
+        e -= 1;
+        f = (m + m) - 1.0f;
+    } else {
+        f = m - 1.0f;
+    }
+    float z = f * f;
+    float p = 7.0376836292e-2f;
+    p = fmaf(p, f, -1.1514610310e-1f);
+    p = fmaf(p, f, 1.1676998740e-1f);
+    p = fmaf(p, f, -1.2420140846e-1f);
+    p = fmaf(p, f, 1.4249322787e-1f);
+    p = fmaf(p, f, -1.6668057665e-1f);
+    p = fmaf(p, f, 2.0000714765e-1f);
+    p = fmaf(p, f, -2.4999993993e-1f);
+    p = fmaf(p, f, 3.3333331174e-1f);
+    float fe = (float)e;
+    float y = (p * f) * z;
+    y = fmaf(fe, -2.12194440e-4f, y);
+    y = fmaf(z, -0.5f, y);
+    float res = f + y;
+    return fmaf(fe, 0.693359375f, res);
+}
+
+/* log(x) for x known to be a positive NORMAL float (no zero / negative / subnormal handling): the argument of the
+ * normal quantile below is always in [2^-32, 1]. Same arithmetic as mbt_log_f32 on that domain. */
+MBT_HD float mbt_log_pn_f32(float x) {
+    uint32_t b = mbt_f32_bits(x);
+    int32_t e = (int32_t)(b >> 23) - 126;
     float m = mbt_bits_f32((b & 0x007FFFFFu) | 0x3F000000u); /* [0.5, 1) */
     float f;
     if (m < 0.707106781186547524f) {
@@ -146,9 +181,8 @@ MBT_TABLE(mbt_exp64_c, 12, 1.6059043836821614599e-10, 2.0876756987868098979e-9, 
           2.7557319223985890653e-7, 2.7557319223985890653e-6, 2.4801587301587301587e-5, 1.9841269841269841270e-4,
           1.3888888888888888889e-3, 8.3333333333333333333e-3, 4.1666666666666666667e-2, 1.6666666666666666667e-1, 0.5)
 
-MBT_HD double mbt_exp_f64(double x) {
-    if (!(x > -700.0)) return (x != x) ? x : 0.0;
-    if (x > 700.0) return 1.7976931348623157e308;
+MBT_HD double mbt_exp2k_f64(double x, int k) {
+    x = fmin(fmax(x, -700.0), 700.0 - 0.7 * (double)k); /* branch-free clamp; NaN is treated as -700 */
     const double magic = 6755399441055744.0; /* 1.5 * 2^52 */
     double t = fma(x, 1.4426950408889634074, magic);
     double n = t - magic;
@@ -158,13 +192,14 @@ MBT_HD double mbt_exp_f64(double x) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int k = 1; k < 12; ++k) p = fma(p, r, MBT_T(mbt_exp64_c)[k]);
+    for (int j = 1; j < 12; ++j) p = fma(p, r, MBT_T(mbt_exp64_c)[j]);
     double r2 = r * r;
     double y = fma(p, r2, r) + 1.0;
     /* n is an integer in [-1010, 1010]: the low word of t holds it in two's complement */
     int32_t ni = (int32_t)(uint32_t)mbt_f64_bits(t);
-    return mbt_bits_f64(mbt_f64_bits(y) + ((uint64_t)(int64_t)ni << 52));
+    return mbt_bits_f64(mbt_f64_bits(y) + ((uint64_t)(int64_t)(ni + k) << 52));
 }
+MBT_HD double mbt_exp_f64(double x) { return mbt_exp2k_f64(x, 0); }
 
 /* ------------------------------------------------------------------ log, double */
 /* log(m) = 2*atanh(s), s = f/(2+f), odd series to s^23 (|s| <= 0.1716 -> trunc < 2e-19). */
@@ -221,7 +256,7 @@ MBT_HD float mbt_normal_from_bits_f32(uint32_t bits) {
     uint32_t mc = 0x7FFFFFFFu - (bits & 0x7FFFFFFFu);
     float t = fmaf((float)mc, 4.656612873077392578125e-10f /* 2^-31 */, 2.3283064365386962890625e-10f /* 2^-32 */);
     float v = 1.0f - t;
-    float w = -mbt_log_f32(t * (2.0f - t));
+    float w = -mbt_log_pn_f32(t * (2.0f - t));
     float p;
     if (w < 5.0f) {
         w = w - 2.5f;
@@ -342,11 +377,15 @@ MBT_HD double mbt_normal_from_bits_f64(uint32_t bits) {
 /* 24-bit integer -> the uniform k * 2^-24 in [0,1), exactly, in either precision.  On the device the double
  * version avoids the slow I2F.F64 unit: OR the integer into the mantissa of 2^52 and subtract 2^52. */
 MBT_HD float mbt_u24_to_unit_f32(uint32_t k) { return (float)k * 5.9604644775390625e-08f; }
-MBT_HD double mbt_u24_to_unit_f64(uint32_t k) {
+MBT_HD double mbt_u24_to_unit_f64(uint32_t k) { return (double)k * 5.9604644775390625e-08; }
+/* the integer itself as a real (exact): the kernels compare  k < p * 2^24  instead of  k * 2^-24 < p  -- the same
+ * predicate, since scaling by a power of two is exact -- with the 2^24 folded into p for free */
+MBT_HD float mbt_u24_to_real_f32(uint32_t k) { return (float)k; }
+MBT_HD double mbt_u24_to_real_f64(uint32_t k) {
 #if defined(__CUDA_ARCH__)
-    return (__hiloint2double(0x43300000, (int)k) - 4503599627370496.0) * 5.9604644775390625e-08;
+    return __hiloint2double(0x43300000, (int)k) - 4503599627370496.0; /* no I2F.F64 */
 #else
-    return (double)k * 5.9604644775390625e-08;
+    return (double)k;
 #endif
 }
 

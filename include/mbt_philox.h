@@ -140,7 +140,11 @@ MBT_HD mbt_u32x4 mbt_draw(uint64_t seed, uint64_t traj, uint64_t n, uint32_t str
 MBT_HD uint32_t mbt_uniform_bits24(uint32_t word) { return word >> 8; }
 
 MBT_HD uint32_t mbt_normal_bits(mbt_u32x4 r) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(__byte_perm(r.x, r.y, 0x0040), __byte_perm(r.z, r.w, 0x0040), 0x5410); /* 3 PRMT */
+#else
     return (r.x & 0xFFu) | ((r.y & 0xFFu) << 8) | ((r.z & 0xFFu) << 16) | ((r.w & 0xFFu) << 24);
+#endif
 }
 
 #endif /* MBT_PHILOX_H */

@@ -46,6 +46,7 @@ struct mbt_env {
     mbt_config cfg;
     int device = 0;
     int A = 0, D = 0, S = 0;
+    int sm_count = 1;
     size_t esz = 8;
     long long N = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -148,12 +149,32 @@ static void par_memcpy(void *dst, const void *src, size_t bytes) {
 }
 
 /* ------------------------------------------------------------------ launchers */
+/* blocks of MBT_BLOCK threads resident per SM for one kernel instantiation (queried once) */
+template <typename K>
+static int resident_blocks_per_sm(K kernel) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, MBT_BLOCK, 0) != cudaSuccess || nb < 1) {
+        cudaGetLastError();
+        nb = 1;
+    }
+    return nb;
+}
+
+/* single-wave grid: never more blocks than the device holds at once (the kernel loops over tiles) */
+template <typename T, class V, bool VEC>
+static void launch_step_k(mbt_env *e, const StepArgs<T> &g) {
+    static const int per_sm = resident_blocks_per_sm(mbt_step_kernel<T, V, VEC>);
+    const long long resident = (long long)per_sm * e->sm_count;
+    const unsigned grid = (unsigned)std::min<long long>(grid_for(g.n), resident);
+    mbt_step_kernel<T, V, VEC><<<grid, MBT_BLOCK, 0, e->stream>>>(g);
+}
+
 template <typename T, class V>
 static void launch_step_v(mbt_env *e, const StepArgs<T> &g, bool vec) {
     if (vec)
-        mbt_step_kernel<T, V, true><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
+        launch_step_k<T, V, true>(e, g);
     else
-        mbt_step_kernel<T, V, false><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
+        launch_step_k<T, V, false>(e, g);
 }
 
 /*
@@ -427,6 +448,7 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
             return bail(_e == cudaErrorMemoryAllocation ? MBT_E_NOMEM : MBT_E_CUDA);                      \
         }                                                                                                 \
     } while (0)
+    CUB(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUB(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
     CUB(cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking));

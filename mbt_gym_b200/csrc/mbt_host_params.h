@@ -104,6 +104,12 @@ static inline StepParams<T> mbt_make_params(const mbt_config &c, double t0, int 
         p.p_arr[0] = (T)(1.0 - mbt_exp_f64(-c.arr_rate[0] * c.arr_step));
         p.p_arr[1] = (T)(1.0 - mbt_exp_f64(-c.arr_rate[1] * c.arr_step));
     }
+    for (int j = 0; j < 2; ++j) { /* k*2^-24 < p  <=>  k < ceil(p*2^24), k integer in [0, 2^24) */
+        double scaled = std::ceil((double)p.p_arr[j] * 16777216.0);
+        p.arr_thr[j] = scaled <= 0.0 ? 0u : (scaled >= 16777216.0 ? 16777216u : (uint32_t)scaled);
+        if (!((double)p.p_arr[j] == (double)p.p_arr[j])) p.arr_thr[j] = 0u; /* NaN: never */
+    }
+    p.arr_step_2p24 = (T)c.arr_step * (T)16777216.0;
     p.arr_step = (T)c.arr_step; p.arr_rate[0] = (T)c.arr_rate[0]; p.arr_rate[1] = (T)c.arr_rate[1];
     p.hawkes_speed = (T)c.hawkes_speed; p.hawkes_jump = (T)c.hawkes_jump;
     p.neg_kappa = -(T)c.fill_exponent;

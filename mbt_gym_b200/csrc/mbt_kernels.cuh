@@ -156,13 +156,10 @@ __device__ __forceinline__ void store_traj(const StepParams<T> &p, const DevStat
 }
 
 /* ------------------------------------------------------------------ step */
-/* VEC: the caller's action/obs pointers are aligned for whole-row vector access. */
+/* One trajectory, one env-step: load state + action row, draw, advance, store state + observation row + reward. */
 template <typename T, class V, bool VEC>
-__global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_constant__ StepArgs<T> g) {
-    const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
-    if (i >= g.n) return;
+__device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i) {
     const StepParams<T> &p = g.p;
-
     const int A = action_width<T, V>(p);
     T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
     load_row<T>(g.actions, i, A, a, VEC);
@@ -188,6 +185,25 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_consta
     }
     if (g.rew) g.rew[i] = rwd;
     if (clipped) atomicAdd(g.clipped, 1ull);
+}
+
+/*
+ * Persistent warp-tile loop.  The launch puts exactly as many blocks on the GPU as are resident at once
+ * (SM count x occupancy, a single wave), and every warp walks tiles of 32 consecutive trajectories with a grid
+ * stride.  All SMs then carry the same number of tiles (+-1) and finish together: with one thread per trajectory
+ * and 2^20 trajectories the launch was 3.46 waves and the SMs sat idle for a quarter of the kernel (profiles/).
+ * VEC: the caller's action/obs pointers are aligned for whole-row vector access.
+ */
+template <typename T, class V, bool VEC>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_constant__ StepArgs<T> g) {
+    constexpr int WARPS = MBT_BLOCK / 32;
+    const long long n_tiles = (g.n + 31) >> 5;
+    const long long stride = (long long)gridDim.x * WARPS;
+    const unsigned lane = threadIdx.x & 31u;
+    for (long long tile = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); tile < n_tiles; tile += stride) {
+        const long long i = (tile << 5) + lane;
+        if (i < g.n) step_row<T, V, VEC>(g, i);
+    }
 }
 
 /* ------------------------------------------------------------------ reset */

@@ -38,8 +38,10 @@ MBT_HD float mbt_exp_t(float x) { return mbt_exp_f32(x); }
 MBT_HD double mbt_exp_t(double x) { return mbt_exp_f64(x); }
 MBT_HD float mbt_pow_t(float x, float p) { return mbt_pow_f32(x, p); }
 MBT_HD double mbt_pow_t(double x, double p) { return mbt_pow_f64(x, p); }
-MBT_HD void mbt_unit_t(uint32_t k, float *u) { *u = mbt_u24_to_unit_f32(k); }
-MBT_HD void mbt_unit_t(uint32_t k, double *u) { *u = mbt_u24_to_unit_f64(k); }
+MBT_HD float mbt_exp2k_t(float x, int k) { return mbt_exp2k_f32(x, k); }
+MBT_HD double mbt_exp2k_t(double x, int k) { return mbt_exp2k_f64(x, k); }
+MBT_HD void mbt_real_t(uint32_t k, float *u) { *u = mbt_u24_to_real_f32(k); }
+MBT_HD void mbt_real_t(uint32_t k, double *u) { *u = mbt_u24_to_real_f64(k); }
 
 /*
  * Uniform (per-episode) quantities, already in the arithmetic type T.  Built on the host by
@@ -59,7 +61,8 @@ struct StepParams {
     T qmax, cmax;
 
     T p_arr[2];  /* Poisson: intensity*step_size ; NonLinear: 1-exp(-intensity*step_size) */
-    T arr_step, arr_rate[2], hawkes_speed, hawkes_jump;
+    uint32_t arr_thr[2]; /* ceil(p_arr * 2^24) clamped to [0, 2^24]:  k*2^-24 < p_arr  <=>  k < arr_thr */
+    T arr_step, arr_step_2p24 /* arr_step * 2^24 */, arr_rate[2], hawkes_speed, hawkes_jump;
     T neg_kappa; /* -fill_exponent */
     T drift_dt, vol_sqdt, sqdt, mid_drift, mid_vol, mid_step, ou_neg_speed, ou_level;
     T imp_temp, imp_perm, imp_exp, imp_step, half_spread;
@@ -122,18 +125,19 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
 
     if (dyn != MBT_DYN_SPEED) {
         /* get_arrivals_and_fills                                    ModelDynamics.py:127-131,169-172 */
-        T pb, pa, ub, ua;
+        /* every "unif < p" below is evaluated as  k < p * 2^24  on the 24-bit integer k of the draw: the same
+         * predicate as  k * 2^-24 < p  (power-of-two scaling is exact), minus a multiply per uniform */
+        const uint32_t kb = mbt_uniform_bits24(r.x), ka = mbt_uniform_bits24(r.y);
         if (arr_kind == MBT_ARR_HAWKES) { /* unif < lambda_t * step   arrival_models.py:121-123 */
-            pb = s.x0 * p.arr_step;
-            pa = s.x1 * p.arr_step;
-        } else { /* arrival_models.py:54-56,81-83 */
-            pb = p.p_arr[0];
-            pa = p.p_arr[1];
+            T ub, ua;
+            mbt_real_t(kb, &ub);
+            mbt_real_t(ka, &ua);
+            arr_b = (ub < s.x0 * p.arr_step_2p24) ? (T)1 : (T)0;
+            arr_a = (ua < s.x1 * p.arr_step_2p24) ? (T)1 : (T)0;
+        } else { /* unif < p, p uniform over the batch   arrival_models.py:54-56,81-83 */
+            arr_b = (kb < p.arr_thr[0]) ? (T)1 : (T)0;
+            arr_a = (ka < p.arr_thr[1]) ? (T)1 : (T)0;
         }
-        mbt_unit_t(mbt_uniform_bits24(r.x), &ub);
-        mbt_unit_t(mbt_uniform_bits24(r.y), &ua);
-        arr_b = (ub < pb) ? (T)1 : (T)0;
-        arr_a = (ua < pa) ? (T)1 : (T)0;
         T fil_b, fil_a, off_b, off_a;
         if (dyn == MBT_DYN_AT_TOUCH) { /* fills = action[:, 0:2]      ModelDynamics.py:157-158,171 */
             fil_b = a[0];
@@ -142,10 +146,10 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
             off_a = p.half_spread;
         } else { /* unif < exp(-kappa*depth)   fill_probability_models.py:28-34,57-58 */
             T vb, va;
-            mbt_unit_t(mbt_uniform_bits24(r.z), &vb);
-            mbt_unit_t(mbt_uniform_bits24(r.w), &va);
-            fil_b = (vb < mbt_exp_t(p.neg_kappa * a[0])) ? (T)1 : (T)0;
-            fil_a = (va < mbt_exp_t(p.neg_kappa * a[1])) ? (T)1 : (T)0;
+            mbt_real_t(mbt_uniform_bits24(r.z), &vb);
+            mbt_real_t(mbt_uniform_bits24(r.w), &va);
+            fil_b = (vb < mbt_exp2k_t(p.neg_kappa * a[0], 24)) ? (T)1 : (T)0;
+            fil_a = (va < mbt_exp2k_t(p.neg_kappa * a[1], 24)) ? (T)1 : (T)0;
             off_b = a[0];
             off_a = a[1];
         }

@@ -23,7 +23,7 @@ def _ulp_err(got, want, eps):
 
 def test_exp_log_accuracy_vs_libm():
     rng = np.random.default_rng(0)
-    x = rng.uniform(-86, 88, 400_000).astype(np.float32)
+    x = rng.uniform(-87, 88, 400_000).astype(np.float32)
     assert _ulp_err(O.vec("exp_f32", x), np.exp(x.astype(np.float64)), 2.0 ** -24) < 2.0
     x = np.exp(rng.uniform(-80, 80, 400_000)).astype(np.float32)
     assert _ulp_err(O.vec("log_f32", x), np.log(x.astype(np.float64)), 2.0 ** -24) < 2.0
@@ -31,9 +31,11 @@ def test_exp_log_accuracy_vs_libm():
     assert _ulp_err(O.vec("exp_f64", x), np.exp(x), 2.0 ** -53) < 4.0
     x = np.exp(rng.uniform(-700, 700, 400_000))
     assert _ulp_err(O.vec("log_f64", x), np.log(x), 2.0 ** -53) < 4.0
-    # range ends
-    assert O.vec("exp_f32", np.array([-100.0, 100.0], np.float32)).tolist() == [0.0, np.finfo(np.float32).max]
-    assert O.vec("exp_f64", np.array([-1000.0]))[0] == 0.0
+    # range ends: branch-free clamp to [-87, 88] / [-700, 700]; NaN counts as the lower end
+    ends = O.vec("exp_f32", np.array([-100.0, -87.0, 88.0, 100.0, np.nan], np.float32))
+    assert ends[0] == ends[1] == ends[4] and ends[2] == ends[3] and 1e-38 < ends[0] < 2e-38 and ends[2] > 1e38
+    ends = O.vec("exp_f64", np.array([-1000.0, -700.0, 700.0, 1000.0]))
+    assert ends[0] == ends[1] and ends[2] == ends[3] and ends[0] < 1e-300 and ends[2] > 1e300
 
 
 def test_pow_matches_numpy_fast_paths():
