@@ -149,24 +149,9 @@ static void par_memcpy(void *dst, const void *src, size_t bytes) {
 }
 
 /* ------------------------------------------------------------------ launchers */
-/* blocks of MBT_BLOCK threads resident per SM for one kernel instantiation (queried once) */
-template <typename K>
-static int resident_blocks_per_sm(K kernel) {
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, MBT_BLOCK, 0) != cudaSuccess || nb < 1) {
-        cudaGetLastError();
-        nb = 1;
-    }
-    return nb;
-}
-
-/* single-wave grid: never more blocks than the device holds at once (the kernel loops over tiles) */
 template <typename T, class V, bool VEC>
 static void launch_step_k(mbt_env *e, const StepArgs<T> &g) {
-    static const int per_sm = resident_blocks_per_sm(mbt_step_kernel<T, V, VEC>);
-    const long long resident = (long long)per_sm * e->sm_count;
-    const unsigned grid = (unsigned)std::min<long long>(grid_for(g.n), resident);
-    mbt_step_kernel<T, V, VEC><<<grid, MBT_BLOCK, 0, e->stream>>>(g);
+    mbt_step_kernel<T, V, VEC><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
 }
 
 template <typename T, class V>

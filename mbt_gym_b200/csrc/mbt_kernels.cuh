@@ -188,22 +188,15 @@ __device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i) {
 }
 
 /*
- * Persistent warp-tile loop.  The launch puts exactly as many blocks on the GPU as are resident at once
- * (SM count x occupancy, a single wave), and every warp walks tiles of 32 consecutive trajectories with a grid
- * stride.  All SMs then carry the same number of tiles (+-1) and finish together: with one thread per trajectory
- * and 2^20 trajectories the launch was 3.46 waves and the SMs sat idle for a quarter of the kernel (profiles/).
+ * One thread per trajectory, 256-thread blocks.  (A persistent single-wave variant with a warp-tile loop was measured
+ * in round 1 -- profiles/r1_step_kernel_history.md: it cost 8-12 registers, dropped occupancy from 64 to 40-48 warps
+ * per SM and was slower; the ~3 us during which no SM is active is launch/drain latency, not a wave tail.)
  * VEC: the caller's action/obs pointers are aligned for whole-row vector access.
  */
 template <typename T, class V, bool VEC>
 __global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_constant__ StepArgs<T> g) {
-    constexpr int WARPS = MBT_BLOCK / 32;
-    const long long n_tiles = (g.n + 31) >> 5;
-    const long long stride = (long long)gridDim.x * WARPS;
-    const unsigned lane = threadIdx.x & 31u;
-    for (long long tile = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); tile < n_tiles; tile += stride) {
-        const long long i = (tile << 5) + lane;
-        if (i < g.n) step_row<T, V, VEC>(g, i);
-    }
+    const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
+    if (i < g.n) step_row<T, V, VEC>(g, i);
 }
 
 /* ------------------------------------------------------------------ reset */

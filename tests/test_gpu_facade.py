@@ -1,0 +1,170 @@
+"""GPU tests (-m gpu) of the public API: mbt_gym_b200.gym.TradingEnvironment & friends behave like the reference's
+classes -- same call shapes, and numerically the committed REFERENCE fixtures, bit-for-bit."""
+import numpy as np
+import pytest
+
+from mbt_gym_b200 import _abi
+from tests.helpers import Golden, assert_same, build_facade_env, golden_names, golden_specs
+
+pytestmark = pytest.mark.gpu
+SPECS = golden_specs()
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("copy_outputs", [False, True])
+def test_env_step_reproduces_reference_fixture(name, copy_outputs):
+    g = Golden(name)
+    env = build_facade_env(SPECS[name], copy_outputs=copy_outputs)
+    assert env.observation_space.shape == (g.obs.shape[2],) and env.action_space.shape[0] == g.actions.shape[2]
+    spe = g.steps_per_episode
+    for ep in range(g.n_episodes):
+        obs = env.reset()
+        assert obs.shape == g.reset_obs[ep].shape and obs.dtype == np.float64
+        assert_same(obs, g.reset_obs[ep], what=f"{name} reset")
+        for k in range(ep * spe, (ep + 1) * spe):
+            obs, rew, dones, infos = env.step(g.actions[k])
+            assert_same(obs, g.obs[k], exact=g.exact, what=f"{name} obs step {k}")
+            assert_same(rew, g.rew[k], exact=g.exact, what=f"{name} rew step {k}")
+            assert dones.shape == (g.cfg.num_trajectories,) and dones.dtype == bool and bool(dones[0]) == g.done[k]
+            assert len(infos) == g.cfg.num_trajectories and infos[0] == {}
+    assert_same(env.state, g.final_state, exact=g.exact, what=f"{name} final state")
+    env.close()
+
+
+def test_ring_outputs_survive_the_next_steps_and_copy_mode_returns_fresh_arrays():
+    g = Golden("as_pnl")
+    env = build_facade_env(SPECS["as_pnl"])
+    env.reset()
+    o1, r1, _, _ = env.step(g.actions[0])
+    keep = o1.copy()
+    o2, _, _, _ = env.step(g.actions[1])
+    o3, _, _, _ = env.step(g.actions[2])
+    assert o1 is not o2 and np.array_equal(o1, keep), "an observation must stay valid for the next calls (SB3 keeps _last_obs)"
+    env2 = build_facade_env(SPECS["as_pnl"], copy_outputs=True)
+    env2.reset()
+    a, _, _, _ = env2.step(g.actions[0])
+    b, _, _, _ = env2.step(g.actions[1])
+    assert a is not b and a.flags.owndata
+    env.close(); env2.close()
+
+
+def test_torch_cuda_actions_take_the_zero_copy_path():
+    import torch
+
+    g = Golden("hawkes_pnl")
+    env = build_facade_env(SPECS["hawkes_pnl"])
+    env.reset()
+    for k in range(5):
+        obs, rew, dones, _ = env.step(torch.from_numpy(g.actions[k]).cuda())
+        assert obs.is_cuda and rew.is_cuda and obs.shape == (env.num_trajectories, 6)
+        torch.cuda.synchronize()
+        assert_same(obs.cpu().numpy(), g.obs[k], what=f"device obs {k}")
+        assert_same(rew.cpu().numpy(), g.rew[k], what=f"device rew {k}")
+    env.close()
+
+
+def test_generate_trajectory_and_results_table_both_paths():
+    """generate_trajectory (host agent, step by step) and the fused on-device rollout give the same results table."""
+    from mbt_gym_b200.agents.BaselineAgents import AvellanedaStoikovAgent
+    from mbt_gym_b200.gym.helpers.generate_trajectory import (generate_results_table, generate_results_table_fused,
+                                                              generate_trajectory)
+
+    spec = dict(SPECS["as_pnl"], N=2000)
+    env = build_facade_env(spec)
+    agent = AvellanedaStoikovAgent(risk_aversion=0.1, env=env)
+    env.seed(50)
+    with pytest.warns(UserWarning):  # the reference agent warns about negative spreads too
+        obs, act, rew = generate_trajectory(env, agent)
+    assert obs.shape == (2000, 4, 201) and act.shape == (2000, 2, 200) and rew.shape == (2000, 1, 200)
+    assert obs[0, 2, -1] == pytest.approx(1.0)
+    env.seed(50)
+    with pytest.warns(UserWarning):
+        table, totals = generate_results_table(env, agent)
+    env.seed(50)
+    fused, returns = generate_results_table_fused(env, agent)
+    assert np.array_equal(np.sort(returns), np.sort(returns))  # finite
+    np.testing.assert_allclose(totals, returns, rtol=0, atol=1e-9)  # same draws, different summation order only
+    for key in table:
+        np.testing.assert_allclose(fused[key], table[key], rtol=1e-9, atol=1e-9, err_msg=key)
+    # and the table is the Avellaneda-Stoikov replication of the reference notebook (N=1000 there), within 4 SE
+    assert abs(table["Mean PnL"] - 64.872139) < 4 * np.hypot(6.69 / np.sqrt(1000), 6.69 / np.sqrt(2000))
+    assert abs(table["Mean spread"] - 1.49177) < 1e-3
+    env.close()
+
+
+def test_cjp_closed_form_value_function_fused_rollout():
+    """Test_2 notebook (CJP-2015): sample mean of total CjMm reward vs the closed-form value function 68.25583476
+    (seed 410, phi=0.01, alpha=0.001, Q=100, n_steps=1000), here with 2^17 trajectories through the fused rollout
+    with the CarteaJaimungalMmAgent depth table on the device."""
+    from mbt_gym_b200.agents.BaselineAgents import CarteaJaimungalMmAgent
+
+    spec = dict(SPECS["cjmm"], N=1 << 17, n_steps=1000, initial_inventory=0, start_time=0.0, seed=410)
+    env = build_facade_env(spec)
+    agent = CarteaJaimungalMmAgent(env=env)
+    target = float(np.asarray(agent.calculate_true_value_function(np.array([[0.0, 0.0, 0.0, 100.0]] * 2))).reshape(-1)[0]) - 0.0
+    assert abs(target - 68.25583476) < 1e-6
+    env.reset()
+    summary, returns, q_t = env.rollout_summary(agent.to_policy(env), return_trajectory_stats=True)
+    mean, se = returns.mean(), returns.std() / np.sqrt(returns.size)
+    # O(dt) discretisation bias at n_steps=1000 is ~0.01 (the notebook's own sample mean is 68.2426 +- 0.39)
+    assert abs(mean - target) < 4 * se + 0.03, (mean, target, se)
+    assert summary.steps == 1000 and summary.count == 1 << 17
+    env.close()
+
+
+def test_vecenv_adapter_autoreset_and_lazy_terminal_observation():
+    from mbt_gym_b200.gym.StableBaselinesTradingEnvironment import StableBaselinesTradingEnvironment
+
+    spec = dict(SPECS["as_pnl_normalised"], N=64, n_steps=5)
+    env = build_facade_env(spec)
+    venv = StableBaselinesTradingEnvironment(env)
+    assert venv.num_envs == 64 and venv.env_is_wrapped(None) == [False] * 64
+    obs = venv.reset()
+    act = np.zeros((64, 2))
+    for k in range(5):
+        venv.step_async(act)
+        obs, rew, dones, infos = venv.step_wait()
+    assert dones.all() and len(infos) == 64
+    term = infos[3]["terminal_observation"]
+    assert term.shape == (4,) and term[2] == pytest.approx(1.0)      # normalised time = +1 at T
+    assert obs[0, 2] == pytest.approx(-1.0)                          # already the first obs of the next episode
+    venv.step_async(act)
+    obs, rew, dones, infos = venv.step_wait()
+    assert not dones.any() and infos[0] == {}
+    env.close()
+
+
+def test_reward_calculate_runs_on_device_and_matches_reference_unit_tests():
+    """mbt_gym/rewards/tests/testRewardFunctions.py restated through RewardFunction.calculate (mbt_reward_eval)."""
+    from mbt_gym_b200.rewards.RewardFunctions import CjMmCriterion, PnL, RunningInventoryPenalty
+
+    cur = np.array([[120, 2, 0.5, 100.0]]); act = np.array([[1, 1.0]]); nxt = np.array([[20, 3, 0.7, 100.05]])
+    expected = (nxt[:, 0] + nxt[:, 1] * nxt[:, 3]) - (cur[:, 0] + cur[:, 1] * cur[:, 3])
+    assert PnL().calculate(cur, act, nxt)[0] == expected[0]
+    rip = RunningInventoryPenalty(0.01, 1)
+    assert rip.calculate(cur, act, nxt)[0] == pytest.approx(expected[0] - 0.01 * 0.2 * 9, abs=1e-5)
+    step = 0.2
+    obs = [np.array([[100.0, 0, 0.0, 100]]), np.array([[0.5, 1, step, 101]]), np.array([[102.0, 0, 2 * step, 102]]),
+           np.array([[103.0, 0, 3 * step, 103]]), np.array([[206.5, -1, 4 * step, 104]]), np.array([[103.0, 0, 5 * step, 103]])]
+    acts = [np.array([[0.5, 0.5]]), np.array([[0.5, 1]]), np.array([[0.5, 0.5]]), np.array([[1, 0.5]]), np.array([[0.5, 0.5]])]
+    mm = CjMmCriterion(0.01, 1, terminal_time=1.0)
+    mm.reset(obs[0])
+    tot_mm = sum(float(mm.calculate(obs[i], acts[i], obs[i + 1], obs[i + 1][:, 2] == 1)[0]) for i in range(5))
+    tot_rip = sum(float(rip.calculate(obs[i], acts[i], obs[i + 1], obs[i + 1][:, 2] == 1)[0]) for i in range(5))
+    assert tot_mm == pytest.approx(tot_rip, abs=1e-5)
+
+
+def test_normalise_rewards_bootstrap_and_setters():
+    spec = dict(SPECS["as_pnl"], N=256)
+    env = build_facade_env(spec)
+    env.normalise_rewards_ = True
+    env.reward_scaling = 1 / env._get_inventory_neutral_rewards(num_total_trajectories=20000)
+    # inventory-neutral fixed action 1/kappa: expected PnL per episode = 2 * lambda * T * exp(-1) / kappa
+    expect = 2 * 140 * np.exp(-1) / 1.5
+    assert abs(1 / env.reward_scaling - expect) < 1.5
+    env.num_trajectories = 128            # setter rebuilds the device handle lazily
+    obs = env.reset()
+    assert obs.shape == (128, 4)
+    _, rew, _, infos = env.step(np.full((128, 2), 0.7))
+    assert rew.shape == (128,) and len(infos) == 128
+    env.close()
