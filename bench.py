@@ -37,38 +37,41 @@ L2_BYTES = 126e6
 WORKLOADS = ("as", "cjmm", "hawkes", "oe")
 
 
-def make_config(workload, precision, n_local, traj_offset):
-    """BASELINE.json configs[1..4] as mbt_config (SURVEY.md 8d synthetic inputs)."""
-    from mbt_gym_b200 import _abi
+def make_env(workload, precision, n_local, traj_offset, device):
+    """BASELINE.json configs[1..4] through the PUBLIC API (SURVEY.md 8d synthetic inputs), normalisation off."""
+    from mbt_gym_b200.gym.ModelDynamics import LimitOrderModelDynamics, TradinghWithSpeedModelDynamics
+    from mbt_gym_b200.gym.TradingEnvironment import TradingEnvironment
+    from mbt_gym_b200.rewards.RewardFunctions import CjMmCriterion, CjOeCriterion, PnL
+    from mbt_gym_b200.stochastic_processes.arrival_models import HawkesArrivalModel, PoissonArrivalModel
+    from mbt_gym_b200.stochastic_processes.fill_probability_models import ExponentialFillFunction
+    from mbt_gym_b200.stochastic_processes.midprice_models import BrownianMotionMidpriceModel, OuMidpriceModel
+    from mbt_gym_b200.stochastic_processes.price_impact_models import TemporaryAndPermanentPriceImpact
 
-    n_steps, T = 200, 1.0
+    n_steps, T, N = 200, 1.0, n_local
     dt = T / n_steps
-    common = dict(precision=precision, num_trajectories=n_local, traj_offset=traj_offset, n_steps=n_steps,
-                  terminal_time=T, step_size=dt, rew_terminal_time=T, mid_initial=100.0, mid_vol=2.0, mid_step=dt)
-    s_max = 100.0 + 4 * 2.0 * np.sqrt(T)
+    kw = dict(terminal_time=T, n_steps=n_steps, seed=1234, num_trajectories=N, normalise_action_space=False,
+              normalise_observation_space=False, precision=precision, device=device, traj_offset=traj_offset)
     if workload in ("as", "cjmm", "hawkes"):
-        cfg = _abi.new_config(dynamics=_abi.MBT_DYN_LIMIT, midprice=_abi.MBT_MID_BM, fill=_abi.MBT_FILL_EXPONENTIAL,
-                              fill_exponent=1.5, arr_step=dt, max_inventory=200.0, max_cash=n_steps * s_max, **common)
+        mid = BrownianMotionMidpriceModel(volatility=2.0, initial_price=100.0, terminal_time=T, step_size=dt, num_trajectories=N)
         if workload == "hawkes":
-            cfg.arrival = _abi.MBT_ARR_HAWKES
-            cfg.arr_rate[0] = cfg.arr_rate[1] = 10.0
-            cfg.hawkes_jump, cfg.hawkes_speed = 40.0, 60.0
+            arr = HawkesArrivalModel(baseline_arrival_rate=np.array([[10.0, 10.0]]), step_size=dt, jump_size=40.0,
+                                     mean_reversion_speed=60.0, terminal_time=T, num_trajectories=N)
         else:
-            cfg.arrival = _abi.MBT_ARR_POISSON
-            cfg.arr_rate[0] = cfg.arr_rate[1] = 140.0
+            arr = PoissonArrivalModel(intensity=np.array([140.0, 140.0]), step_size=dt, num_trajectories=N)
+        fill = ExponentialFillFunction(fill_exponent=1.5, step_size=dt, num_trajectories=N)
+        dyn = LimitOrderModelDynamics(midprice_model=mid, arrival_model=arr, fill_probability_model=fill, num_trajectories=N)
         if workload == "cjmm":
-            cfg.reward = _abi.MBT_REW_CJ_MM
-            cfg.rew_phi, cfg.rew_alpha, cfg.max_inventory = 0.01, 0.001, 100.0
-        else:
-            cfg.reward = _abi.MBT_REW_PNL
-    elif workload == "oe":
-        cfg = _abi.new_config(dynamics=_abi.MBT_DYN_SPEED, midprice=_abi.MBT_MID_OU, impact=_abi.MBT_IMP_TEMP_PERM,
-                              ou_level=100.0, ou_speed=1.0, imp_temp=0.01, imp_perm=0.01, imp_step=dt,
-                              reward=_abi.MBT_REW_CJ_OE, rew_phi=0.01, rew_alpha=0.001, q0_const=100.0,
-                              max_inventory=10_000.0, max_cash=n_steps * (100.0 + 4 * 2.0 * T), **common)
-    else:
-        raise ValueError(workload)
-    return cfg
+            return TradingEnvironment(reward_function=CjMmCriterion(0.01, 0.001, 2.0, T), model_dynamics=dyn,
+                                      max_inventory=100, **kw)
+        return TradingEnvironment(reward_function=PnL(), model_dynamics=dyn, max_inventory=n_steps, **kw)
+    if workload == "oe":
+        mid = OuMidpriceModel(mean_reversion_level=100.0, mean_reversion_speed=1.0, volatility=2.0, initial_price=100.0,
+                              terminal_time=T, step_size=dt, num_trajectories=N)
+        imp = TemporaryAndPermanentPriceImpact(0.01, 0.01, n_steps=n_steps, terminal_time=T, num_trajectories=N)
+        dyn = TradinghWithSpeedModelDynamics(midprice_model=mid, price_impact_model=imp, num_trajectories=N)
+        return TradingEnvironment(reward_function=CjOeCriterion(0.01, 0.001, 2.0, T), model_dynamics=dyn,
+                                  initial_inventory=100, max_inventory=10_000, **kw)
+    raise ValueError(workload)
 
 
 def algorithmic_bytes_per_env_step(A, D, esz):
@@ -187,6 +190,8 @@ def main():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--no-episode-stats", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -208,13 +213,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    precision = _abi.MBT_F64 if args.precision == "f64" else _abi.MBT_F32
     tdt = torch.float64 if args.precision == "f64" else torch.float32
     esz = 8 if args.precision == "f64" else 4
-    cfg = make_config(args.workload, precision, N_PER_GPU, rank * N_PER_GPU)
-    env = _lib.NativeEnv(cfg, device=local_rank)
+    n_local = args.n_per_gpu
+    facade = make_env(args.workload, "float64" if args.precision == "f64" else "float32", n_local, rank * n_local, local_rank)
+    env = facade._ensure_native()  # the handle behind the public API: same kernels, explicit device buffers
     N, A, D = env.N, env.A, env.D
-    env.seed(1234)
     stream = torch.cuda.Stream()  # a real (non-default) stream: the env's kernels and the timing events share it
     torch.cuda.set_stream(stream)
     env.set_stream(stream.cuda_stream)
@@ -258,28 +262,67 @@ def main():
     launches = env.launch_count() - launches0
     ktimes = env.kernel_times_ms()
     env.enable_timing(False)
-
     env.set_stream(None)  # back to the handle's own stream for the host-buffer path
-    # ---- e2e: host buffers through the call a user makes (pinned action array in, pinned obs/rew out)
+
+    # ---- e2e: the call a user makes -- TradingEnvironment.step(numpy action) -> numpy obs, rewards, dones, infos.
+    # Every step: H2D of the (N,A) action array from pinned host memory, D2H of (N,D) observations + (N,) rewards.
     e2e_steps = args.e2e_steps or max(10, min(args.steps, 50))
-    h_act = _lib.PinnedArray((N, A), env.dtype)
-    h_obs = _lib.PinnedArray((N, D), env.dtype)
-    h_rew = _lib.PinnedArray((N,), env.dtype)
-    h_act.array[:] = fixed_action_value(args.workload)
-    env.reset(h_obs.array)
+    h_act = facade.pinned_actions()
+    h_act[:] = fixed_action_value(args.workload)
+    facade.reset()
     for _ in range(3):
-        if env.step(h_act.array, h_obs.array, h_rew.array):
-            env.reset(h_obs.array)
+        _o, _r, d, _i = facade.step(h_act)
+        if d[0]:
+            facade.reset()
     barrier()
     t0 = time.perf_counter()
     checksum = 0.0
     for _ in range(e2e_steps):
-        if env.step(h_act.array, h_obs.array, h_rew.array):
-            env.reset(h_obs.array)
-        checksum += float(h_rew.array[0])  # the step's result is read on the host
+        o, r, d, _i = facade.step(h_act)
+        checksum += float(r[0]) + float(o[-1, 0])  # the step's result is read on the host
+        if d[0]:
+            facade.reset()
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
+
+    # ---- per-episode statistics: fused on-device rollout, summary all-reduced / returns all-gathered over NCCL
+    episode = None
+    if not args.no_episode_stats:
+        from mbt_gym_b200 import sharding
+
+        pol = _abi.mbt_policy()
+        pol.kind = _abi.MBT_POL_FIXED
+        for j in range(A):
+            pol.fixed[j] = fixed_action_value(args.workload)
+        env.set_stream(stream.cuda_stream)
+        ret = torch.empty((N,), dtype=tdt, device="cuda")
+        env.reset(mem=_abi.MBT_MEM_DEVICE)
+        env.rollout(pol, ret, None, mem=_abi.MBT_MEM_DEVICE)  # warm-up episode
+        env.reset(mem=_abi.MBT_MEM_DEVICE)
+        barrier()
+        r0, r1, r2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        r0.record(stream)
+        summ = env.rollout(pol, ret, None, mem=_abi.MBT_MEM_DEVICE)
+        r1.record(stream)
+        if world > 1:
+            merged = sharding.allreduce_summary(summ, device=torch.device("cuda", local_rank))
+            all_ret = sharding.allgather_returns(ret)
+        else:
+            merged = sharding.array_to_summary(sharding.summary_to_array(summ))
+            all_ret = ret
+        r2.record(stream)
+        barrier()
+        tt = torch.tensor([r0.elapsed_time(r1), r1.elapsed_time(r2)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        table = sharding.results_table(merged, A)
+        episode = {"fused_rollout_ms": float(tt[0]), "fused_rollout_env_steps_per_sec": N * world * summ.steps / (float(tt[0]) * 1e-3),
+                   "summary_collective_ms": float(tt[1]), "collective": "nccl all_reduce(9 f64) + all_gather(returns)" if world > 1 else "none (1 GPU)",
+                   "returns_gathered": int(all_ret.numel()), "mean_episode_return": table["Mean PnL"],
+                   "std_episode_return": table["Std PnL"], "mean_terminal_inventory": table["Mean terminal inventory"],
+                   "policy": f"fixed action {fixed_action_value(args.workload)}"}
+        env.set_stream(None)
 
     t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -313,11 +356,12 @@ def main():
                          "kernel_launches_timed": int(len(ktimes)),
                          "kernel_share_of_step": mean_kernel_ms / (elapsed_ms / args.steps)},
             "clocks": clocks,
+            "episode_stats": episode,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line))
-    env.close()
+    facade.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -188,9 +188,10 @@ __device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i) {
 }
 
 /*
- * One thread per trajectory, 256-thread blocks.  (A persistent single-wave variant with a warp-tile loop was measured
- * in round 1 -- profiles/r1_step_kernel_history.md: it cost 8-12 registers, dropped occupancy from 64 to 40-48 warps
- * per SM and was slower; the ~3 us during which no SM is active is launch/drain latency, not a wave tail.)
+ * One thread per trajectory, 256-thread blocks.  Two alternatives were measured in round 1 and dropped
+ * (profiles/r1_step_kernel_history.md): a persistent single-wave warp-tile loop (cost 8-12 registers, occupancy
+ * 64 -> 40-48 warps/SM, slower) and two trajectories per thread (no change).  The marginal cost per trajectory
+ * already equals the measured HBM rate; what is left at N = 2^20 is a fixed ~5 us of launch / ramp / drain.
  * VEC: the caller's action/obs pointers are aligned for whole-row vector access.
  */
 template <typename T, class V, bool VEC>

@@ -242,6 +242,13 @@ class TradingEnvironment(_EnvBase):
         self._dones_cache = None
         self._ring = None
 
+    def pinned_actions(self):
+        """A page-locked (N, A) array in the environment's dtype: fill it and pass it to `step()` and the action copy
+        is one direct DMA (any other host array is first staged through the handle's own pinned buffer)."""
+        native = self._ensure_native()
+        self._pinned_actions = _lib.PinnedArray((self.num_trajectories, native.A), self.dtype)
+        return self._pinned_actions.array
+
     def close(self):
         if self._native is not None:
             self._native.close()
