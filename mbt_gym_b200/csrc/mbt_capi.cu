@@ -40,7 +40,8 @@ static int fail(int code, const std::string &msg) {
 
 /* ------------------------------------------------------------------ handle */
 constexpr int MBT_TIMING_RING = 8192;
-constexpr int MBT_PIPE_CHUNKS = 8;
+constexpr int MBT_PIPE_CHUNKS = 16;        /* capacity */
+constexpr int MBT_PIPE_CHUNKS_DEFAULT = 8;
 
 struct mbt_env {
     mbt_config cfg;
@@ -261,6 +262,16 @@ static int do_step_device(mbt_env *e, const void *actions, void *obs, void *rew,
     return MBT_OK;
 }
 
+/* number of pipeline chunks of the host-buffer path (MBT_PIPE_CHUNKS_ENV overrides for tuning; max 8) */
+static int pipe_chunks() {
+    static const int n = [] {
+        const char *v = getenv("MBT_PIPE_CHUNKS");
+        int k = v ? atoi(v) : MBT_PIPE_CHUNKS_DEFAULT;
+        return k < 1 ? 1 : (k > MBT_PIPE_CHUNKS ? MBT_PIPE_CHUNKS : k);
+    }();
+    return n;
+}
+
 /*
  * Host-buffer step: the batch is cut into row chunks and each chunk flows H2D(actions) -> kernel -> D2H(obs, rewards)
  * on three streams, so the two copy engines (PCIe is full duplex) and the SMs overlap; the call returns when the last
@@ -274,7 +285,7 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
     const StepParams<T> p = mbt_make_params<T>(c, e->t0, e->q0_per_traj, e->q0_uniform);
     const StepClock<T> ck = mbt_make_clock<T>(c, e->t, t_next);
     const long long N = e->N;
-    int chunks = N >= (1 << 17) ? MBT_PIPE_CHUNKS : 1;
+    int chunks = N >= (1 << 17) ? pipe_chunks() : 1;
     long long rows = ((N + chunks - 1) / chunks + 255) & ~255ll;
     const size_t arow = (size_t)e->A * sizeof(T), orow = (size_t)e->D * sizeof(T);
     for (int k = 0; k < chunks; ++k) {

@@ -131,12 +131,13 @@ class TradingEnvironment(_EnvBase):
     def step(self, action):
         """One env-step for all trajectories  (TradingEnvironment.py:103-110).
         action (N, A) -> observations (N, D), rewards (N,), dones (N,) bool, infos."""
-        native = self._ensure_native()
-        if not self._started:
+        native = self._native  # the handle is (re)validated against the Python attributes at reset(), not per step
+        if native is None or not self._started:
             raise RuntimeError("step() called before reset()")
         if hasattr(action, "is_cuda") and action.is_cuda:
             return self._step_device(native, action)
-        a = np.ascontiguousarray(action, dtype=self.dtype)
+        a = action if (type(action) is np.ndarray and action.dtype == self.dtype and action.flags.c_contiguous) \
+            else np.ascontiguousarray(action, dtype=self.dtype)
         if a.shape != (self.num_trajectories, native.A):
             if a.size == self.num_trajectories * native.A and self.num_trajectories == 1:
                 a = a.reshape(1, native.A)
