@@ -131,6 +131,33 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the committed ncu captures
+# (profiles/r1_final_f64.ncu_summary.csv, profiles/r1_step_v3_f32.ncu_summary.csv; cold cache, N = 2^20)
+NCU_DRAM_TRAFFIC_BYTES = {("as", "f64"): 53.5e6, ("as", "f32"): 21.4e6}
+
+
+def size_matched_copy_us(nbytes, stream, reps=60):
+    """Median duration of a plain device copy moving `nbytes` (half read, half written), bracketed by CUDA events exactly
+    like the step kernel, rotating over buffers that exceed L2: what a memcpy achieves at THIS size on THIS box."""
+    import torch
+
+    half = int(nbytes // 2)
+    nbuf = max(2, int(2 * L2_BYTES // half) + 1)
+    src = [torch.empty(half, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
+    dst = [torch.empty(half, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
+    for i in range(nbuf):
+        dst[i].copy_(src[i])
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for k, (a, b) in enumerate(evs):
+        a.record(stream)
+        dst[k % nbuf].copy_(src[k % nbuf])
+        b.record(stream)
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    return 1e3 * ms[len(ms) // 2]
+
+
 def cpu_baseline(workload, seconds_target=15.0):
     """NumPy port of the reference step(), one env per host core (fork), bounded sample."""
     from oracle import numpy_port as P
@@ -210,6 +237,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: mbt_gym_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MBT_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
@@ -262,6 +290,7 @@ def main():
     launches = env.launch_count() - launches0
     ktimes = env.kernel_times_ms()
     env.enable_timing(False)
+    copy_us = size_matched_copy_us(N * algorithmic_bytes_per_env_step(A, D, esz), stream) if rank == 0 else None
     env.set_stream(None)  # back to the handle's own stream for the host-buffer path
 
     # ---- e2e: the call a user makes -- TradingEnvironment.step(numpy action) -> numpy obs, rewards, dones, infos.
@@ -351,7 +380,13 @@ def main():
                     "d2h_bytes_per_step": N * (D + 1) * esz, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "mbt_step_kernel",
+                         "traffic": NCU_DRAM_TRAFFIC_BYTES.get((args.workload, args.precision)) if N == N_PER_GPU else None,
+                         "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/ (cold cache)",
+                         "peak_source": peak_src, "kernel": "mbt_step_kernel",
+                         "size_matched_copy_us": copy_us,
+                         "frac_of_size_matched_copy": (copy_us * 1e-3 / mean_kernel_ms) if copy_us else None,
+                         "note": "peak is a 2 GiB copy; size_matched_copy_us is a plain device copy of the same bytes as one "
+                                 "step, timed the same way: the fixed launch/ramp/drain cost at this size is common to both",
                          "algorithmic_bytes_per_env_step": b_step, "mean_kernel_ms": mean_kernel_ms,
                          "kernel_launches_timed": int(len(ktimes)),
                          "kernel_share_of_step": mean_kernel_ms / (elapsed_ms / args.steps)},

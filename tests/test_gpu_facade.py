@@ -168,3 +168,35 @@ def test_normalise_rewards_bootstrap_and_setters():
     _, rew, _, infos = env.step(np.full((128, 2), 0.7))
     assert rew.shape == (128,) and len(infos) == 128
     env.close()
+
+
+def test_wrappers_and_full_size_step_properties():
+    """(1) the reference's gym wrappers on top of the device env; (2) size-independent properties of the STEP path at
+    BASELINE size N = 2^20: PnL rewards telescope to the change in marked-to-market wealth, inventories stay integral,
+    the empirical fill rate matches lambda*dt*exp(-kappa*delta), time advances by dt."""
+    from mbt_gym_b200.gym.wrappers import ReduceStateSizeWrapper
+
+    spec = dict(SPECS["as_pnl"], N=1 << 20)
+    env = build_facade_env(spec)
+    wrapped = ReduceStateSizeWrapper(env)
+    assert wrapped.observation_space.shape == (2,)
+    obs = wrapped.reset()
+    assert obs.shape == (1 << 20, 2) and np.all(obs == 0)
+    a = np.full((1 << 20, 2), 0.7)
+    total = np.zeros(1 << 20)
+    steps = 25
+    for k in range(steps):
+        o, r, d, _ = wrapped.step(a)
+        total += r
+    state = env.state
+    wealth = state[:, 0] + state[:, 1] * state[:, 3]
+    np.testing.assert_allclose(total, wealth - 0.0, rtol=0, atol=1e-9)          # sum of PnL rewards telescopes
+    assert np.all(state[:, 1] == np.round(state[:, 1]))                         # inventory moves in whole units
+    assert state[0, 2] == pytest.approx(steps * env.step_size)
+    # each side fills with probability 0.7 * exp(-1.05) per step; |q| changes only through fills
+    p = 0.7 * np.exp(-1.5 * 0.7)
+    expected_var_q = 2 * steps * p * (1 - p)                                    # bid/ask fills independent Bernoulli(p)
+    assert abs(state[:, 1].var() - expected_var_q) < 6 * expected_var_q * np.sqrt(2 / (1 << 20))
+    assert abs(state[:, 1].mean()) < 6 * np.sqrt(expected_var_q / (1 << 20))
+    assert abs(state[:, 3].var() - 4.0 * steps * env.step_size) < 6 * 4.0 * steps * env.step_size * np.sqrt(2 / (1 << 20))
+    env.close()
