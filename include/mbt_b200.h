@@ -251,6 +251,14 @@ int mbt_set_state(mbt_env *env, const void *state_in, int mem);
 int mbt_get_clock(mbt_env *env, double *time, int64_t *steps_this_episode, int64_t *steps_since_seed,
                   int64_t *episodes_since_seed);
 
+/* Checkpoint / resume.  With a counter-based RNG the whole environment is the structure-of-arrays state block plus a
+ * few counters (seed, clock, step / episode counters, what reset captured): save into / load from a HOST buffer of
+ * mbt_checkpoint_size bytes.  A checkpoint loads only into a handle created with the same num_trajectories, precision
+ * and model layout.  (The reference has no env checkpointing) */
+int mbt_checkpoint_size(mbt_env *env, size_t *bytes);
+int mbt_checkpoint_save(mbt_env *env, void *host_buf, size_t capacity);
+int mbt_checkpoint_load(mbt_env *env, const void *host_buf, size_t bytes);
+
 /* Trajectories whose inventory or cash was clipped since mbt_create (the reference prints the arrays
  * instead, TradingEnvironment.py:283-297). */
 int mbt_get_clip_count(mbt_env *env, int64_t *count);
@@ -277,6 +285,8 @@ int mbt_get_kernel_times(mbt_env *env, float *ms_out, int64_t capacity, int64_t 
 /* Pinned (page-locked) host memory for caller buffers: MBT_MEM_HOST buffers allocated here are DMA'd
  * directly; any other host pointer is staged through the handle's own pinned buffers. */
 int mbt_host_alloc(size_t bytes, void **out);
+/* same, placed on the NUMA node of `device` (pages on the far socket are DMA-read at less than half the rate) */
+int mbt_host_alloc_near(size_t bytes, int device, void **out);
 int mbt_host_free(void *ptr);
 
 #ifdef __cplusplus

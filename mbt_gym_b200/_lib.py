@@ -17,7 +17,8 @@ ABI_SYMBOLS = [
     "mbt_abi_version", "mbt_last_error", "mbt_config_dims", "mbt_create", "mbt_destroy", "mbt_set_stream", "mbt_sync",
     "mbt_seed", "mbt_reset", "mbt_step", "mbt_get_state", "mbt_set_state", "mbt_get_clock", "mbt_get_clip_count",
     "mbt_reward_eval", "mbt_rollout", "mbt_get_launch_count", "mbt_enable_timing", "mbt_get_kernel_times",
-    "mbt_host_alloc", "mbt_host_free",
+    "mbt_host_alloc", "mbt_host_alloc_near", "mbt_host_free", "mbt_checkpoint_size", "mbt_checkpoint_save",
+    "mbt_checkpoint_load",
 ]
 
 _lib = None
@@ -62,7 +63,11 @@ def load():
     L.mbt_enable_timing.argtypes = [vp, C.c_int]
     L.mbt_get_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int64, i64p]
     L.mbt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.mbt_host_alloc_near.argtypes = [C.c_size_t, C.c_int, C.POINTER(vp)]
     L.mbt_host_free.argtypes = [vp]
+    L.mbt_checkpoint_size.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.mbt_checkpoint_save.argtypes = [vp, vp, C.c_size_t]
+    L.mbt_checkpoint_load.argtypes = [vp, vp, C.c_size_t]
     if L.mbt_abi_version() != _abi.MBT_ABI_VERSION:
         raise ImportError(f"libmbt_b200.so ABI {L.mbt_abi_version()} != binding ABI {_abi.MBT_ABI_VERSION}")
     _lib = L
@@ -83,12 +88,12 @@ def config_dims(cfg):
 class PinnedArray:
     """A numpy array backed by page-locked memory from mbt_host_alloc (freed with the object)."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, device=0):
         self.shape = tuple(int(x) for x in np.atleast_1d(shape))
         self.dtype = np.dtype(dtype)
         nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
         p = C.c_void_p()
-        _check(load().mbt_host_alloc(max(nbytes, 1), C.byref(p)))
+        _check(load().mbt_host_alloc_near(max(nbytes, 1), int(device), C.byref(p)))
         self._ptr = p
         buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
@@ -199,6 +204,18 @@ class NativeEnv:
         _check(load().mbt_reward_eval(self._h, cur.shape[0], _addr(cur), _addr(act), _addr(nxt), int(bool(is_terminal)),
                                       _addr(out), _abi.MBT_MEM_HOST))
         return out
+
+    # -- checkpoint / resume
+    def checkpoint(self):
+        n = C.c_size_t()
+        _check(load().mbt_checkpoint_size(self._h, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        _check(load().mbt_checkpoint_save(self._h, buf.ctypes.data, n.value))
+        return buf
+
+    def restore(self, buf):
+        buf = np.ascontiguousarray(buf, np.uint8)
+        _check(load().mbt_checkpoint_load(self._h, buf.ctypes.data, buf.size))
 
     # -- statistics
     def launch_count(self):

@@ -5,8 +5,10 @@
  * kernels of mbt_kernels.cuh on the handle's stream.
  */
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -118,6 +120,74 @@ static int timing_end(mbt_env *e) {
     e->timed += 1;
     return MBT_OK;
 }
+
+/*
+ * NUMA placement of pinned host buffers.  cudaHostAlloc places pages on the NUMA node of the calling thread; on a
+ * two-socket host a buffer on the far socket is read by the GPU at ~16-25 GB/s instead of ~45-55 GB/s (measured:
+ * profiles/r1_pcie_numa.md).  While it allocates, the library therefore narrows the calling thread's affinity to the
+ * CPUs of the GPU's own node (intersected with what the process is allowed to use) and restores it afterwards.
+ */
+static int gpu_numa_node(int device) {
+    char bdf[64] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char *c = bdf; *c; ++c) *c = (char)tolower(*c);
+    char path[160];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+static bool node_cpus(int node, cpu_set_t *set) {
+    char path[96];
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    CPU_ZERO(set);
+    int a, b;
+    bool any = false;
+    while (fscanf(f, "%d", &a) == 1) {
+        b = a;
+        int c = fgetc(f);
+        if (c == '-') {
+            if (fscanf(f, "%d", &b) != 1) break;
+            c = fgetc(f);
+        }
+        for (int i = a; i <= b && i < CPU_SETSIZE; ++i) {
+            CPU_SET(i, set);
+            any = true;
+        }
+        if (c != ',') break;
+    }
+    fclose(f);
+    return any;
+}
+
+struct ScopedNumaAffinity {
+    cpu_set_t old_set;
+    bool active = false;
+    explicit ScopedNumaAffinity(int device) {
+        if (getenv("MBT_NO_NUMA_BIND")) return;
+        const int node = gpu_numa_node(device);
+        cpu_set_t want, allowed;
+        if (node < 0 || !node_cpus(node, &want)) return;
+        if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return;
+        old_set = allowed;
+        cpu_set_t both;
+        CPU_AND(&both, &want, &allowed);
+        if (CPU_COUNT(&both) == 0) return;
+        if (sched_setaffinity(0, sizeof both, &both) == 0) active = true;
+    }
+    ~ScopedNumaAffinity() {
+        if (active) sched_setaffinity(0, sizeof old_set, &old_set);
+    }
+};
 
 /* is this host pointer page-locked (DMA-able without staging)? */
 static bool host_ptr_is_pinned(const void *p) {
@@ -369,7 +439,19 @@ int mbt_config_dims(const mbt_config *cfg, int32_t *action_dim, int32_t *obs_dim
 
 int mbt_host_alloc(size_t bytes, void **out) {
     if (!out) return fail(MBT_E_INVALID_ARG, "out is NULL");
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) {
+        cudaGetLastError();
+        device = 0;
+    }
+    return mbt_host_alloc_near(bytes, device, out);
+}
+
+int mbt_host_alloc_near(size_t bytes, int device, void **out) {
+    if (!out) return fail(MBT_E_INVALID_ARG, "out is NULL");
+    ScopedNumaAffinity near_gpu(device);
     CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    memset(*out, 0, bytes ? bytes : 1); /* first touch on the GPU-local node */
     return MBT_OK;
 }
 int mbt_host_free(void *ptr) {
@@ -496,6 +578,7 @@ static int ensure_staging(mbt_env *e) {
     CU(cudaMalloc(&e->d_actions, ab));
     CU(cudaMalloc(&e->d_obs, ob));
     CU(cudaMalloc(&e->d_rew, rb));
+    ScopedNumaAffinity near_gpu(e->device);
     CU(cudaHostAlloc(&e->h_actions, ab, cudaHostAllocDefault));
     CU(cudaHostAlloc(&e->h_obs, ob, cudaHostAllocDefault));
     CU(cudaHostAlloc(&e->h_rew, rb, cudaHostAllocDefault));
@@ -631,6 +714,70 @@ int mbt_get_clock(mbt_env *e, double *time, int64_t *steps_this_episode, int64_t
     if (steps_this_episode) *steps_this_episode = e->k;
     if (steps_since_seed) *steps_since_seed = e->n_step;
     if (episodes_since_seed) *episodes_since_seed = e->n_episode;
+    return MBT_OK;
+}
+
+/* ---- checkpoint / resume: header + the raw structure-of-arrays block (counter-based RNG: no generator state) */
+struct mbt_ckpt_header {
+    uint64_t magic;
+    int64_t num_trajectories;
+    int32_t precision, obs_dim;
+    uint64_t seed;
+    double t, t0, q0_uniform;
+    int64_t k, n_step, n_episode;
+    int32_t q0_per_traj, started;
+    uint64_t state_bytes;
+};
+static const uint64_t MBT_CKPT_MAGIC = 0x4D42543230304231ull; /* "MBT200B1" */
+
+static size_t state_block_bytes(const mbt_env *e) {
+    return ((((size_t)e->N * e->esz) + 255) & ~(size_t)255) * 6;
+}
+
+int mbt_checkpoint_size(mbt_env *e, size_t *bytes) {
+    if (!e || !bytes) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    *bytes = sizeof(mbt_ckpt_header) + state_block_bytes(e);
+    return MBT_OK;
+}
+
+int mbt_checkpoint_save(mbt_env *e, void *host_buf, size_t capacity) {
+    if (!e || !host_buf) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    const size_t sb = state_block_bytes(e);
+    if (capacity < sizeof(mbt_ckpt_header) + sb) return fail(MBT_E_INVALID_ARG, "checkpoint buffer too small");
+    CU(cudaSetDevice(e->device));
+    mbt_ckpt_header h;
+    memset(&h, 0, sizeof h);
+    h.magic = MBT_CKPT_MAGIC;
+    h.num_trajectories = e->N;
+    h.precision = e->cfg.precision;
+    h.obs_dim = e->D;
+    h.seed = e->seed;
+    h.t = e->t; h.t0 = e->t0; h.q0_uniform = e->q0_uniform;
+    h.k = e->k; h.n_step = e->n_step; h.n_episode = e->n_episode;
+    h.q0_per_traj = e->q0_per_traj; h.started = e->started ? 1 : 0;
+    h.state_bytes = sb;
+    memcpy(host_buf, &h, sizeof h);
+    CU(cudaMemcpyAsync((char *)host_buf + sizeof h, e->state_block, sb, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MBT_OK;
+}
+
+int mbt_checkpoint_load(mbt_env *e, const void *host_buf, size_t bytes) {
+    if (!e || !host_buf) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    if (bytes < sizeof(mbt_ckpt_header)) return fail(MBT_E_INVALID_ARG, "checkpoint truncated");
+    mbt_ckpt_header h;
+    memcpy(&h, host_buf, sizeof h);
+    if (h.magic != MBT_CKPT_MAGIC) return fail(MBT_E_INVALID_ARG, "not an mbt_b200 checkpoint");
+    if (h.num_trajectories != e->N || h.precision != e->cfg.precision || h.obs_dim != e->D ||
+        h.state_bytes != state_block_bytes(e) || bytes < sizeof h + h.state_bytes)
+        return fail(MBT_E_INVALID_ARG, "checkpoint does not match this handle (num_trajectories / precision / model layout)");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(e->state_block, (const char *)host_buf + sizeof h, h.state_bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->seed = h.seed;
+    e->t = h.t; e->t0 = h.t0; e->q0_uniform = h.q0_uniform;
+    e->k = h.k; e->n_step = h.n_step; e->n_episode = h.n_episode;
+    e->q0_per_traj = h.q0_per_traj; e->started = h.started != 0;
     return MBT_OK;
 }
 

@@ -243,11 +243,24 @@ class TradingEnvironment(_EnvBase):
         self._dones_cache = None
         self._ring = None
 
+    def save_checkpoint(self):
+        """The whole environment (device state + clock + RNG counters) as a uint8 array; see `load_checkpoint`."""
+        if self._native is None or not self._started:
+            raise RuntimeError("nothing to checkpoint before reset()")
+        return self._native.checkpoint()
+
+    def load_checkpoint(self, blob):
+        """Resume exactly where `save_checkpoint` was taken (same trajectories, same future random draws)."""
+        native = self._ensure_native()
+        native.restore(blob)
+        self._key = None  # the key now lives in the handle; a later seed() replaces it
+        self._started = True
+
     def pinned_actions(self):
         """A page-locked (N, A) array in the environment's dtype: fill it and pass it to `step()` and the action copy
         is one direct DMA (any other host array is first staged through the handle's own pinned buffer)."""
         native = self._ensure_native()
-        self._pinned_actions = _lib.PinnedArray((self.num_trajectories, native.A), self.dtype)
+        self._pinned_actions = _lib.PinnedArray((self.num_trajectories, native.A), self.dtype, self.device)
         return self._pinned_actions.array
 
     def close(self):
@@ -390,7 +403,8 @@ class TradingEnvironment(_EnvBase):
             if self._native is not None:
                 self._native.close()
             self._native = _lib.NativeEnv(cfg, device=self.device)
-            self._native.seed(self._key)
+            if self._key is not None:
+                self._native.seed(self._key)
             self._native_cfg_bytes = raw
             self._started = False
             self._ring = None
@@ -401,7 +415,8 @@ class TradingEnvironment(_EnvBase):
         if self.copy_outputs:
             return np.empty((n, d), self.dtype), np.empty((n,), self.dtype)
         if self._ring is None:
-            self._ring = [(_lib.PinnedArray((n, d), self.dtype), _lib.PinnedArray((n,), self.dtype)) for _ in range(_RING)]
+            self._ring = [(_lib.PinnedArray((n, d), self.dtype, self.device), _lib.PinnedArray((n,), self.dtype, self.device))
+                          for _ in range(_RING)]
             self._ring_pos = 0
         o, r = self._ring[self._ring_pos]
         self._ring_pos = (self._ring_pos + 1) % _RING

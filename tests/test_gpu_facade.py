@@ -200,3 +200,23 @@ def test_wrappers_and_full_size_step_properties():
     assert abs(state[:, 1].mean()) < 6 * np.sqrt(expected_var_q / (1 << 20))
     assert abs(state[:, 3].var() - 4.0 * steps * env.step_size) < 6 * 4.0 * steps * env.step_size * np.sqrt(2 / (1 << 20))
     env.close()
+
+
+def test_checkpoint_resume_is_exact():
+    g = Golden("cjmm")   # random initial inventories + late start: exercises q0 column, t0, counters
+    env = build_facade_env(SPECS["cjmm"])
+    env.reset()
+    for k in range(10):
+        env.step(g.actions[k])
+    blob = env.save_checkpoint()
+    tail = [tuple(np.array(x, copy=True) for x in env.step(g.actions[k])[:2]) for k in range(10, 30)]
+    other = build_facade_env(dict(SPECS["cjmm"], seed=999))      # a different key: the checkpoint must carry its own
+    other.reset()
+    other.load_checkpoint(blob)
+    for k, (o, r) in zip(range(10, 30), tail):
+        o2, r2, _, _ = other.step(g.actions[k])
+        assert_same(o2, o, what=f"resumed obs {k}"); assert_same(r2, r, what=f"resumed rew {k}")
+        assert_same(o2, g.obs[k], what=f"fixture obs {k}")
+    with pytest.raises(Exception):
+        build_facade_env(dict(SPECS["cjmm"], N=7)).load_checkpoint(blob)
+    env.close(); other.close()
