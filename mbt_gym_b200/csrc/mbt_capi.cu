@@ -332,6 +332,15 @@ static int do_step_device(mbt_env *e, const void *actions, void *obs, void *rew,
     return MBT_OK;
 }
 
+/* host-buffer path: MBT_HOST_PATH=zerocopy lets the kernel access pinned host memory directly; default = DMA pipeline */
+static bool host_path_zero_copy() {
+    static const bool zc = [] {
+        const char *v = getenv("MBT_HOST_PATH");
+        return v && strcmp(v, "zerocopy") == 0;
+    }();
+    return zc;
+}
+
 /* number of pipeline chunks of the host-buffer path (MBT_PIPE_CHUNKS_ENV overrides for tuning; max 8) */
 static int pipe_chunks() {
     static const int n = [] {
@@ -643,9 +652,21 @@ int mbt_step(mbt_env *e, const void *actions, void *obs_out, void *rew_out, uint
     const bool un_obs = obs_out && !host_ptr_is_pinned(obs_out), un_rew = rew_out && !host_ptr_is_pinned(rew_out);
     void *obs_dst = obs_out ? (un_obs ? e->h_obs : obs_out) : nullptr;
     void *rew_dst = rew_out ? (un_rew ? e->h_rew : rew_out) : nullptr;
-    rc = f64 ? do_step_host_pipelined<double>(e, src, obs_dst, rew_dst, done_out)
-             : do_step_host_pipelined<float>(e, src, obs_dst, rew_dst, done_out);
-    if (rc) return rc;
+    if (host_path_zero_copy()) {
+        /* the step kernel reads the action rows and writes observation rows / rewards DIRECTLY in pinned host memory
+         * (UVA mapping): one launch, PCIe reads and posted writes in flight together, no DMA descriptors */
+        void *da = nullptr, *dobs = nullptr, *drew = nullptr;
+        CU(cudaHostGetDevicePointer(&da, const_cast<void *>(src), 0));
+        if (obs_dst) CU(cudaHostGetDevicePointer(&dobs, obs_dst, 0));
+        if (rew_dst) CU(cudaHostGetDevicePointer(&drew, rew_dst, 0));
+        rc = f64 ? do_step_device<double>(e, da, dobs, drew, done_out) : do_step_device<float>(e, da, dobs, drew, done_out);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(e->stream));
+    } else {
+        rc = f64 ? do_step_host_pipelined<double>(e, src, obs_dst, rew_dst, done_out)
+                 : do_step_host_pipelined<float>(e, src, obs_dst, rew_dst, done_out);
+        if (rc) return rc;
+    }
     if (un_obs) par_memcpy(obs_out, e->h_obs, ob);
     if (un_rew) par_memcpy(rew_out, e->h_rew, rb);
     return MBT_OK;

@@ -53,9 +53,6 @@ template <typename T, class V>
 __device__ __forceinline__ int obs_width(const StepParams<T> &p) { return V::D ? V::D : p.obs_dim; }
 
 /* ------------------------------------------------------------------ row access helpers */
-template <typename T, int W>
-struct RowIO; /* W = row width known at compile time (0 = runtime width, scalar accesses) */
-
 __device__ __forceinline__ void st_v4_f64(double *ptr, double a, double b, double c, double d) {
     /* sm_100: 256-bit global store (SASS STG.E.ENL2.256), 32-byte aligned */
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(ptr), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
