@@ -64,8 +64,8 @@ def assert_same(a, b, exact=True, rtol=1e-11, atol=1e-11, what=""):
     a, b = np.asarray(a), np.asarray(b)
     assert a.shape == b.shape, (what, a.shape, b.shape)
     if exact:
-        if not np.array_equal(a, b):
-            bad = np.argwhere(a != b)
+        if not np.array_equal(a, b, equal_nan=True):
+            bad = np.argwhere(~((a == b) | (np.isnan(a) & np.isnan(b))))
             i = tuple(bad[0])
             raise AssertionError(f"{what}: {len(bad)} of {a.size} values differ; first at {i}: {a[i]!r} vs {b[i]!r}")
     else:
