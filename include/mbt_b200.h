@@ -72,6 +72,8 @@ extern "C" {
 #define MBT_MID_BM 1       /* BrownianMotionMidpriceModel          :36-68   */
 #define MBT_MID_GBM 2      /* GeometricBrownianMotionMidpriceModel :71-111  */
 #define MBT_MID_OU 3       /* OuMidpriceModel                      :114-146 */
+#define MBT_MID_BM_JUMP 4  /* BrownianMotionJumpMidpriceModel      :193-230 (jumps on the agent's own fills) */
+#define MBT_MID_OU_JUMP 5  /* OuJumpMidpriceModel                  :233-273 */
 
 /* arrival_models.py */
 #define MBT_ARR_NONE 0
@@ -87,6 +89,8 @@ extern "C" {
 #define MBT_IMP_NONE 0
 #define MBT_IMP_TEMP_PERM 1  /* TemporaryAndPermanentPriceImpact :64-96 state = (I)        */
 #define MBT_IMP_TEMP_POWER 2 /* TemporaryPowerPriceImpact        :34-61 stateless          */
+#define MBT_IMP_TEMP_TRANSIENT 3 /* TemporaryAndTransientPriceImpact :99-139 state = (Y)     */
+#define MBT_IMP_TRANSIENT 4      /* TransientPriceImpact             :142-179 state = (Y)    */
 
 /* RewardFunctions.py */
 #define MBT_REW_PNL 0                       /* PnL                     :20-36   */
@@ -133,6 +137,7 @@ typedef struct mbt_config {
     double mid_step;    /* midprice_model.step_size */
     double ou_level;    /* mean_reversion_level */
     double ou_speed;    /* mean_reversion_speed */
+    double mid_jump;    /* jump_size (jump models) */
 
     /* arrival model */
     double arr_rate[2];  /* Poisson intensity, or Hawkes baseline_arrival_rate (bid, ask) */
@@ -148,6 +153,10 @@ typedef struct mbt_config {
     double imp_perm;     /* permanent_impact_coefficient */
     double imp_exponent; /* temporary_impact_exponent (TemporaryPowerPriceImpact) */
     double imp_step;     /* price_impact_model.step_size */
+    double imp_transient;  /* transient_impact_coefficient  (kappa in Neuman-Voss 2022) */
+    double imp_resilience; /* resilience_coefficient        (rho)                        */
+    double imp_kernel;     /* linear_kernel_coefficient     (gamma)                      */
+    double imp_initial;    /* initial_transient_impact      (y)                          */
 
     /* AtTheTouch / LimitAndMarket */
     double half_spread; /* fixed_market_half_spread */

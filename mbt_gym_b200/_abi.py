@@ -29,6 +29,8 @@ MBT_MID_CONSTANT = 0
 MBT_MID_BM = 1
 MBT_MID_GBM = 2
 MBT_MID_OU = 3
+MBT_MID_BM_JUMP = 4
+MBT_MID_OU_JUMP = 5
 
 MBT_ARR_NONE = 0
 MBT_ARR_POISSON = 1
@@ -41,6 +43,9 @@ MBT_FILL_EXPONENTIAL = 1
 MBT_IMP_NONE = 0
 MBT_IMP_TEMP_PERM = 1
 MBT_IMP_TEMP_POWER = 2
+MBT_IMP_TEMP_TRANSIENT = 3
+MBT_IMP_TRANSIENT = 4
+IMPACTS_WITH_STATE = (MBT_IMP_TEMP_PERM, MBT_IMP_TEMP_TRANSIENT, MBT_IMP_TRANSIENT)
 
 MBT_REW_PNL = 0
 MBT_REW_RUNNING_INVENTORY_PENALTY = 1
@@ -90,6 +95,7 @@ class mbt_config(C.Structure):
         ("mid_step", C.c_double),
         ("ou_level", C.c_double),
         ("ou_speed", C.c_double),
+        ("mid_jump", C.c_double),
         ("arr_rate", C.c_double * 2),
         ("arr_step", C.c_double),
         ("hawkes_jump", C.c_double),
@@ -99,6 +105,10 @@ class mbt_config(C.Structure):
         ("imp_perm", C.c_double),
         ("imp_exponent", C.c_double),
         ("imp_step", C.c_double),
+        ("imp_transient", C.c_double),
+        ("imp_resilience", C.c_double),
+        ("imp_kernel", C.c_double),
+        ("imp_initial", C.c_double),
         ("half_spread", C.c_double),
         ("rew_phi", C.c_double),
         ("rew_alpha", C.c_double),

@@ -416,6 +416,7 @@ static int do_reset_device(mbt_env *e, const mbt_reset_args *args, void *obs) {
     g.mid0 = (T)c.mid_initial;
     g.lam0[0] = (T)c.arr_rate[0];
     g.lam0[1] = (T)c.arr_rate[1];
+    g.imp0 = c.impact == MBT_IMP_TEMP_PERM ? (T)0 : (T)c.imp_initial;
     g.q0_mode = q0_mode;
     g.q0_const = (T)q0_const;
     g.q0_lo = lo;

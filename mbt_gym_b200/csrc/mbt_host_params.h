@@ -25,7 +25,7 @@ static inline int mbt_dims(const mbt_config *c, int32_t *A, int32_t *D, int32_t 
     default: return MBT_E_UNSUPPORTED;
     }
     if (c->arrival == MBT_ARR_HAWKES) d += 2;
-    if (c->impact == MBT_IMP_TEMP_PERM) d += 1;
+    if (c->impact == MBT_IMP_TEMP_PERM || c->impact == MBT_IMP_TEMP_TRANSIENT || c->impact == MBT_IMP_TRANSIENT) d += 1;
     if (A) *A = a;
     if (D) *D = d;
     if (S) *S = d - 1;
@@ -49,12 +49,16 @@ static inline int mbt_validate_config(const mbt_config *c, std::string &err) {
         return MBT_E_INVALID_ARG;
     }
     if (mbt_dims(c, nullptr, nullptr, nullptr) != MBT_OK) { err = "unknown dynamics kind"; return MBT_E_UNSUPPORTED; }
-    if (c->midprice < MBT_MID_CONSTANT || c->midprice > MBT_MID_OU) { err = "unknown midprice model"; return MBT_E_UNSUPPORTED; }
+    if (c->midprice < MBT_MID_CONSTANT || c->midprice > MBT_MID_OU_JUMP) { err = "unknown midprice model"; return MBT_E_UNSUPPORTED; }
     if (c->reward < MBT_REW_PNL || c->reward > MBT_REW_EXP_UTILITY) { err = "unknown reward function"; return MBT_E_UNSUPPORTED; }
     if (c->dynamics == MBT_DYN_SPEED) {
         /* ModelDynamics.py:273-275: required_processes = ["price_impact_model"] */
-        if (c->impact != MBT_IMP_TEMP_PERM && c->impact != MBT_IMP_TEMP_POWER) {
-            err = "speed dynamics needs a price impact model (temp_perm or temp_power)";
+        if (c->impact < MBT_IMP_TEMP_PERM || c->impact > MBT_IMP_TRANSIENT) {
+            err = "speed dynamics needs a price impact model";
+            return MBT_E_UNSUPPORTED;
+        }
+        if (c->midprice == MBT_MID_BM_JUMP || c->midprice == MBT_MID_OU_JUMP) {
+            err = "jump midprice models need limit-order fills (the reference fails with speed dynamics too)";
             return MBT_E_UNSUPPORTED;
         }
         if (c->arrival == MBT_ARR_HAWKES) { err = "speed dynamics with a Hawkes arrival model is not supported"; return MBT_E_UNSUPPORTED; }
@@ -117,8 +121,9 @@ static inline StepParams<T> mbt_make_params(const mbt_config &c, double t0, int 
     p.vol_sqdt = (T)(c.mid_vol * std::sqrt(c.mid_step));
     p.sqdt = (T)std::sqrt(c.mid_step);
     p.mid_drift = (T)c.mid_drift; p.mid_vol = (T)c.mid_vol; p.mid_step = (T)c.mid_step;
-    p.ou_neg_speed = -(T)c.ou_speed; p.ou_level = (T)c.ou_level;
+    p.ou_neg_speed = -(T)c.ou_speed; p.ou_speed = (T)c.ou_speed; p.ou_level = (T)c.ou_level; p.mid_jump = (T)c.mid_jump;
     p.imp_temp = (T)c.imp_temp; p.imp_perm = (T)c.imp_perm; p.imp_exp = (T)c.imp_exponent; p.imp_step = (T)c.imp_step;
+    p.imp_transient = (T)c.imp_transient; p.imp_resilience = (T)c.imp_resilience; p.imp_kernel = (T)c.imp_kernel;
     p.half_spread = (T)c.half_spread;
     p.phi = (T)c.rew_phi; p.alpha = (T)c.rew_alpha; p.pexp = (T)c.rew_exponent; p.risk_aversion = (T)c.rew_risk_aversion;
     p.reward_scaling = (T)c.reward_scaling;

@@ -126,7 +126,7 @@ __device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T
         row[d] = norm_obs<T, V>(p, s.x0, d); ++d;
         row[d] = norm_obs<T, V>(p, s.x1, d); ++d;
     }
-    if (imp == MBT_IMP_TEMP_PERM) { row[d] = norm_obs<T, V>(p, s.x0, d); ++d; }
+    if (imp_has_state(imp)) { row[d] = norm_obs<T, V>(p, s.x0, d); ++d; }
     return d;
 }
 
@@ -139,7 +139,7 @@ __device__ __forceinline__ void load_traj(const StepParams<T> &p, const DevState
     s.x0 = (T)0;
     s.x1 = (T)0;
     if (arr == MBT_ARR_HAWKES) { s.x0 = st.x0[i]; s.x1 = st.x1[i]; }
-    if (imp == MBT_IMP_TEMP_PERM) s.x0 = st.x0[i];
+    if (imp_has_state(imp)) s.x0 = st.x0[i];
 }
 
 template <typename T, class V>
@@ -149,7 +149,7 @@ __device__ __forceinline__ void store_traj(const StepParams<T> &p, const DevStat
     st.inv[i] = s.inv;
     if (mid != MBT_MID_CONSTANT) st.mid[i] = s.mid;
     if (arr == MBT_ARR_HAWKES) { st.x0[i] = s.x0; st.x1[i] = s.x1; }
-    if (imp == MBT_IMP_TEMP_PERM) st.x0[i] = s.x0;
+    if (imp_has_state(imp)) st.x0[i] = s.x0;
 }
 
 /* ------------------------------------------------------------------ step */
@@ -205,7 +205,7 @@ struct ResetArgs {
     T *obs;
     long long n;
     unsigned long long seed, traj_offset, n_episode;
-    T cash0, t0, mid0, lam0[2];
+    T cash0, t0, mid0, lam0[2], imp0;
     int q0_mode;
     T q0_const;
     long long q0_lo;
@@ -229,11 +229,12 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_reset_kernel(const __grid_const
     s.x0 = (T)0;
     s.x1 = (T)0;
     if (p.arr == MBT_ARR_HAWKES) { s.x0 = g.lam0[0]; s.x1 = g.lam0[1]; }
+    if (imp_has_state(p.imp)) s.x0 = g.imp0; /* 0 for the permanent impact, initial_transient_impact otherwise */
     g.st.cash[i] = s.cash;
     g.st.inv[i] = s.inv;
     g.st.mid[i] = s.mid;
     if (p.arr == MBT_ARR_HAWKES) { g.st.x0[i] = s.x0; g.st.x1[i] = s.x1; }
-    if (p.imp == MBT_IMP_TEMP_PERM) g.st.x0[i] = s.x0;
+    if (imp_has_state(p.imp)) g.st.x0[i] = s.x0;
     if (g.q0_mode == MBT_Q0_UNIFORM_INT) g.st.q0[i] = s.inv; /* reward_function.reset  RewardFunctions.py:72,111 */
     if (g.obs) {
         T row[MBT_MAX_OBS_DIM];
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_scatter_state_kernel(StepParams
     st.mid[i] = row[3];
     int d = 4;
     if (p.arr == MBT_ARR_HAWKES) { st.x0[i] = row[d]; st.x1[i] = row[d + 1]; d += 2; }
-    if (p.imp == MBT_IMP_TEMP_PERM) st.x0[i] = row[d];
+    if (imp_has_state(p.imp)) st.x0[i] = row[d];
 }
 
 /* ------------------------------------------------------------------ reward on caller rows */

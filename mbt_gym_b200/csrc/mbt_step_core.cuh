@@ -29,7 +29,9 @@ struct Variant {
     static constexpr int dyn = DYN, mid = MID, arr = ARR, imp = IMP, rew = REW, norm = NORM;
     /* action / observation widths when the model kinds are fixed (0 = runtime) */
     static constexpr int A = DYN < 0 ? 0 : (DYN == MBT_DYN_SPEED ? 1 : (DYN == MBT_DYN_LIMIT_AND_MARKET ? 4 : 2));
-    static constexpr int D = (DYN < 0 || ARR < 0 || IMP < 0) ? 0 : 4 + (ARR == MBT_ARR_HAWKES ? 2 : 0) + (IMP == MBT_IMP_TEMP_PERM ? 1 : 0);
+    static constexpr int D = (DYN < 0 || ARR < 0 || IMP < 0) ? 0
+                                                             : 4 + (ARR == MBT_ARR_HAWKES ? 2 : 0) +
+                                                                   ((IMP == MBT_IMP_TEMP_PERM || IMP == MBT_IMP_TEMP_TRANSIENT || IMP == MBT_IMP_TRANSIENT) ? 1 : 0);
 };
 using VariantGeneric = Variant<-1, -1, -1, -1, -1, -1>;
 
@@ -64,8 +66,8 @@ struct StepParams {
     uint32_t arr_thr[2]; /* ceil(p_arr * 2^24) clamped to [0, 2^24]:  k*2^-24 < p_arr  <=>  k < arr_thr */
     T arr_step, arr_step_2p24 /* arr_step * 2^24 */, arr_rate[2], hawkes_speed, hawkes_jump;
     T neg_kappa; /* -fill_exponent */
-    T drift_dt, vol_sqdt, sqdt, mid_drift, mid_vol, mid_step, ou_neg_speed, ou_level;
-    T imp_temp, imp_perm, imp_exp, imp_step, half_spread;
+    T drift_dt, vol_sqdt, sqdt, mid_drift, mid_vol, mid_step, ou_neg_speed, ou_speed, ou_level, mid_jump;
+    T imp_temp, imp_perm, imp_exp, imp_step, imp_transient, imp_resilience, imp_kernel, half_spread;
     T phi, alpha, pexp, risk_aversion, reward_scaling;
     T act_low[MBT_MAX_ACTION_DIM], act_grad[MBT_MAX_ACTION_DIM];
     T obs_low[MBT_MAX_OBS_DIM], obs_grad[MBT_MAX_OBS_DIM];
@@ -88,6 +90,9 @@ struct Traj {
 
 template <int CT>
 MBT_HD int pick(int runtime) { return CT >= 0 ? CT : runtime; }
+
+/* price-impact models that carry one state column (permanent impact I, or transient impact Y) */
+MBT_HD bool imp_has_state(int imp) { return imp == MBT_IMP_TEMP_PERM || imp == MBT_IMP_TEMP_TRANSIENT || imp == MBT_IMP_TRANSIENT; }
 
 /* reward_function.calculate for one row; (c0, q_cur, S0) = current_state, s = next_state. */
 template <typename T, class V>
@@ -122,6 +127,7 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
               imp = pick<V::imp>(p.imp);
     const T c0 = s.cash, q_cur = s.inv, S = s.mid; /* current_state = state.copy()   TradingEnvironment.py:105 */
     T arr_b = 0, arr_a = 0;
+    T own_b = 0, own_a = 0; /* the agent's own executed fills (fill * arrival), for the jump midprice models */
 
     if (dyn != MBT_DYN_SPEED) {
         /* get_arrivals_and_fills                                    ModelDynamics.py:127-131,169-172 */
@@ -163,12 +169,17 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
         }
         /* update_state with fill_multiplier (-1,+1)                   ModelDynamics.py:71-73,108-116 */
         T b = arr_b * fil_b, k = arr_a * fil_a;
+        own_b = fil_b * arr_b;
+        own_a = fil_a * arr_a;
         s.inv = s.inv + (b - k);
         s.cash = s.cash + (k * (S + off_a) - b * (S - off_b));
     } else { /* TradinghWithSpeedModelDynamics.update_state            ModelDynamics.py:262-267 */
         T nu = a[0];
-        T impact = (imp == MBT_IMP_TEMP_PERM) ? p.imp_temp * nu + s.x0              /* price_impact_models.py:91-92 */
-                                              : p.imp_temp * mbt_pow_t(nu, p.imp_exp); /* :55-56 */
+        T impact;
+        if (imp == MBT_IMP_TEMP_PERM) impact = p.imp_temp * nu + s.x0;                               /* price_impact_models.py:91-92 */
+        else if (imp == MBT_IMP_TEMP_TRANSIENT) impact = p.imp_temp * nu + p.imp_transient * s.x0;   /* :133-134 */
+        else if (imp == MBT_IMP_TRANSIENT) impact = p.imp_transient * s.x0;                          /* :174-175 */
+        else impact = p.imp_temp * mbt_pow_t(nu, p.imp_exp);                                         /* :55-56 */
         T vol = nu * p.mid_step;
         s.cash = s.cash - vol * (S + impact);
         s.inv = s.inv + vol;
@@ -189,8 +200,12 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
             s.mid = (S + p.drift_dt) + p.vol_sqdt * z;
         else if (mid == MBT_MID_GBM) /* midprice_models.py:97-105 */
             s.mid = (S + (p.mid_drift * S) * p.mid_step) + (((p.mid_vol * S) * p.sqdt) * z);
-        else /* MBT_MID_OU  midprice_models.py:140-143: drift not scaled by dt, as written there */
+        else if (mid == MBT_MID_OU) /* midprice_models.py:140-143: drift not scaled by dt, as written there */
             s.mid = S + (p.ou_neg_speed * (S - p.ou_level) + p.vol_sqdt * z);
+        else if (mid == MBT_MID_BM_JUMP) /* midprice_models.py:222-230: jumps on the agent's own fills */
+            s.mid = ((S + p.drift_dt) + p.vol_sqdt * z) + (p.mid_jump * own_a - p.mid_jump * own_b);
+        else /* MBT_MID_OU_JUMP  midprice_models.py:262-270 */
+            s.mid = ((S - p.ou_speed * (S - p.ou_level)) + p.vol_sqdt * z) + (p.mid_jump * own_a - p.mid_jump * own_b);
     }
     if (arr_kind == MBT_ARR_HAWKES) { /* arrival_models.py:110-119 (jump on arrival, not on fill) */
         s.x0 = (s.x0 + ((p.hawkes_speed * (p.arr_rate[0] - s.x0)) * p.arr_step)) + p.hawkes_jump * arr_b;
@@ -198,6 +213,8 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
     }
     if (imp == MBT_IMP_TEMP_PERM) /* price_impact_models.py:88-89 */
         s.x0 = s.x0 + (p.imp_perm * a[0]) * p.imp_step;
+    else if (imp == MBT_IMP_TEMP_TRANSIENT || imp == MBT_IMP_TRANSIENT) /* price_impact_models.py:129-131,170-172 */
+        s.x0 = (s.x0 - (p.imp_resilience * s.x0) * p.imp_step) + (p.imp_kernel * a[0]) * p.imp_step;
 
     /* rewards = reward_function.calculate(current_state, action, next_state, dones[0])   :108 */
     T rwd = reward_one<T, V>(p, ck, c0, q_cur, S, s, a, q_init);

@@ -1,7 +1,8 @@
 """Midprice model descriptors (reference: mbt_gym/stochastic_processes/midprice_models.py).
 
-Supported on the device: Constant (:12-33), BrownianMotion (:36-68), GeometricBrownianMotion (:71-111), Ou (:114-146).
-The reference's alpha / jump / Heston / CEV models are outside the BASELINE hot path --
+Supported on the device: Constant (:12-33), BrownianMotion (:36-68), GeometricBrownianMotion (:71-111), Ou (:114-146),
+BrownianMotionJump (:193-230), OuJump (:233-273).
+The reference's alpha / Heston / CEV models are outside the BASELINE hot path --
 several of them do not run for num_trajectories > 1 in the reference itself.
 """
 from math import sqrt
@@ -30,6 +31,7 @@ class _SymmetricBoundsMidprice(StochasticProcessModel):
         cfg.mid_vol = float(getattr(self, "volatility", 0.0))
         cfg.ou_level = float(getattr(self, "mean_reversion_level", 0.0))
         cfg.ou_speed = float(getattr(self, "mean_reversion_speed", 0.0))
+        cfg.mid_jump = float(getattr(self, "jump_size", 0.0))
 
 
 class ConstantMidpriceModel(_SymmetricBoundsMidprice):
@@ -78,6 +80,34 @@ class OuMidpriceModel(_SymmetricBoundsMidprice):
                  terminal_time=1.0, step_size=0.01, num_trajectories=1, seed=None):
         self.mean_reversion_level, self.mean_reversion_speed, self.volatility = (mean_reversion_level,
                                                                                  mean_reversion_speed, volatility)
+        self._finish(initial_price, terminal_time, step_size, num_trajectories, seed)
+
+    def _get_max_value(self, initial_price, terminal_time):
+        return initial_price + 4 * self.volatility * terminal_time
+
+
+class BrownianMotionJumpMidpriceModel(_SymmetricBoundsMidprice):
+    """Brownian midprice that also jumps by +/- jump_size when the agent's ask / bid order is filled (:193-230).
+    Only meaningful with limit-order dynamics (it needs fills)."""
+    KIND = _abi.MBT_MID_BM_JUMP
+
+    def __init__(self, drift=0.0, volatility=2.0, jump_size=1.0, initial_price=100, terminal_time=1.0, step_size=0.01,
+                 num_trajectories=1, seed=None):
+        self.drift, self.volatility, self.jump_size = drift, volatility, jump_size
+        self._finish(initial_price, terminal_time, step_size, num_trajectories, seed)
+
+    def _get_max_value(self, initial_price, terminal_time):
+        return initial_price + 4 * self.volatility * terminal_time
+
+
+class OuJumpMidpriceModel(_SymmetricBoundsMidprice):
+    """OU midprice (drift not scaled by dt, as in the reference) with fill-driven jumps (:233-273)."""
+    KIND = _abi.MBT_MID_OU_JUMP
+
+    def __init__(self, mean_reversion_level=0.0, mean_reversion_speed=1.0, volatility=2.0, jump_size=1.0,
+                 initial_price=100.0, terminal_time=1.0, step_size=0.01, num_trajectories=1, seed=None):
+        self.mean_reversion_level, self.mean_reversion_speed = mean_reversion_level, mean_reversion_speed
+        self.volatility, self.jump_size = volatility, jump_size
         self._finish(initial_price, terminal_time, step_size, num_trajectories, seed)
 
     def _get_max_value(self, initial_price, terminal_time):

@@ -38,7 +38,8 @@ static int orc_dims(const mbt_config *c, int32_t *A, int32_t *D, int32_t *S) {
     default: return -1;
     }
     if (c->arrival == MBT_ARR_HAWKES) d += 2;    /* arrival_models.py:99-103 */
-    if (c->impact == MBT_IMP_TEMP_PERM) d += 1;  /* price_impact_models.py:79-83 */
+    if (c->impact == MBT_IMP_TEMP_PERM || c->impact == MBT_IMP_TEMP_TRANSIENT || c->impact == MBT_IMP_TRANSIENT)
+        d += 1; /* one state column: price_impact_models.py:79-83,119-127,162-170 */
     *A = a;
     *D = d;
     *S = d - 1;

@@ -139,6 +139,8 @@ static void FN(orc_reset)(FN(orc_env) * e, const mbt_reset_args *args, REAL *obs
             s[col++] = (REAL)c->arr_rate[1];
         }
         if (c->impact == MBT_IMP_TEMP_PERM) s[col++] = (REAL)0; /* price_impact_models.py:83 */
+        if (c->impact == MBT_IMP_TEMP_TRANSIENT || c->impact == MBT_IMP_TRANSIENT)
+            s[col++] = (REAL)c->imp_initial; /* initial_transient_impact   price_impact_models.py:124,167 */
         e->q0[i] = s[1]; /* reward_function.reset: initial_inventory  RewardFunctions.py:72,111 */
     }
     e->t = t0;
@@ -188,6 +190,7 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
         }
         const REAL S = cs[3]; /* ModelDynamics.midprice: pre-update price   ModelDynamics.py:82-84 */
         REAL arr[2] = {0, 0};
+        REAL fil_bid = 0, fil_ask = 0; /* fills after max-inventory suppression (what the processes' update() receives) */
 
         if (c->dynamics == MBT_DYN_LIMIT || c->dynamics == MBT_DYN_AT_TOUCH || c->dynamics == MBT_DYN_LIMIT_AND_MARKET) {
             /* ---- get_arrivals_and_fills                                ModelDynamics.py:127-131,169-172 */
@@ -209,6 +212,8 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
             /* ---- _remove_max_inventory_fills (pre-step inventory)      TradingEnvironment.py:146-152,323-327 */
             fil[0] = (REAL)(1 - (cs[1] >= qmax)) * fil[0];
             fil[1] = (REAL)(1 - (cs[1] <= -qmax)) * fil[1];
+            fil_bid = fil[0];
+            fil_ask = fil[1];
             /* ---- update_state                                          ModelDynamics.py:108-116,151-160,208-224 */
             REAL hs = (REAL)c->half_spread;
             if (c->dynamics == MBT_DYN_LIMIT_AND_MARKET) {
@@ -231,6 +236,10 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
             REAL impact;
             if (c->impact == MBT_IMP_TEMP_PERM)
                 impact = (REAL)c->imp_temp * nu + cs[4]; /* price_impact_models.py:91-92 */
+            else if (c->impact == MBT_IMP_TEMP_TRANSIENT) /* price_impact_models.py:133-134 */
+                impact = (REAL)c->imp_temp * nu + (REAL)c->imp_transient * cs[4];
+            else if (c->impact == MBT_IMP_TRANSIENT) /* price_impact_models.py:174-175 */
+                impact = (REAL)c->imp_transient * cs[4];
             else
                 impact = (REAL)c->imp_temp * FN(orc_pow)(nu, (REAL)c->imp_exponent); /* :55-56 */
             REAL px = S + impact;
@@ -255,6 +264,17 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
         case MBT_MID_OU: /* midprice_models.py:140-143 (drift NOT scaled by dt, as written there) */
             s[3] = S + ((-(REAL)c->ou_speed) * (S - (REAL)c->ou_level) + vol_sqdt * z[i]);
             break;
+        case MBT_MID_BM_JUMP: { /* midprice_models.py:222-230: jumps with the agent's own (post-suppression) fills */
+            REAL fb = fil_bid * arr[0], fa = fil_ask * arr[1];
+            s[3] = ((S + drift_dt) + vol_sqdt * z[i]) + ((REAL)c->mid_jump * fa - (REAL)c->mid_jump * fb);
+            break;
+        }
+        case MBT_MID_OU_JUMP: { /* midprice_models.py:262-270 */
+            REAL fb = fil_bid * arr[0], fa = fil_ask * arr[1];
+            s[3] = ((S - (REAL)c->ou_speed * (S - (REAL)c->ou_level)) + vol_sqdt * z[i]) +
+                   ((REAL)c->mid_jump * fa - (REAL)c->mid_jump * fb);
+            break;
+        }
         default: /* MBT_MID_CONSTANT  midprice_models.py:32-33 */
             break;
         }
@@ -267,6 +287,9 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
         }
         if (c->impact == MBT_IMP_TEMP_PERM) /* price_impact_models.py:88-89 */
             s[4] = cs[4] + ((REAL)c->imp_perm * a[0]) * (REAL)c->imp_step;
+        if (c->impact == MBT_IMP_TEMP_TRANSIENT || c->impact == MBT_IMP_TRANSIENT) /* price_impact_models.py:129-131,170-172 */
+            s[4] = (cs[4] - ((REAL)c->imp_resilience * cs[4]) * (REAL)c->imp_step) +
+                   ((REAL)c->imp_kernel * a[0]) * (REAL)c->imp_step;
 
         /* ---- reward_function.calculate(current_state, action, next_state, dones[0])  :108 */
         REAL r = FN(orc_reward)(c, cs, s, a, done, (REAL)(t_next - t_cur), e->q0[i],

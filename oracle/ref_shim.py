@@ -102,6 +102,14 @@ def build_reference_env(spec):
         mid = MM.OuMidpriceModel(mean_reversion_level=m["level"], mean_reversion_speed=m["speed"],
                                  volatility=m["volatility"], initial_price=m["initial_price"], terminal_time=T,
                                  step_size=dt, num_trajectories=N)
+    elif m["kind"] == "bm_jump":
+        mid = MM.BrownianMotionJumpMidpriceModel(drift=m.get("drift", 0.0), volatility=m["volatility"],
+                                                 jump_size=m["jump"], initial_price=m["initial_price"], terminal_time=T,
+                                                 step_size=dt, num_trajectories=N)
+    elif m["kind"] == "ou_jump":
+        mid = MM.OuJumpMidpriceModel(mean_reversion_level=m["level"], mean_reversion_speed=m["speed"],
+                                     volatility=m["volatility"], jump_size=m["jump"], initial_price=m["initial_price"],
+                                     terminal_time=T, step_size=dt, num_trajectories=N)
     elif m["kind"] == "constant":
         mid = MM.ConstantMidpriceModel(initial_price=m["initial_price"], terminal_time=T, step_size=dt,
                                        num_trajectories=N)
@@ -131,6 +139,12 @@ def build_reference_env(spec):
         elif p["kind"] == "temp_power":
             imp = PM.TemporaryPowerPriceImpact(temporary_impact_coefficient=p["temp"],
                                                temporary_impact_exponent=p["exponent"], num_trajectories=N)
+        elif p["kind"] == "temp_transient":
+            imp = PM.TemporaryAndTransientPriceImpact(p["temp"], p["transient"], p["resilience"], p["initial"], p["kernel"],
+                                                      n_steps=n_steps, terminal_time=T, num_trajectories=N)
+        elif p["kind"] == "transient":
+            imp = PM.TransientPriceImpact(p["transient"], p["resilience"], p["initial"], p["kernel"], n_steps=n_steps,
+                                          terminal_time=T, num_trajectories=N)
     dyn_kind = spec["dynamics"]
     if dyn_kind == "limit":
         dyn = MD.LimitOrderModelDynamics(midprice_model=mid, arrival_model=arr, fill_probability_model=fill,
@@ -174,7 +188,8 @@ def build_reference_env(spec):
 
 _DYN = {"limit": _abi.MBT_DYN_LIMIT, "speed": _abi.MBT_DYN_SPEED, "touch": _abi.MBT_DYN_AT_TOUCH,
         "limit_and_market": _abi.MBT_DYN_LIMIT_AND_MARKET}
-_MID = {"constant": _abi.MBT_MID_CONSTANT, "bm": _abi.MBT_MID_BM, "gbm": _abi.MBT_MID_GBM, "ou": _abi.MBT_MID_OU}
+_MID = {"constant": _abi.MBT_MID_CONSTANT, "bm": _abi.MBT_MID_BM, "gbm": _abi.MBT_MID_GBM, "ou": _abi.MBT_MID_OU,
+        "bm_jump": _abi.MBT_MID_BM_JUMP, "ou_jump": _abi.MBT_MID_OU_JUMP}
 _ARR = {"poisson": _abi.MBT_ARR_POISSON, "poisson_nonlinear": _abi.MBT_ARR_POISSON_NONLINEAR,
         "hawkes": _abi.MBT_ARR_HAWKES}
 _REW = {"pnl": _abi.MBT_REW_PNL, "rip": _abi.MBT_REW_RUNNING_INVENTORY_PENALTY, "cjmm": _abi.MBT_REW_CJ_MM,
@@ -202,6 +217,7 @@ def config_from_reference_env(spec, env, precision=_abi.MBT_F64, traj_offset=0):
     cfg.mid_step = float(mid.step_size)
     cfg.ou_level = float(getattr(mid, "mean_reversion_level", 0.0))
     cfg.ou_speed = float(getattr(mid, "mean_reversion_speed", 0.0))
+    cfg.mid_jump = float(getattr(mid, "jump_size", 0.0))
     arr = md.arrival_model
     if arr is not None:
         cfg.arrival = _ARR[spec["arrival"]["kind"]]
@@ -217,13 +233,19 @@ def config_from_reference_env(spec, env, precision=_abi.MBT_F64, traj_offset=0):
         cfg.fill_exponent = float(fill.fill_exponent)
     imp = md.price_impact_model
     if imp is not None:
-        cfg.imp_temp = float(imp.temporary_impact_coefficient)
-        if spec["impact"]["kind"] == "temp_perm":
+        kind = spec["impact"]["kind"]
+        cfg.imp_temp = float(getattr(imp, "temporary_impact_coefficient", 0.0))
+        if kind == "temp_perm":
             cfg.impact = _abi.MBT_IMP_TEMP_PERM
             cfg.imp_perm, cfg.imp_step = float(imp.permanent_impact_coefficient), float(imp.step_size)
-        else:
+        elif kind == "temp_power":
             cfg.impact = _abi.MBT_IMP_TEMP_POWER
             cfg.imp_exponent = float(imp.temporary_impact_exponent)
+        else:
+            cfg.impact = _abi.MBT_IMP_TEMP_TRANSIENT if kind == "temp_transient" else _abi.MBT_IMP_TRANSIENT
+            cfg.imp_transient, cfg.imp_resilience = float(imp.transient_impact_coefficient), float(imp.resilience_coefficient)
+            cfg.imp_kernel, cfg.imp_initial = float(imp.linear_kernel_coefficient), float(imp.initial_transient_impact)
+            cfg.imp_step = float(imp.step_size)
     cfg.half_spread = float(getattr(md, "fixed_market_half_spread", 0.0))
     rf = env.reward_function
     cfg.reward = _REW[spec["reward"]["kind"]]

@@ -92,6 +92,11 @@ def build_facade_env(spec, **extra):
     elif m["kind"] == "ou":
         mid = MM.OuMidpriceModel(mean_reversion_level=m["level"], mean_reversion_speed=m["speed"],
                                  volatility=m["volatility"], **kw)
+    elif m["kind"] == "bm_jump":
+        mid = MM.BrownianMotionJumpMidpriceModel(drift=m.get("drift", 0.0), volatility=m["volatility"], jump_size=m["jump"], **kw)
+    elif m["kind"] == "ou_jump":
+        mid = MM.OuJumpMidpriceModel(mean_reversion_level=m["level"], mean_reversion_speed=m["speed"],
+                                     volatility=m["volatility"], jump_size=m["jump"], **kw)
     else:
         mid = MM.ConstantMidpriceModel(**kw)
     arr = fill = imp = None
@@ -113,9 +118,15 @@ def build_facade_env(spec, **extra):
             imp = PM.TemporaryAndPermanentPriceImpact(temporary_impact_coefficient=p["temp"],
                                                       permanent_impact_coefficient=p["perm"], n_steps=n_steps,
                                                       terminal_time=T, num_trajectories=N)
-        else:
+        elif p["kind"] == "temp_power":
             imp = PM.TemporaryPowerPriceImpact(temporary_impact_coefficient=p["temp"],
                                                temporary_impact_exponent=p["exponent"], num_trajectories=N)
+        elif p["kind"] == "temp_transient":
+            imp = PM.TemporaryAndTransientPriceImpact(p["temp"], p["transient"], p["resilience"], p["initial"], p["kernel"],
+                                                      n_steps=n_steps, terminal_time=T, num_trajectories=N)
+        else:
+            imp = PM.TransientPriceImpact(p["transient"], p["resilience"], p["initial"], p["kernel"], n_steps=n_steps,
+                                          terminal_time=T, num_trajectories=N)
     kind = spec["dynamics"]
     if kind == "limit":
         dyn = MD.LimitOrderModelDynamics(midprice_model=mid, arrival_model=arr, fill_probability_model=fill, num_trajectories=N)

@@ -44,7 +44,7 @@ static void run(const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, 
             Traj<T> s;
             s.cash = row[0]; s.inv = row[1]; s.mid = row[3]; s.x0 = 0; s.x1 = 0;
             if (c.arrival == MBT_ARR_HAWKES) { s.x0 = row[4]; s.x1 = row[5]; }
-            if (c.impact == MBT_IMP_TEMP_PERM) s.x0 = row[4];
+            if (imp_has_state(c.impact)) s.x0 = row[4];
             T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
             for (int j = 0; j < A; ++j) a[j] = denorm_action<T, V>(p, actions[((int64_t)k * N + i) * A + j], j);
             mbt_u32x4 r = mbt_draw_keyed(keys, (uint64_t)(c.traj_offset + i), (uint64_t)(n_step0 + k), MBT_STREAM_STEP);
@@ -52,7 +52,7 @@ static void run(const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, 
             T rw = step_one<T, V>(p, ck, s, a, r, q0_per_traj ? q0[i] : (T)q0_uniform, &clipped);
             row[0] = s.cash; row[1] = s.inv; row[2] = ck.t_next; row[3] = s.mid;
             if (c.arrival == MBT_ARR_HAWKES) { row[4] = s.x0; row[5] = s.x1; }
-            if (c.impact == MBT_IMP_TEMP_PERM) row[4] = s.x0;
+            if (imp_has_state(c.impact)) row[4] = s.x0;
             for (int d = 0; d < D; ++d) obs[((int64_t)k * N + i) * D + d] = norm_obs<T, V>(p, row[d], d);
             rew[(int64_t)k * N + i] = rw;
         }

@@ -18,7 +18,7 @@ def random_spec(rng):
     T = float(rng.choice([0.5, 1.0, 2.0]))
     spec = dict(N=int(rng.integers(1, 70)), n_steps=int(rng.integers(3, 13)), terminal_time=T,
                 seed=int(rng.integers(1, 2 ** 31)), dynamics=dyn)
-    mk = rng.choice(["bm", "bm", "gbm", "ou", "constant"])
+    mk = rng.choice(["bm", "bm", "gbm", "ou", "constant"] + ([] if dyn == "speed" else ["bm_jump", "ou_jump"]))
     S0 = float(rng.uniform(20, 200))
     if mk == "bm":
         spec["midprice"] = dict(kind="bm", drift=float(rng.uniform(-1, 1)), volatility=float(rng.uniform(0.2, 3)), initial_price=S0)
@@ -27,12 +27,23 @@ def random_spec(rng):
     elif mk == "ou":
         spec["midprice"] = dict(kind="ou", level=S0 + float(rng.uniform(-2, 2)), speed=float(rng.uniform(0.01, 1.0)),
                                 volatility=float(rng.uniform(0.2, 3)), initial_price=S0)
+    elif mk == "bm_jump":
+        spec["midprice"] = dict(kind="bm_jump", drift=float(rng.uniform(-1, 1)), volatility=float(rng.uniform(0.2, 3)),
+                                jump=float(rng.uniform(0.05, 1.0)), initial_price=S0)
+    elif mk == "ou_jump":
+        spec["midprice"] = dict(kind="ou_jump", level=S0 + float(rng.uniform(-2, 2)), speed=float(rng.uniform(0.01, 1.0)),
+                                volatility=float(rng.uniform(0.2, 3)), jump=float(rng.uniform(0.05, 1.0)), initial_price=S0)
     else:
         spec["midprice"] = dict(kind="constant", initial_price=S0)
     rewards = ["pnl", "rip", "cjmm", "exputil"]
     if dyn == "speed":
-        spec["impact"] = (dict(kind="temp_perm", temp=float(rng.uniform(0.001, 0.05)), perm=float(rng.uniform(0.001, 0.05)))
-                          if rng.random() < 0.7 else dict(kind="temp_power", temp=float(rng.uniform(0.001, 0.05)), exponent=1.0))
+        ik = rng.choice(["temp_perm", "temp_perm", "temp_power", "temp_transient", "transient"])
+        tr = dict(transient=float(rng.uniform(0.1, 1.0)), resilience=float(rng.uniform(0.1, 3.0)),
+                  initial=float(rng.uniform(0, 0.05)), kernel=float(rng.uniform(0.1, 1.0)))
+        spec["impact"] = {"temp_perm": dict(kind="temp_perm", temp=float(rng.uniform(0.001, 0.05)), perm=float(rng.uniform(0.001, 0.05))),
+                          "temp_power": dict(kind="temp_power", temp=float(rng.uniform(0.001, 0.05)), exponent=1.0),
+                          "temp_transient": dict(kind="temp_transient", temp=float(rng.uniform(0.001, 0.05)), **tr),
+                          "transient": dict(kind="transient", **tr)}[str(ik)]
         rewards = ["pnl", "rip", "cjoe", "cjmm"]
         spec["initial_inventory"] = int(rng.integers(-50, 51))
     else:

@@ -79,6 +79,21 @@ SPECS = {
                              half_spread=0.25, reward=dict(kind="rip", phi=0.01, alpha=0.01), max_inventory=5, **AS),
     "exputil": dict(N=53, n_steps=25, terminal_time=1.0, seed=1243, dynamics="limit",
                     reward=dict(kind="exputil", risk_aversion=0.01), max_inventory=100, **AS),
+    "bm_jump": dict(N=57, n_steps=40, terminal_time=1.0, seed=1245, dynamics="limit",
+                    midprice=dict(kind="bm_jump", drift=0.1, volatility=1.5, jump=0.25, initial_price=100.0),
+                    arrival=AS["arrival"], fill=AS["fill"], reward=dict(kind="pnl"), max_inventory=3),
+    "ou_jump_hawkes": dict(N=47, n_steps=40, terminal_time=1.0, seed=1246, dynamics="limit",
+                           midprice=dict(kind="ou_jump", level=100.0, speed=0.1, volatility=1.0, jump=0.5, initial_price=100.5),
+                           arrival=dict(kind="hawkes", baseline=[30.0, 20.0], jump=20.0, speed=40.0), fill=AS["fill"],
+                           reward=dict(kind="rip", phi=0.01, alpha=0.1), max_inventory=50, normalise_obs=True),
+    "oe_temp_transient": dict(N=43, n_steps=40, terminal_time=1.0, seed=1247, dynamics="speed",
+                              midprice=dict(kind="bm", volatility=1.0, initial_price=100.0),
+                              impact=dict(kind="temp_transient", temp=0.01, transient=0.5, resilience=2.0, initial=0.02, kernel=0.3),
+                              reward=dict(kind="cjoe", phi=0.01, alpha=0.001), initial_inventory=20, max_inventory=1000),
+    "oe_transient": dict(N=37, n_steps=30, terminal_time=1.0, seed=1248, dynamics="speed",
+                         midprice=dict(kind="gbm", drift=0.02, volatility=0.1, initial_price=80.0),
+                         impact=dict(kind="transient", transient=0.8, resilience=1.0, initial=0.0, kernel=0.5),
+                         reward=dict(kind="pnl"), initial_inventory=-15, max_inventory=1000, normalise_action=True),
     # two episodes back to back: RNG stream continues, reset redraws inventories
     "two_episodes": dict(N=59, n_steps=30, terminal_time=1.0, seed=1244, dynamics="limit",
                          reward=dict(kind="cjmm", phi=0.01, alpha=0.001), max_inventory=20,
