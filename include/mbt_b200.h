@@ -283,6 +283,17 @@ int mbt_reward_eval(mbt_env *env, int64_t n, const void *current_state, const vo
 int mbt_rollout(mbt_env *env, const mbt_policy *policy, mbt_summary *summary_out, void *returns_out,
                 void *terminal_q_out, int mem);
 
+/* mbt_rollout that also records the whole trajectory, i.e. what generate_trajectory returns
+ * (gym/helpers/generate_trajectory.py:13-15,19,27-29).  Buffers are TIME-MAJOR (every store coalesced):
+ *   obs (steps+1, N, D), actions (steps, N, A) as the policy returned them, rewards (steps, N);
+ * the reference's (N, D, T+1) / (N, A, T) / (N, 1, T) are transposed views of these.  Any of the three may be NULL.
+ * `steps_capacity` is the number of steps the buffers can hold; MBT_E_INVALID_ARG if the episode needs more. */
+typedef struct mbt_record {
+    void *obs, *actions, *rewards;
+    int64_t steps_capacity;
+} mbt_record;
+int mbt_rollout_record(mbt_env *env, const mbt_policy *policy, mbt_summary *summary_out, const mbt_record *record, int mem);
+
 /* Per-call statistics for bench.py: number of kernel launches issued by this handle so far, and the
  * device time (ms, CUDA events on the handle's stream) of the most recent step kernel when enabled. */
 int mbt_get_launch_count(mbt_env *env, int64_t *launches);

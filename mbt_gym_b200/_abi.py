@@ -153,6 +153,10 @@ class mbt_policy(C.Structure):
     ]
 
 
+class mbt_record(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("actions", C.c_void_p), ("rewards", C.c_void_p), ("steps_capacity", C.c_int64)]
+
+
 class mbt_summary(C.Structure):
     _fields_ = [
         ("count", C.c_int64),

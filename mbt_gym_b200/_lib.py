@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libmbt_b200.so")
 ABI_SYMBOLS = [
     "mbt_abi_version", "mbt_last_error", "mbt_config_dims", "mbt_create", "mbt_destroy", "mbt_set_stream", "mbt_sync",
     "mbt_seed", "mbt_reset", "mbt_step", "mbt_get_state", "mbt_set_state", "mbt_get_clock", "mbt_get_clip_count",
-    "mbt_reward_eval", "mbt_rollout", "mbt_get_launch_count", "mbt_enable_timing", "mbt_get_kernel_times",
+    "mbt_reward_eval", "mbt_rollout", "mbt_rollout_record", "mbt_get_launch_count", "mbt_enable_timing", "mbt_get_kernel_times",
     "mbt_host_alloc", "mbt_host_alloc_near", "mbt_host_free", "mbt_checkpoint_size", "mbt_checkpoint_save",
     "mbt_checkpoint_load",
 ]
@@ -59,6 +59,7 @@ def load():
     L.mbt_get_clip_count.argtypes = [vp, i64p]
     L.mbt_reward_eval.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, vp, C.c_int]
     L.mbt_rollout.argtypes = [vp, C.POINTER(_abi.mbt_policy), C.POINTER(_abi.mbt_summary), vp, vp, C.c_int]
+    L.mbt_rollout_record.argtypes = [vp, C.POINTER(_abi.mbt_policy), C.POINTER(_abi.mbt_summary), C.POINTER(_abi.mbt_record), C.c_int]
     L.mbt_get_launch_count.argtypes = [vp, i64p]
     L.mbt_enable_timing.argtypes = [vp, C.c_int]
     L.mbt_get_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int64, i64p]
@@ -172,6 +173,17 @@ class NativeEnv:
         summary = _abi.mbt_summary()
         _check(load().mbt_rollout(self._h, C.byref(policy), C.byref(summary), _addr(returns_out), _addr(terminal_q_out), mem))
         return summary
+
+    def rollout_record(self, policy, steps_capacity, obs=True, actions=True, rewards=True):
+        """Fused rollout that records the trajectory into host arrays (time-major); returns (summary, obs, act, rew)."""
+        o = np.empty((steps_capacity + 1, self.N, self.D), self.dtype) if obs else None
+        a = np.empty((steps_capacity, self.N, self.A), self.dtype) if actions else None
+        r = np.empty((steps_capacity, self.N), self.dtype) if rewards else None
+        rec = _abi.mbt_record(_addr(o), _addr(a), _addr(r), int(steps_capacity))
+        summary = _abi.mbt_summary()
+        _check(load().mbt_rollout_record(self._h, C.byref(policy), C.byref(summary), C.byref(rec), _abi.MBT_MEM_HOST))
+        n = int(summary.steps)
+        return summary, (None if o is None else o[: n + 1]), (None if a is None else a[:n]), (None if r is None else r[:n])
 
     # -- state
     def get_state(self, out=None, mem=_abi.MBT_MEM_HOST):

@@ -852,7 +852,8 @@ int mbt_reward_eval(mbt_env *e, int64_t n, const void *current_state, const void
 } /* extern "C" */
 
 template <typename T>
-static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, void *returns, void *term_q) {
+static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, void *returns, void *term_q,
+                      const mbt_record *rec = nullptr) {
     const mbt_config &c = e->cfg;
     /* the clock exactly as repeated `state[:, TIME] += step_size` produces it   TradingEnvironment.py:216 */
     std::vector<double> times;
@@ -920,6 +921,12 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
     if (pol->kind == MBT_POL_AVELLANEDA_STOIKOV && e->A != 2) return fail(MBT_E_UNSUPPORTED, "Avellaneda-Stoikov policy needs a 2-d action");
     g.returns = (T *)returns;
     g.term_q = (T *)term_q;
+    if (rec) {
+        if (rec->steps_capacity < steps) return fail(MBT_E_INVALID_ARG, "record buffers hold fewer steps than the episode has left");
+        g.rec_obs = (T *)rec->obs;
+        g.rec_act = (T *)rec->actions;
+        g.rec_rew = (T *)rec->rewards;
+    }
     const int blocks = (int)grid_for(g.n);
     if (blocks > e->block_sums_cap) {
         cudaFree(e->d_block_sums);
@@ -991,6 +998,43 @@ int mbt_rollout(mbt_env *e, const mbt_policy *policy, mbt_summary *summary_out, 
         CU(cudaStreamSynchronize(e->stream));
     }
     return MBT_OK;
+}
+
+int mbt_rollout_record(mbt_env *e, const mbt_policy *policy, mbt_summary *summary_out, const mbt_record *record, int mem) {
+    if (!e || !policy || !record) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    if (!e->started) return fail(MBT_E_STATE, "mbt_rollout_record called before mbt_reset");
+    if (e->t >= e->cfg.terminal_time - e->cfg.step_size / 2) return fail(MBT_E_STATE, "episode already finished; call mbt_reset");
+    if (record->steps_capacity <= 0) return fail(MBT_E_INVALID_ARG, "steps_capacity must be > 0");
+    CU(cudaSetDevice(e->device));
+    const size_t cap = (size_t)record->steps_capacity;
+    const size_t ob = (cap + 1) * (size_t)e->N * e->D * e->esz, ab = cap * (size_t)e->N * e->A * e->esz, rb = cap * (size_t)e->N * e->esz;
+    mbt_record dev = *record;
+    void *tmp = nullptr;
+    if (mem == MBT_MEM_HOST) { /* stage through one temporary device block */
+        const size_t need = (record->obs ? ob : 0) + (record->actions ? ab : 0) + (record->rewards ? rb : 0);
+        cudaError_t me = cudaMalloc(&tmp, need ? need : 1);
+        if (me != cudaSuccess) {
+            cudaGetLastError();
+            return fail(MBT_E_NOMEM, "not enough device memory to record the trajectory; record fewer trajectories");
+        }
+        char *b = (char *)tmp;
+        dev.obs = record->obs ? b : nullptr;      b += record->obs ? ob : 0;
+        dev.actions = record->actions ? b : nullptr; b += record->actions ? ab : 0;
+        dev.rewards = record->rewards ? b : nullptr;
+    }
+    int rc = e->cfg.precision == MBT_F64 ? do_rollout<double>(e, policy, summary_out, nullptr, nullptr, &dev)
+                                         : do_rollout<float>(e, policy, summary_out, nullptr, nullptr, &dev);
+    if (rc == MBT_OK && mem == MBT_MEM_HOST) {
+        cudaError_t ce = cudaSuccess;
+        if (record->obs) ce = cudaMemcpyAsync(record->obs, dev.obs, ob, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess && record->actions) ce = cudaMemcpyAsync(record->actions, dev.actions, ab, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess && record->rewards) ce = cudaMemcpyAsync(record->rewards, dev.rewards, rb, cudaMemcpyDeviceToHost, e->stream);
+        cudaError_t se = cudaStreamSynchronize(e->stream);
+        if (ce == cudaSuccess) ce = se;
+        if (ce != cudaSuccess) rc = fail(MBT_E_CUDA, std::string("mbt_rollout_record: ") + cudaGetErrorString(ce));
+    }
+    if (tmp) cudaFree(tmp);
+    return rc;
 }
 
 int mbt_get_launch_count(mbt_env *e, int64_t *launches) {

@@ -309,6 +309,10 @@ struct RolloutArgs {
     /* outputs */
     T *returns; /* (N,) or NULL */
     T *term_q;  /* (N,) or NULL */
+    /* optional full recording, TIME-MAJOR so every store is a coalesced row write:
+     * rec_obs (steps+1, N, D) normalised like reset()/step() return them, rec_act (steps, N, A) as the agent
+     * returned them, rec_rew (steps, N).  The host exposes them transposed, in the shapes of generate_trajectory. */
+    T *rec_obs, *rec_act, *rec_rew;
     double *block_sums; /* (gridDim.x, MBT_SUMMARY_DOUBLES) */
     unsigned long long *clipped;
 };
@@ -354,6 +358,12 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
         T ret = (T)0;
         int clipped = 0;
         double t_cur = g.times[0];
+        const int D = obs_width<T, V>(p);
+        if (g.rec_obs) {
+            T row[MBT_MAX_OBS_DIM];
+            make_obs_row<T, V>(p, s, (T)t_cur, row);
+            store_row<T>(g.rec_obs, i, D, row, false);
+        }
         for (int k = 0; k < g.steps; ++k) {
             const double t_next = g.times[k + 1];
             StepClock<T> ck;
@@ -362,6 +372,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
             ck.done = t_next >= g.terminal_time - g.step_size / 2;
             T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
             policy_action<T>(g, k, (T)t_cur, s, a);
+            if (g.rec_act) store_row<T>(g.rec_act, (long long)k * g.n + i, A, a, false);
 #pragma unroll
             for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j)
                 if (j < A) {
@@ -372,6 +383,12 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
             const T rwd = step_one<T, V>(p, ck, s, a, r, q_init, &clipped);
             ret = ret + rwd;
             acc[5] += (double)rwd * (double)rwd;
+            if (g.rec_rew) g.rec_rew[(long long)k * g.n + i] = rwd;
+            if (g.rec_obs) {
+                T row[MBT_MAX_OBS_DIM];
+                make_obs_row<T, V>(p, s, ck.t_next, row);
+                store_row<T>(g.rec_obs, (long long)(k + 1) * g.n + i, D, row, false);
+            }
             t_cur = t_next;
         }
         store_traj<T, V>(p, g.st, i, s);

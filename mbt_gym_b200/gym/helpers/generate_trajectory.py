@@ -35,6 +35,18 @@ def generate_trajectory(env, agent, seed=None, include_log_probs=False):
     return (observations, actions, rewards, log_probs) if include_log_probs else (observations, actions, rewards)
 
 
+def generate_trajectory_fused(env, agent, seed=None):
+    """`generate_trajectory` for agents with an on-device form (`agent.to_policy`): the whole episode runs in ONE kernel
+    and the recording comes back in the reference's shapes -- observations (N, D, T+1), actions (N, A, T),
+    rewards (N, 1, T) -- as transposed views of the time-major device recording."""
+    if seed is not None:
+        env.seed(seed)
+    env.reset()
+    native = env._native
+    _summary, obs, act, rew = native.rollout_record(agent.to_policy(env), env.n_steps)
+    return obs.transpose(1, 2, 0), act.transpose(1, 2, 0), rew.T[:, None, :]
+
+
 RESULT_COLUMNS = ["Mean spread", "Mean PnL", "Std PnL", "Mean terminal inventory", "Std terminal inventory"]
 
 

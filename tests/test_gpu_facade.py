@@ -220,3 +220,37 @@ def test_checkpoint_resume_is_exact():
     with pytest.raises(Exception):
         build_facade_env(dict(SPECS["cjmm"], N=7)).load_checkpoint(blob)
     env.close(); other.close()
+
+
+def test_generate_trajectory_fused_equals_stepwise_generate_trajectory():
+    """The fused, recording rollout returns exactly what the reference-style step-by-step helper returns."""
+    from mbt_gym_b200.agents.BaselineAgents import AvellanedaStoikovAgent, CarteaJaimungalMmAgent, CarteaJaimungalOeAgent
+    from mbt_gym_b200.gym.helpers.generate_trajectory import generate_trajectory, generate_trajectory_fused
+
+    import warnings
+    for name, make_agent in [("as_pnl", lambda e: AvellanedaStoikovAgent(0.1, e)),
+                             ("cjmm", lambda e: CarteaJaimungalMmAgent(e)),
+                             ("oe_ou_cjoe", lambda e: CarteaJaimungalOeAgent(env=e)),
+                             ("hawkes_normalised", None)]:
+        spec = dict(SPECS[name], N=300)
+        if name == "cjmm":
+            spec.update(initial_inventory=0, start_time=0.0)
+        if name == "hawkes_normalised":
+            spec.update(normalise_action=False)
+        env = build_facade_env(spec)
+        if make_agent is None:
+            from mbt_gym_b200.agents.BaselineAgents import FixedSpreadAgent
+            agent = FixedSpreadAgent(env, half_spread=0.8, offset=0.1)
+        else:
+            agent = make_agent(env)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            env.seed(123)
+            o1, a1, r1 = generate_trajectory(env, agent)
+            env.seed(123)
+            o2, a2, r2 = generate_trajectory_fused(env, agent)
+        assert o2.shape == o1.shape and a2.shape == a1.shape and r2.shape == r1.shape, name
+        assert_same(a2, a1, what=f"{name} actions")
+        assert_same(o2, o1, what=f"{name} observations")
+        assert_same(r2, r1, what=f"{name} rewards")
+        env.close()

@@ -22,7 +22,9 @@ SO = os.path.join(ROOT, "tests", "hostsim", "_build", "libhostsim.so")
 @pytest.fixture(scope="module")
 def hostsim():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-march=x86-64-v3", "-x", "c++",
+    cpuinfo = open("/proc/cpuinfo").read() if os.path.exists("/proc/cpuinfo") else ""
+    march = ["-march=x86-64-v3"] if (" fma" in cpuinfo and " avx2" in cpuinfo) else []
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", *march, "-x", "c++",
                     SRC, "-o", SO], check=True)
     lib = C.CDLL(SO)
     vp = C.c_void_p
