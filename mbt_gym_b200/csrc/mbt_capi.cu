@@ -943,7 +943,11 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
     int rc = timing_begin(e);
     if (rc) return rc;
     switch (variant_of(c)) {
-#define X(id, ...) case id: mbt_rollout_kernel<T, __VA_ARGS__><<<blocks, MBT_BLOCK, 0, e->stream>>>(g); break;
+#define X(id, ...)                                                                                  \
+    case id:                                                                                        \
+        if (rec) mbt_rollout_kernel<T, __VA_ARGS__, true><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);  \
+        else mbt_rollout_kernel<T, __VA_ARGS__, false><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);     \
+        break;
         MBT_FOR_EACH_VARIANT(X)
 #undef X
     }

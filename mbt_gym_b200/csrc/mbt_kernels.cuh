@@ -342,7 +342,8 @@ __device__ __forceinline__ void policy_action(const RolloutArgs<T> &g, int k, T 
     }
 }
 
-template <typename T, class V>
+/* REC: compile the trajectory-recording stores in (mbt_rollout_record) or out (mbt_rollout, the fast path) */
+template <typename T, class V, bool REC>
 __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_constant__ RolloutArgs<T> g) {
     const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
     const bool live = i < g.n;
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
         int clipped = 0;
         double t_cur = g.times[0];
         const int D = obs_width<T, V>(p);
-        if (g.rec_obs) {
+        if (REC && g.rec_obs) {
             T row[MBT_MAX_OBS_DIM];
             make_obs_row<T, V>(p, s, (T)t_cur, row);
             store_row<T>(g.rec_obs, i, D, row, false);
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
             ck.done = t_next >= g.terminal_time - g.step_size / 2;
             T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
             policy_action<T>(g, k, (T)t_cur, s, a);
-            if (g.rec_act) store_row<T>(g.rec_act, (long long)k * g.n + i, A, a, false);
+            if (REC && g.rec_act) store_row<T>(g.rec_act, (long long)k * g.n + i, A, a, false);
 #pragma unroll
             for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j)
                 if (j < A) {
@@ -383,8 +384,8 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
             const T rwd = step_one<T, V>(p, ck, s, a, r, q_init, &clipped);
             ret = ret + rwd;
             acc[5] += (double)rwd * (double)rwd;
-            if (g.rec_rew) g.rec_rew[(long long)k * g.n + i] = rwd;
-            if (g.rec_obs) {
+            if (REC && g.rec_rew) g.rec_rew[(long long)k * g.n + i] = rwd;
+            if (REC && g.rec_obs) {
                 T row[MBT_MAX_OBS_DIM];
                 make_obs_row<T, V>(p, s, ck.t_next, row);
                 store_row<T>(g.rec_obs, (long long)(k + 1) * g.n + i, D, row, false);
