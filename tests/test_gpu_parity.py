@@ -276,3 +276,52 @@ def test_full_size_properties_2pow20():
     assert abs(qT.std() - 2.893544) < 4 * 2.893544 / np.sqrt(2 * 1000)
     np.testing.assert_allclose(s.sum_return / N, mean_pnl, rtol=1e-10)
     assert np.all(qT == np.round(qT))
+
+
+def test_inventory_distribution_and_reward_per_step_vs_numpy_port():
+    """statistical parity of the Philox/CUDA path with the PCG64/NumPy path on the quantities
+    BASELINE.json names -- terminal-inventory distribution (chi-square, p > 0.001), mean terminal PnL and mean reward per
+    step (4 standard errors) -- for the Avellaneda-Stoikov agent.  The NumPy port reproduces the reference's notebook
+    golden exactly (tests/test_reference_live.py), so it stands in for the reference on the GPU box."""
+    from scipy import stats
+
+    from oracle import numpy_port as P
+
+    g = Golden("as_pnl")
+    gamma, n_gpu, n_ref = 0.1, 1 << 18, 1 << 15
+    cfg = g.config(_abi.MBT_F64, num_trajectories=n_gpu)
+    pol = _abi.mbt_policy()
+    pol.kind = _abi.MBT_POL_AVELLANEDA_STOIKOV
+    pol.as_gamma, pol.as_sigma_sq = gamma, cfg.mid_vol ** 2
+    pol.as_fill_comp = 2 / gamma * np.log(1 + gamma / cfg.fill_exponent)
+    pol.as_terminal_time = cfg.terminal_time
+    e = _lib.NativeEnv(cfg)
+    e.seed(2024)
+    e.reset()
+    ret = np.empty(n_gpu); qT = np.empty(n_gpu)
+    e.rollout(pol, ret, qT)
+    e.close()
+    ref = P.NumpyPortEnv("as", N=n_ref, seed=77)
+    obs = ref.reset()
+    R = np.zeros(n_ref)
+    while True:
+        obs, r, d, _ = ref.step(P.as_agent_action(obs, gamma, 2.0, 1.5, 1.0))
+        R += r
+        if d[0]:
+            break
+    q_ref = obs[:, 1]
+    # mean terminal PnL and mean reward per step
+    se = np.hypot(ret.std() / np.sqrt(n_gpu), R.std() / np.sqrt(n_ref))
+    assert abs(ret.mean() - R.mean()) < 4 * se
+    assert abs(ret.mean() / 200 - R.mean() / 200) < 4 * se / 200
+    assert abs(ret.std() - R.std()) < 4 * R.std() / np.sqrt(2 * n_ref)
+    # terminal inventory histogram: chi-square homogeneity test, bins with expected count >= 10
+    lo, hi = int(min(qT.min(), q_ref.min())), int(max(qT.max(), q_ref.max()))
+    bins = np.arange(lo - 0.5, hi + 1.5)
+    h_gpu, _ = np.histogram(qT, bins)
+    h_ref, _ = np.histogram(q_ref, bins)
+    keep = (h_gpu + h_ref) * (n_ref / (n_gpu + n_ref)) >= 10
+    table = np.array([np.append(h_gpu[keep], h_gpu[~keep].sum()), np.append(h_ref[keep], h_ref[~keep].sum())])
+    table = table[:, table.sum(axis=0) > 0]
+    chi2, p, dof, _ = stats.chi2_contingency(table)
+    assert p > 0.001, (chi2, p, dof)
