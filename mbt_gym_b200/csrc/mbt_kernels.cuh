@@ -112,6 +112,27 @@ __device__ __forceinline__ void store_row(T *__restrict__ base, long long i, int
     }
 }
 
+/*
+ * Observation rows whose width is not a power of two (D = 5: price-impact column, D = 6: Hawkes intensities) cannot
+ * be written with one aligned vector per thread; per-thread scalar stores would touch every 32 B sector of the warp's
+ * 32 x D block several times.  Instead the warp stages its block in shared memory and writes it back as contiguous
+ * runs -- lane l stores elements l, l+32, ... of the block -- so every store instruction covers 32 consecutive elements
+ * (full 128 B / 256 B lines).  Only used when all 32 lanes hold valid rows (the last partial warp stores per thread).
+ */
+template <typename T>
+__device__ __forceinline__ void store_rows_staged(T *__restrict__ base, long long warp_row0, int w, const T *v,
+                                                  T *warp_smem, unsigned lane) {
+#pragma unroll
+    for (int j = 0; j < MBT_MAX_OBS_DIM; ++j)
+        if (j < w) warp_smem[lane * w + j] = v[j];
+    __syncwarp();
+    T *dst = base + warp_row0 * w;
+#pragma unroll
+    for (int j = 0; j < MBT_MAX_OBS_DIM; ++j)
+        if (j < w) dst[j * 32 + lane] = warp_smem[j * 32 + lane];
+    __syncwarp();
+}
+
 /* observation row of one trajectory: [cash, inventory, time, midprice | arrival cols | impact col]
  * (TradingEnvironment.py:131-140,303-318), normalised on the way out (:112-118). */
 template <typename T, class V>
@@ -155,7 +176,7 @@ __device__ __forceinline__ void store_traj(const StepParams<T> &p, const DevStat
 /* ------------------------------------------------------------------ step */
 /* One trajectory, one env-step: load state + action row, draw, advance, store state + observation row + reward. */
 template <typename T, class V, bool VEC>
-__device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i) {
+__device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i, bool full_warp, T *warp_smem) {
     const StepParams<T> &p = g.p;
     const int A = action_width<T, V>(p);
     T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
@@ -178,7 +199,11 @@ __device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i) {
     if (g.obs) {
         T row[MBT_MAX_OBS_DIM];
         make_obs_row<T, V>(p, s, g.ck.t_next, row);
-        store_row<T>(g.obs, i, obs_width<T, V>(p), row, VEC);
+        const int D = obs_width<T, V>(p);
+        if (D != 4 && full_warp)
+            store_rows_staged<T>(g.obs, i - (long long)(threadIdx.x & 31u), D, row, warp_smem, threadIdx.x & 31u);
+        else
+            store_row<T>(g.obs, i, D, row, VEC);
     }
     if (g.rew) g.rew[i] = rwd;
     if (clipped) atomicAdd(g.clipped, 1ull);
@@ -193,8 +218,14 @@ __device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i) {
  */
 template <typename T, class V, bool VEC>
 __global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_constant__ StepArgs<T> g) {
+    /* staging for non-power-of-two observation rows: one 32 x MBT_MAX_OBS_DIM tile per warp (unused when D == 4) */
+    constexpr int SW = V::D ? V::D : MBT_MAX_OBS_DIM; /* staged row width */
+    __shared__ T smem[(V::D == 4) ? 1 : (MBT_BLOCK / 32) * 32 * SW];
     const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
-    if (i < g.n) step_row<T, V, VEC>(g, i);
+    const long long warp_row0 = i - (long long)(threadIdx.x & 31u);
+    const bool full_warp = (V::D != 4) && (warp_row0 + 32 <= g.n); /* warp-uniform */
+    T *warp_smem = (V::D == 4) ? smem : smem + (threadIdx.x >> 5) * 32 * SW;
+    if (i < g.n) step_row<T, V, VEC>(g, i, full_warp, warp_smem);
 }
 
 /* ------------------------------------------------------------------ reset */
