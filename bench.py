@@ -155,7 +155,15 @@ def size_matched_copy_us(nbytes, stream, reps=60):
         b.record(stream)
     torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in evs)
-    return 1e3 * ms[len(ms) // 2]
+    bracketed = 1e3 * ms[len(ms) // 2]
+    # and back to back, timed like the step loop: two events around `reps` copies
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for k in range(reps):
+        dst[k % nbuf].copy_(src[k % nbuf])
+    b.record(stream)
+    torch.cuda.synchronize()
+    return bracketed, 1e3 * a.elapsed_time(b) / reps
 
 
 def cpu_baseline(workload, seconds_target=15.0):
@@ -219,6 +227,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--no-episode-stats", action="store_true")
+    ap.add_argument("--timing-mode", type=int, default=0, choices=[0, 1, 2],
+                    help="extra per-kernel CUDA events INSIDE the timed region: 0 = none (only the two bracket events; "
+                         "default), 1 = two events per launch, 2 = one event per launch.  They perturb the loop: "
+                         "18.6 / 23.8 / 21.2 us per step on a B200 (profiles/r1_step_kernel_history.md)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -273,7 +285,7 @@ def main():
                 env.reset(obs[i], mem=_abi.MBT_MEM_DEVICE)
 
     env.reset(obs[0], mem=_abi.MBT_MEM_DEVICE)
-    run_steps(args.warmup, False)
+    run_steps(args.warmup, 0)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -283,14 +295,20 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    run_steps(args.steps, True)
+    run_steps(args.steps, args.timing_mode)
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = env.launch_count() - launches0
-    ktimes = env.kernel_times_ms()
-    env.enable_timing(False)
-    copy_us = size_matched_copy_us(N * algorithmic_bytes_per_env_step(A, D, esz), stream) if rank == 0 else None
+    ktimes = env.kernel_times_ms() if args.timing_mode else np.array([])
+    env.enable_timing(0)
+    # separate instrumented pass (NOT the timed region): every launch bracketed by its own two events
+    barrier()
+    run_steps(min(args.steps, 100), 1)
+    barrier()
+    ktimes_bracketed = env.kernel_times_ms()
+    env.enable_timing(0)
+    copy_us, copy_b2b_us = size_matched_copy_us(N * algorithmic_bytes_per_env_step(A, D, esz), stream) if rank == 0 else (None, None)
     env.set_stream(None)  # back to the handle's own stream for the host-buffer path
 
     # ---- e2e: the call a user makes -- TradingEnvironment.step(numpy action) -> numpy obs, rewards, dones, infos.
@@ -364,7 +382,9 @@ def main():
         e2e_value = total_n * e2e_steps / (e2e_ms * 1e-3)
         b_step = algorithmic_bytes_per_env_step(A, D, esz)
         peak, peak_src = measured_hbm_peak()
-        mean_kernel_ms = float(np.mean(ktimes)) if len(ktimes) else float("nan")
+        # launch duration over the timed region: the two CUDA events that bracket the K back-to-back steps, divided by K.
+        # An upper bound on the kernel's own duration (it still contains the launch gaps and 1 reset per 200 steps).
+        mean_kernel_ms = float(np.mean(ktimes)) if len(ktimes) else elapsed_ms / args.steps
         achieved = N * b_step / (mean_kernel_ms * 1e-3) / 1e9
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
@@ -383,13 +403,19 @@ def main():
                          "traffic": NCU_DRAM_TRAFFIC_BYTES.get((args.workload, args.precision)) if N == N_PER_GPU else None,
                          "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/ (cold cache)",
                          "peak_source": peak_src, "kernel": "mbt_step_kernel",
-                         "size_matched_copy_us": copy_us,
-                         "frac_of_size_matched_copy": (copy_us * 1e-3 / mean_kernel_ms) if copy_us else None,
-                         "note": "peak is a 2 GiB copy; size_matched_copy_us is a plain device copy of the same bytes as one "
-                                 "step, timed the same way: the fixed launch/ramp/drain cost at this size is common to both",
+                         "size_matched_copy_us": copy_b2b_us if not len(ktimes) else copy_us,
+                         "frac_of_size_matched_copy": ((copy_b2b_us if not len(ktimes) else copy_us) * 1e-3 / mean_kernel_ms) if copy_us else None,
+                         "size_matched_copy_two_event_bracket_us": copy_us,
+                         "note": "peak is a 2 GiB copy; size_matched_copy_us is a plain torch device copy of the same bytes as one "
+                                 "step, timed the same way as mean_kernel_ms: the fixed launch/ramp/drain cost at this size is common to both",
                          "algorithmic_bytes_per_env_step": b_step, "mean_kernel_ms": mean_kernel_ms,
-                         "kernel_launches_timed": int(len(ktimes)),
-                         "kernel_share_of_step": mean_kernel_ms / (elapsed_ms / args.steps)},
+                         "duration_method": ("CUDA events bracketing the timed region / steps (upper bound: includes launch gaps)"
+                                             if not len(ktimes) else f"per-launch CUDA events inside the timed region (mode {args.timing_mode})"),
+                         "kernel_launches_timed": int(len(ktimes)) if len(ktimes) else int(args.steps),
+                         "kernel_share_of_step": mean_kernel_ms / (elapsed_ms / args.steps),
+                         "two_event_bracket_kernel_us": float(1e3 * np.mean(ktimes_bracketed)) if len(ktimes_bracketed) else None,
+                         "two_event_bracket_note": "separate pass, each launch between its own two events: the events add ~3-5 us "
+                                                   "per launch (a 1-element kernel reads 6.5 us this way)"},
             "clocks": clocks,
             "episode_stats": episode,
         }

@@ -297,8 +297,10 @@ int mbt_rollout_record(mbt_env *env, const mbt_policy *policy, mbt_summary *summ
 /* Per-call statistics for bench.py: number of kernel launches issued by this handle so far, and the
  * device time (ms, CUDA events on the handle's stream) of the most recent step kernel when enabled. */
 int mbt_get_launch_count(mbt_env *env, int64_t *launches);
-/* enable != 0: bracket every subsequent hot-path kernel (step / rollout) with CUDA events on the handle's
- * stream (up to an internal ring capacity); mbt_get_kernel_times synchronises and returns their durations. */
+/* enable = 1: bracket every subsequent hot-path kernel (step / rollout) with two CUDA events on the handle's stream;
+ * enable = 2: ONE event before every kernel, a launch's duration being the interval to the next launch's event
+ * (kernel + gap: an upper bound that perturbs a back-to-back loop half as much); 0: off.  Up to an internal ring
+ * capacity.  mbt_get_kernel_times synchronises and returns the durations (call it once after the measured loop). */
 int mbt_enable_timing(mbt_env *env, int enable);
 int mbt_get_kernel_times(mbt_env *env, float *ms_out, int64_t capacity, int64_t *count);
 

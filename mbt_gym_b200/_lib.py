@@ -235,8 +235,9 @@ class NativeEnv:
         _check(load().mbt_get_launch_count(self._h, C.byref(c)))
         return c.value
 
-    def enable_timing(self, on=True):
-        _check(load().mbt_enable_timing(self._h, int(bool(on))))
+    def enable_timing(self, mode=1):
+        """0 off; 1 two events around each kernel; 2 one event per kernel (interval to the next launch)."""
+        _check(load().mbt_enable_timing(self._h, int(mode)))
 
     def kernel_times_ms(self):
         n = C.c_int64()

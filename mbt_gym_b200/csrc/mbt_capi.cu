@@ -83,9 +83,10 @@ struct mbt_env {
 
     /* statistics */
     int64_t launches = 0;
-    bool timing = false;
+    int timing = 0; /* 0 off, 1 two events around every kernel, 2 one event before every kernel (interval timing) */
     std::vector<cudaEvent_t> ev0, ev1;
     int64_t timed = 0;
+    bool interval_closed = false;
 };
 
 template <typename T>
@@ -116,7 +117,7 @@ static int timing_begin(mbt_env *e) {
 }
 static int timing_end(mbt_env *e) {
     if (!e->timing || e->timed >= MBT_TIMING_RING) return MBT_OK;
-    CU(cudaEventRecord(e->ev1[e->timed], e->stream));
+    if (e->timing == 1) CU(cudaEventRecord(e->ev1[e->timed], e->stream));
     e->timed += 1;
     return MBT_OK;
 }
@@ -1049,17 +1050,28 @@ int mbt_get_launch_count(mbt_env *e, int64_t *launches) {
 
 int mbt_enable_timing(mbt_env *e, int enable) {
     if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
-    e->timing = enable != 0;
+    e->timing = enable == 2 ? 2 : (enable != 0 ? 1 : 0);
     e->timed = 0;
+    e->interval_closed = false;
     return MBT_OK;
 }
 
 int mbt_get_kernel_times(mbt_env *e, float *ms_out, int64_t capacity, int64_t *count) {
     if (!e || !count) return fail(MBT_E_INVALID_ARG, "NULL argument");
     CU(cudaSetDevice(e->device));
+    if (e->timing == 2 && e->timed > 0 && !e->interval_closed) {
+        /* interval mode: launch i lasted from its own event to the next launch's event; close the last interval */
+        CU(cudaEventRecord(e->ev1[e->timed - 1], e->stream));
+        e->interval_closed = true;
+    }
     CU(cudaStreamSynchronize(e->stream));
     int64_t n = std::min<int64_t>(e->timed, capacity);
-    for (int64_t i = 0; i < n && ms_out; ++i) CU(cudaEventElapsedTime(&ms_out[i], e->ev0[i], e->ev1[i]));
+    for (int64_t i = 0; i < n && ms_out; ++i) {
+        if (e->timing == 2 && i + 1 < e->timed)
+            CU(cudaEventElapsedTime(&ms_out[i], e->ev0[i], e->ev0[i + 1]));
+        else
+            CU(cudaEventElapsedTime(&ms_out[i], e->ev0[i], e->ev1[i]));
+    }
     *count = e->timed;
     return MBT_OK;
 }
