@@ -321,7 +321,7 @@ static int do_step_device(mbt_env *e, const void *actions, void *obs, void *rew,
     const mbt_config &c = e->cfg;
     const double t_next = e->t + c.step_size; /* state[:, TIME] += step_size   TradingEnvironment.py:216 */
     const StepParams<T> p = mbt_make_params<T>(c, e->t0, e->q0_per_traj, e->q0_uniform);
-    const StepClock<T> ck = mbt_make_clock<T>(c, e->t, t_next);
+    const StepClock<T> ck = mbt_make_clock<T>(c, e->t, t_next, e->t0);
     int rc = timing_begin(e);
     if (rc) return rc;
     rc = launch_step_rows<T>(e, p, ck, actions, obs, rew, 0, e->N);
@@ -363,7 +363,7 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
     const mbt_config &c = e->cfg;
     const double t_next = e->t + c.step_size;
     const StepParams<T> p = mbt_make_params<T>(c, e->t0, e->q0_per_traj, e->q0_uniform);
-    const StepClock<T> ck = mbt_make_clock<T>(c, e->t, t_next);
+    const StepClock<T> ck = mbt_make_clock<T>(c, e->t, t_next, e->t0);
     const long long N = e->N;
     int chunks = N >= (1 << 17) ? pipe_chunks() : 1;
     long long rows = ((N + chunks - 1) / chunks + 255) & ~255ll;

@@ -79,11 +79,12 @@ static inline int mbt_validate_config(const mbt_config *c, std::string &err) {
 
 /* The uniform clock of the step that moves time from t_cur to t_next. */
 template <typename T>
-static inline StepClock<T> mbt_make_clock(const mbt_config &c, double t_cur, double t_next) {
+static inline StepClock<T> mbt_make_clock(const mbt_config &c, double t_cur, double t_next, double t0) {
     StepClock<T> ck;
     ck.t_next = (T)t_next;
     ck.dt_r = (T)(t_next - t_cur);
     ck.done = t_next >= c.terminal_time - c.step_size / 2; /* TradingEnvironment.py:218-220 */
+    clock_derive<T>(ck, (T)c.rew_phi, (T)c.rew_alpha, (T)(c.rew_terminal_time - t0));
     return ck;
 }
 

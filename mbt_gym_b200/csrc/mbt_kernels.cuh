@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_reward_kernel(StepParams<T> p, 
     ck.t_next = x[2];
     ck.dt_r = x[2] - c[2];
     ck.done = is_terminal;
+    clock_derive<T>(ck, p.phi, p.alpha, p.ep_len);
     out[i] = reward_one<T, VariantGeneric>(p, ck, c[0], c[1], c[3], s, a, p.q0_uniform);
 }
 
@@ -402,6 +403,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
             ck.t_next = (T)t_next;
             ck.dt_r = (T)(t_next - t_cur);
             ck.done = t_next >= g.terminal_time - g.step_size / 2;
+            clock_derive<T>(ck, p.phi, p.alpha, p.ep_len);
             T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
             policy_action<T>(g, k, (T)t_cur, s, a);
             if (REC && g.rec_act) store_row<T>(g.rec_act, (long long)k * g.n + i, A, a, false);

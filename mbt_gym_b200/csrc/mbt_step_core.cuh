@@ -79,7 +79,21 @@ struct StepClock {
     T t_next; /* time column after the step                           TradingEnvironment.py:216 */
     T dt_r;   /* next[TIME] - current[TIME] as the rewards read it    RewardFunctions.py:58,99,131 */
     int done; /* this step is the terminal one                        TradingEnvironment.py:218-220 */
+    /* products / quotient of UNIFORM quantities that the reward formulas contain: formed once per step (on the host for
+     * the step kernel) with the same IEEE operation each thread would otherwise repeat -- bit-identical results */
+    T dt_phi;      /* dt_r * phi                RewardFunctions.py:60,101,133 */
+    T dt_alpha;    /* dt_r * alpha              RewardFunctions.py:61-62      */
+    T alpha_done;  /* alpha * int(is_terminal)  RewardFunctions.py:134-136    */
+    T dt_over_len; /* dt_r / episode_length     RewardFunctions.py:107        */
 };
+
+template <typename T>
+MBT_HD void clock_derive(StepClock<T> &ck, T phi, T alpha, T ep_len) {
+    ck.dt_phi = ck.dt_r * phi;
+    ck.dt_alpha = ck.dt_r * alpha;
+    ck.alpha_done = alpha * (T)ck.done;
+    ck.dt_over_len = ck.dt_r / ep_len;
+}
 
 /* Per-trajectory state carried between steps (the SoA columns of DESIGN.md "Layout"). */
 template <typename T>
@@ -103,13 +117,13 @@ MBT_HD T reward_one(const StepParams<T> &p, const StepClock<T> &ck, T c0, T q_cu
     if (rew == MBT_REW_EXP_UTILITY) /* RewardFunctions.py:156-163 */
         return ck.done ? -mbt_exp_t(-p.risk_aversion * (s.cash + s.inv * s.mid)) : (T)0;
     T qp = mbt_pow_t(s.inv, p.pexp);
-    T base = pnl - (ck.dt_r * p.phi) * qp;
+    T base = pnl - ck.dt_phi * qp;
     if (rew == MBT_REW_RUNNING_INVENTORY_PENALTY) /* RewardFunctions.py:128-138 */
-        return base - (p.alpha * (T)ck.done) * qp;
+        return base - ck.alpha_done * qp;
     if (rew == MBT_REW_CJ_MM) /* RewardFunctions.py:96-109 */
-        return base - p.alpha * ((qp - mbt_pow_t(q_cur, p.pexp)) + (ck.dt_r / p.ep_len) * mbt_pow_t(q_init, p.pexp));
+        return base - p.alpha * ((qp - mbt_pow_t(q_cur, p.pexp)) + ck.dt_over_len * mbt_pow_t(q_init, p.pexp));
     /* MBT_REW_CJ_OE  RewardFunctions.py:55-70 */
-    return base - (ck.dt_r * p.alpha) *
+    return base - ck.dt_alpha *
                       ((p.pexp * a[0]) * mbt_pow_t(q_cur, p.pexp - (T)1) + mbt_pow_t(q_init, p.pexp) * p.ep_len);
 }
 

@@ -38,7 +38,7 @@ static void run(const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, 
     double t = t_start;
     for (int k = 0; k < steps; ++k) {
         const double t_next = t + c.step_size;
-        StepClock<T> ck = mbt_make_clock<T>(c, t, t_next);
+        StepClock<T> ck = mbt_make_clock<T>(c, t, t_next, t0);
         for (int64_t i = 0; i < N; ++i) {
             T *row = state + i * D;
             Traj<T> s;
