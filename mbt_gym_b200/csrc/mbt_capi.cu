@@ -221,17 +221,42 @@ static void par_memcpy(void *dst, const void *src, size_t bytes) {
 }
 
 /* ------------------------------------------------------------------ launchers */
+/* MBT_PDL=0 disables programmatic dependent launch of consecutive step kernels (default: on) */
+static bool use_pdl() {
+    static const bool on = [] {
+        const char *v = getenv("MBT_PDL");
+        return !(v && v[0] == '0');
+    }();
+    return on;
+}
+
 template <typename T, class V, bool VEC>
-static void launch_step_k(mbt_env *e, const StepArgs<T> &g) {
-    mbt_step_kernel<T, V, VEC><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
+static void launch_step_k(mbt_env *e, const StepArgs<T> &g, bool allow_pdl) {
+    if (!allow_pdl || !use_pdl()) {
+        mbt_step_kernel<T, V, VEC><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
+        return;
+    }
+    /* programmatic stream serialization: this kernel may begin (up to its griddepcontrol.wait) while the previous
+     * kernel in the stream drains -- the next step's launch latency and Philox prologue hide behind this step's tail */
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid_for(g.n));
+    cfg.blockDim = dim3(MBT_BLOCK);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, mbt_step_kernel<T, V, VEC>, g);
 }
 
 template <typename T, class V>
-static void launch_step_v(mbt_env *e, const StepArgs<T> &g, bool vec) {
+static void launch_step_v(mbt_env *e, const StepArgs<T> &g, bool vec, bool allow_pdl) {
     if (vec)
-        launch_step_k<T, V, true>(e, g);
+        launch_step_k<T, V, true>(e, g, allow_pdl);
     else
-        launch_step_k<T, V, false>(e, g);
+        launch_step_k<T, V, false>(e, g, allow_pdl);
 }
 
 /*
@@ -284,7 +309,7 @@ static bool rows_vector_aligned(const mbt_env *e, const void *actions, const voi
 /* launch the step kernel on rows [r0, r0+n) of the batch (base pointers address row 0) */
 template <typename T>
 static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<T> &ck, const void *actions, void *obs,
-                            void *rew, long long r0, long long n) {
+                            void *rew, long long r0, long long n, bool allow_pdl) {
     const mbt_config &c = e->cfg;
     StepArgs<T> g;
     g.p = p;
@@ -301,7 +326,7 @@ static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<
     g.clipped = e->d_clipped;
     const bool vec = rows_vector_aligned<T>(e, g.actions, g.obs);
     switch (variant_of(c)) {
-#define X(id, ...) case id: launch_step_v<T, __VA_ARGS__>(e, g, vec); break;
+#define X(id, ...) case id: launch_step_v<T, __VA_ARGS__>(e, g, vec, allow_pdl); break;
         MBT_FOR_EACH_VARIANT(X)
 #undef X
     }
@@ -324,7 +349,7 @@ static int do_step_device(mbt_env *e, const void *actions, void *obs, void *rew,
     const StepClock<T> ck = mbt_make_clock<T>(c, e->t, t_next, e->t0);
     int rc = timing_begin(e);
     if (rc) return rc;
-    rc = launch_step_rows<T>(e, p, ck, actions, obs, rew, 0, e->N);
+    rc = launch_step_rows<T>(e, p, ck, actions, obs, rew, 0, e->N, /*allow_pdl=*/true);
     if (rc) return rc;
     rc = timing_end(e);
     if (rc) return rc;
@@ -376,7 +401,8 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
                            cudaMemcpyHostToDevice, e->copy_in));
         CU(cudaEventRecord(e->ev_in[k], e->copy_in));
         CU(cudaStreamWaitEvent(e->stream, e->ev_in[k], 0));
-        int rc = launch_step_rows<T>(e, p, ck, e->d_actions, obs_dst ? e->d_obs : nullptr, rew_dst ? e->d_rew : nullptr, r0, n);
+        int rc = launch_step_rows<T>(e, p, ck, e->d_actions, obs_dst ? e->d_obs : nullptr, rew_dst ? e->d_rew : nullptr, r0, n,
+                                     /*allow_pdl=*/false); /* ordered by stream events, not by the previous kernel */
         if (rc) return rc;
         CU(cudaEventRecord(e->ev_k[k], e->stream));
         CU(cudaStreamWaitEvent(e->copy_out, e->ev_k[k], 0));

@@ -175,9 +175,18 @@ __device__ __forceinline__ void store_traj(const StepParams<T> &p, const DevStat
 
 /* ------------------------------------------------------------------ step */
 /* One trajectory, one env-step: load state + action row, draw, advance, store state + observation row + reward. */
+/* Programmatic dependent launch (sm_90+): `launch_dependents` lets the NEXT kernel in the stream start launching while
+ * this one is still running; `wait` blocks until the PREVIOUS kernel has completed and its writes are visible.  Both are
+ * no-ops when the kernel was launched without the programmatic-serialization attribute. */
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename T, class V, bool VEC>
 __device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i, bool full_warp, T *warp_smem) {
     const StepParams<T> &p = g.p;
+    /* state-independent prologue: the step's 128 random bits depend only on (seed, trajectory id, step index) */
+    const mbt_u32x4 r = mbt_draw_keyed(g.keys, g.traj_offset + (unsigned long long)i, g.n_step, MBT_STREAM_STEP);
+    pdl_wait(); /* everything below reads what the previous kernel (previous step, or the caller's policy) wrote */
     const int A = action_width<T, V>(p);
     T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
     load_row<T>(g.actions, i, A, a, VEC);
@@ -191,7 +200,6 @@ __device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i, bool
     T q_init = p.q0_uniform;
     if ((rew_kind == MBT_REW_CJ_MM || rew_kind == MBT_REW_CJ_OE) && p.q0_per_traj) q_init = g.st.q0[i];
 
-    const mbt_u32x4 r = mbt_draw_keyed(g.keys, g.traj_offset + (unsigned long long)i, g.n_step, MBT_STREAM_STEP);
     int clipped = 0;
     const T rwd = step_one<T, V>(p, g.ck, s, a, r, q_init, &clipped);
 
@@ -225,7 +233,9 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_consta
     const long long warp_row0 = i - (long long)(threadIdx.x & 31u);
     const bool full_warp = (V::D != 4) && (warp_row0 + 32 <= g.n); /* warp-uniform */
     T *warp_smem = (V::D == 4) ? smem : smem + (threadIdx.x >> 5) * 32 * SW;
+    pdl_launch_dependents();
     if (i < g.n) step_row<T, V, VEC>(g, i, full_warp, warp_smem);
+    else pdl_wait();
 }
 
 /* ------------------------------------------------------------------ reset */
