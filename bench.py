@@ -240,7 +240,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from mbt_gym_b200 import _abi, _lib
+    from mbt_gym_b200 import _abi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

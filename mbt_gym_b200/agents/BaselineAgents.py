@@ -6,7 +6,6 @@ rollout loops (`generate_trajectory`, SB3-style loops) work unchanged.  Each age
 per-step host round trip disappears.  Policy constants are formed with the same Python expressions in both places, so
 the device reproduces the host agent bit-for-bit.
 """
-import ctypes as C
 import warnings
 from copy import deepcopy
 

@@ -587,9 +587,11 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
 
 int mbt_set_stream(mbt_env *e, void *cuda_stream) {
     if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    cudaStream_t next = cuda_stream == MBT_OWN_STREAM ? e->own_stream : (cudaStream_t)cuda_stream;
+    if (next == e->stream) return MBT_OK; /* unchanged: nothing to order */
     CU(cudaSetDevice(e->device));
-    CU(cudaStreamSynchronize(e->stream));
-    e->stream = cuda_stream == MBT_OWN_STREAM ? e->own_stream : (cudaStream_t)cuda_stream;
+    CU(cudaStreamSynchronize(e->stream)); /* work queued on the old stream must finish before the new one is used */
+    e->stream = next;
     return MBT_OK;
 }
 

@@ -15,7 +15,6 @@ Extra keyword-only arguments (all optional, defaults keep the reference behaviou
 Actions may also be a CUDA torch tensor: then observations and rewards come back as CUDA tensors on the same device
 and nothing crosses PCIe (the zero-copy path for on-device policies).
 """
-import ctypes as C
 import os
 from collections import OrderedDict
 from copy import copy

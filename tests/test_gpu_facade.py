@@ -3,7 +3,6 @@ classes -- same call shapes, and numerically the committed REFERENCE fixtures, b
 import numpy as np
 import pytest
 
-from mbt_gym_b200 import _abi
 from tests.helpers import Golden, assert_same, build_facade_env, golden_names, golden_specs
 
 pytestmark = pytest.mark.gpu

@@ -6,14 +6,12 @@
 Tolerances: float64 and float32 are compared BIT-EXACT (`np.array_equal`), except the two fixtures that reach
 libm pow/exp in the reference (`rip_cubic`, `exputil`), compared at rtol=atol=1e-11.
 """
-import ctypes as C
-
 import numpy as np
 import pytest
 
 from mbt_gym_b200 import _abi, _lib
 from oracle import oracle as O
-from tests.helpers import Golden, assert_same, copy_config, golden_names
+from tests.helpers import Golden, assert_same, golden_names
 
 pytestmark = pytest.mark.gpu
 
