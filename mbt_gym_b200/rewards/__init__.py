@@ -1,0 +1,1 @@
+"""Reward-function descriptors; the arithmetic runs in the fused CUDA kernels."""

@@ -1,0 +1,1 @@
+"""Market-model descriptors (midprice, arrivals, fills, price impact) flattened into mbt_config."""

@@ -1,0 +1,1 @@
+"""TEST INFRASTRUCTURE: CPU oracle, reference shim, NumPy port (never imported by mbt_gym_b200)."""

@@ -1,0 +1,1 @@
+"""Test suite: `-m "not gpu"` runs on CPU, `-m gpu` on a B200."""
