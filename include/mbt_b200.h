@@ -175,6 +175,11 @@ typedef struct mbt_config {
     double obs_low[MBT_MAX_OBS_DIM];     /* original_observation_space.low              */
     double obs_grad[MBT_MAX_OBS_DIM];    /* (high - low) / 2                            */
     double reward_scaling;               /* env.reward_scaling                          */
+
+    /* ReduceStateSizeWrapper fused into the observation store (gym/wrappers.py:10-43): bit d set = column d of the
+     * (normalised) observation is emitted; 0 = all D columns.  Emitted rows are (N, popcount) row-major. */
+    uint32_t obs_select;
+    uint32_t _pad2;
 } mbt_config;
 
 /* Per-reset overrides (start_time / initial_inventory may be callables on the host). */
@@ -229,6 +234,8 @@ const char *mbt_last_error(void);
 
 /* dims implied by a config (no device needed): action dim A, observation dim D, state columns S */
 int mbt_config_dims(const mbt_config *cfg, int32_t *action_dim, int32_t *obs_dim, int32_t *state_cols);
+/* width of the observation rows reset/step/rollout_record emit (= obs_dim unless cfg->obs_select picks columns) */
+int mbt_config_obs_out_dim(const mbt_config *cfg, int32_t *obs_out_dim);
 
 int mbt_create(const mbt_config *cfg, int device, mbt_env **out);
 int mbt_destroy(mbt_env *env);

@@ -124,6 +124,8 @@ class mbt_config(C.Structure):
         ("obs_low", C.c_double * MBT_MAX_OBS_DIM),
         ("obs_grad", C.c_double * MBT_MAX_OBS_DIM),
         ("reward_scaling", C.c_double),
+        ("obs_select", C.c_uint32),
+        ("_pad2", C.c_uint32),
     ]
 
 

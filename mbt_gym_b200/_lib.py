@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmbt_b200.so")
 
 # every symbol include/mbt_b200.h declares (checked by tests/test_abi_symbols.py)
 ABI_SYMBOLS = [
-    "mbt_abi_version", "mbt_last_error", "mbt_config_dims", "mbt_create", "mbt_destroy", "mbt_set_stream", "mbt_sync",
+    "mbt_abi_version", "mbt_last_error", "mbt_config_dims", "mbt_config_obs_out_dim", "mbt_create", "mbt_destroy", "mbt_set_stream", "mbt_sync",
     "mbt_seed", "mbt_reset", "mbt_step", "mbt_get_state", "mbt_set_state", "mbt_get_clock", "mbt_get_clip_count",
     "mbt_reward_eval", "mbt_rollout", "mbt_rollout_record", "mbt_get_launch_count", "mbt_enable_timing", "mbt_get_kernel_times",
     "mbt_host_alloc", "mbt_host_alloc_near", "mbt_host_free", "mbt_checkpoint_size", "mbt_checkpoint_save",
@@ -46,6 +46,7 @@ def load():
     L.mbt_abi_version.restype = C.c_int
     L.mbt_last_error.restype = C.c_char_p
     L.mbt_config_dims.argtypes = [cfgp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.mbt_config_obs_out_dim.argtypes = [cfgp, C.POINTER(C.c_int32)]
     L.mbt_create.argtypes = [cfgp, C.c_int, C.POINTER(vp)]
     L.mbt_destroy.argtypes = [vp]
     L.mbt_set_stream.argtypes = [vp, vp]
@@ -133,6 +134,9 @@ class NativeEnv:
         self.device = device
         self.N = int(cfg.num_trajectories)
         self.A, self.D, self.S = config_dims(cfg)
+        dout = C.c_int32()
+        _check(load().mbt_config_obs_out_dim(C.byref(cfg), C.byref(dout)))
+        self.Dout = dout.value  # emitted observation width (D unless cfg.obs_select picks columns)
         self.dtype = np.dtype(np.float64 if cfg.precision == _abi.MBT_F64 else np.float32)
         _check(load().mbt_create(C.byref(cfg), device, C.byref(self._h)))
 
@@ -176,7 +180,7 @@ class NativeEnv:
 
     def rollout_record(self, policy, steps_capacity, obs=True, actions=True, rewards=True):
         """Fused rollout that records the trajectory into host arrays (time-major); returns (summary, obs, act, rew)."""
-        o = np.empty((steps_capacity + 1, self.N, self.D), self.dtype) if obs else None
+        o = np.empty((steps_capacity + 1, self.N, self.Dout), self.dtype) if obs else None
         a = np.empty((steps_capacity, self.N, self.A), self.dtype) if actions else None
         r = np.empty((steps_capacity, self.N), self.dtype) if rewards else None
         rec = _abi.mbt_record(_addr(o), _addr(a), _addr(r), int(steps_capacity))

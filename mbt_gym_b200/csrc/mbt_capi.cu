@@ -49,6 +49,7 @@ struct mbt_env {
     mbt_config cfg;
     int device = 0;
     int A = 0, D = 0, S = 0;
+    int Dout = 0; /* emitted observation width (D unless cfg.obs_select picks columns) */
     int sm_count = 1;
     size_t esz = 8;
     long long N = 0;
@@ -278,7 +279,7 @@ static void launch_step_v(mbt_env *e, const StepArgs<T> &g, bool vec, bool allow
     X(9, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, -1, -1))
 
 static int variant_of(const mbt_config &c) {
-    const bool plain = !c.normalise_action && !c.normalise_obs && !c.normalise_rewards;
+    const bool plain = !c.normalise_action && !c.normalise_obs && !c.normalise_rewards && !c.obs_select;
     if (c.dynamics == MBT_DYN_LIMIT && c.midprice == MBT_MID_BM && c.impact == MBT_IMP_NONE) {
         if (c.arrival == MBT_ARR_POISSON) {
             if (plain && c.reward == MBT_REW_PNL) return 1;
@@ -302,7 +303,7 @@ static int variant_of(const mbt_config &c) {
 template <typename T>
 static bool rows_vector_aligned(const mbt_env *e, const void *actions, const void *obs) {
     const size_t need_a = (size_t)(e->A == 2 ? 2 : e->A == 4 ? 4 : 1) * sizeof(T);
-    const size_t need_o = (size_t)(e->D == 4 ? 4 : e->D == 6 ? 2 : 1) * sizeof(T);
+    const size_t need_o = (size_t)(e->Dout == 4 ? 4 : (e->Dout == 6 || e->Dout == 2) ? 2 : 1) * sizeof(T);
     return ((uintptr_t)actions % need_a) == 0 && (!obs || ((uintptr_t)obs % need_o) == 0);
 }
 
@@ -317,7 +318,7 @@ static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<
     g.st = dev_state<T>(e);
     g.st.cash += r0; g.st.inv += r0; g.st.mid += r0; g.st.x0 += r0; g.st.x1 += r0; g.st.q0 += r0;
     g.actions = (const T *)actions + r0 * e->A;
-    g.obs = obs ? (T *)obs + r0 * e->D : nullptr;
+    g.obs = obs ? (T *)obs + r0 * e->Dout : nullptr;
     g.rew = rew ? (T *)rew + r0 : nullptr;
     g.n = n;
     g.keys = mbt_philox_expand(e->seed);
@@ -392,7 +393,7 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
     const long long N = e->N;
     int chunks = N >= (1 << 17) ? pipe_chunks() : 1;
     long long rows = ((N + chunks - 1) / chunks + 255) & ~255ll;
-    const size_t arow = (size_t)e->A * sizeof(T), orow = (size_t)e->D * sizeof(T);
+    const size_t arow = (size_t)e->A * sizeof(T), orow = (size_t)e->Dout * sizeof(T);
     for (int k = 0; k < chunks; ++k) {
         const long long r0 = (long long)k * rows;
         if (r0 >= N) break;
@@ -474,6 +475,15 @@ int mbt_config_dims(const mbt_config *cfg, int32_t *action_dim, int32_t *obs_dim
     return MBT_OK;
 }
 
+int mbt_config_obs_out_dim(const mbt_config *cfg, int32_t *obs_out_dim) {
+    if (!cfg || !obs_out_dim) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    int32_t D = 0;
+    int rc = mbt_dims(cfg, nullptr, &D, nullptr);
+    if (rc) return fail(rc, "unknown dynamics kind");
+    *obs_out_dim = mbt_obs_out_dim(cfg, D);
+    return MBT_OK;
+}
+
 int mbt_host_alloc(size_t bytes, void **out) {
     if (!out) return fail(MBT_E_INVALID_ARG, "out is NULL");
     int device = 0;
@@ -547,6 +557,7 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     e->device = device;
     e->N = cfg->num_trajectories;
     mbt_dims(cfg, &e->A, &e->D, &e->S);
+    e->Dout = mbt_obs_out_dim(cfg, e->D);
     e->esz = cfg->precision == MBT_F64 ? 8 : 4;
     auto bail = [&](int code) {
         std::string keep = g_err;
@@ -649,7 +660,7 @@ int mbt_reset(mbt_env *e, const mbt_reset_args *args, void *obs_out, int mem) {
     int rc = e->cfg.precision == MBT_F64 ? do_reset_device<double>(e, args, dev_obs) : do_reset_device<float>(e, args, dev_obs);
     if (rc) return rc;
     if (obs_out && mem == MBT_MEM_HOST) {
-        const size_t ob = (size_t)e->N * e->D * e->esz;
+        const size_t ob = (size_t)e->N * e->Dout * e->esz;
         bool unstage = false;
         rc = d2h(e, obs_out, e->d_obs, e->h_obs, ob, &unstage);
         if (rc) return rc;
@@ -673,7 +684,7 @@ int mbt_step(mbt_env *e, const void *actions, void *obs_out, void *rew_out, uint
     /* host buffers: H2D actions -> kernel -> D2H observations + rewards, pipelined, all inside this call */
     int rc = ensure_staging(e);
     if (rc) return rc;
-    const size_t ab = (size_t)e->N * e->A * e->esz, ob = (size_t)e->N * e->D * e->esz, rb = (size_t)e->N * e->esz;
+    const size_t ab = (size_t)e->N * e->A * e->esz, ob = (size_t)e->N * e->Dout * e->esz, rb = (size_t)e->N * e->esz;
     const void *src = actions;
     if (!host_ptr_is_pinned(actions)) { /* pageable caller memory: stage through the handle's pinned buffer */
         par_memcpy(e->h_actions, actions, ab);
@@ -1040,7 +1051,7 @@ int mbt_rollout_record(mbt_env *e, const mbt_policy *policy, mbt_summary *summar
     if (record->steps_capacity <= 0) return fail(MBT_E_INVALID_ARG, "steps_capacity must be > 0");
     CU(cudaSetDevice(e->device));
     const size_t cap = (size_t)record->steps_capacity;
-    const size_t ob = (cap + 1) * (size_t)e->N * e->D * e->esz, ab = cap * (size_t)e->N * e->A * e->esz, rb = cap * (size_t)e->N * e->esz;
+    const size_t ob = (cap + 1) * (size_t)e->N * e->Dout * e->esz, ab = cap * (size_t)e->N * e->A * e->esz, rb = cap * (size_t)e->N * e->esz;
     mbt_record dev = *record;
     void *tmp = nullptr;
     if (mem == MBT_MEM_HOST) { /* stage through one temporary device block */

@@ -32,6 +32,14 @@ static inline int mbt_dims(const mbt_config *c, int32_t *A, int32_t *D, int32_t 
     return MBT_OK;
 }
 
+/* width of emitted observation rows: D, or the number of selected columns (ReduceStateSizeWrapper fused) */
+static inline int mbt_obs_out_dim(const mbt_config *c, int D) {
+    if (!c->obs_select) return D;
+    int n = 0;
+    for (int d = 0; d < D; ++d) n += (c->obs_select >> d) & 1u;
+    return n;
+}
+
 static inline int mbt_validate_config(const mbt_config *c, std::string &err) {
     char buf[256];
     if (!c) { err = "config is NULL"; return MBT_E_INVALID_ARG; }
@@ -72,6 +80,14 @@ static inline int mbt_validate_config(const mbt_config *c, std::string &err) {
         if (c->impact != MBT_IMP_NONE) { err = "price impact models only combine with speed dynamics"; return MBT_E_UNSUPPORTED; }
         if (c->reward == MBT_REW_CJ_OE) { err = "CjOeCriterion needs a 1-d action (reference fails too, RewardFunctions.py:66)"; return MBT_E_UNSUPPORTED; }
     }
+    {
+        int32_t D = 0;
+        mbt_dims(c, nullptr, &D, nullptr);
+        if (c->obs_select && (mbt_obs_out_dim(c, D) == 0 || (c->obs_select >> D) != 0)) {
+            err = "obs_select must pick at least one of the D observation columns and no others";
+            return MBT_E_INVALID_ARG;
+        }
+    }
     if (c->q0_mode == MBT_Q0_UNIFORM_INT && !(c->q0_hi > c->q0_lo)) { err = "initial inventory range needs hi > lo"; return MBT_E_INVALID_ARG; }
     if (c->q0_mode != MBT_Q0_UNIFORM_INT && c->q0_mode != MBT_Q0_CONST) { err = "unknown q0_mode"; return MBT_E_INVALID_ARG; }
     return MBT_OK;
@@ -97,6 +113,7 @@ static inline StepParams<T> mbt_make_params(const mbt_config &c, double t0, int 
     mbt_dims(&c, &A, &D, &S);
     p.dyn = c.dynamics; p.mid = c.midprice; p.arr = c.arrival; p.imp = c.impact; p.rew = c.reward;
     p.action_dim = A; p.obs_dim = D;
+    p.obs_select = (int)c.obs_select; p.obs_out_dim = mbt_obs_out_dim(&c, D);
     p.normalise_action = c.normalise_action; p.normalise_obs = c.normalise_obs; p.normalise_rewards = c.normalise_rewards;
     p.q0_per_traj = q0_per_traj;
     p.ep_len = (T)(c.rew_terminal_time - t0);

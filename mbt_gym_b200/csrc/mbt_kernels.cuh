@@ -50,7 +50,10 @@ struct StepArgs {
 template <typename T, class V>
 __device__ __forceinline__ int action_width(const StepParams<T> &p) { return V::A ? V::A : p.action_dim; }
 template <typename T, class V>
-__device__ __forceinline__ int obs_width(const StepParams<T> &p) { return V::D ? V::D : p.obs_dim; }
+__device__ __forceinline__ int obs_width(const StepParams<T> &p) {
+    /* the fully specialised variants (V::norm == 0) never select columns: variant_of() routes obs_select to the others */
+    return (V::D && V::norm == 0) ? V::D : p.obs_out_dim;
+}
 
 /* ------------------------------------------------------------------ row access helpers */
 __device__ __forceinline__ void st_v4_f64(double *ptr, double a, double b, double c, double d) {
@@ -96,6 +99,12 @@ __device__ __forceinline__ void store_row(T *__restrict__ base, long long i, int
             *reinterpret_cast<float4 *>(row) = make_float4(v[0], v[1], v[2], v[3]);
         } else {
             st_v4_f64(reinterpret_cast<double *>(row), v[0], v[1], v[2], v[3]);
+        }
+    } else if (vec_ok && w == 2) {
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float2 *>(row) = make_float2(v[0], v[1]);
+        } else {
+            *reinterpret_cast<double2 *>(row) = make_double2(v[0], v[1]);
         }
     } else if (vec_ok && w == 6) {
         if constexpr (sizeof(T) == 4) {
@@ -148,6 +157,13 @@ __device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T
         row[d] = norm_obs<T, V>(p, s.x1, d); ++d;
     }
     if (imp_has_state(imp)) { row[d] = norm_obs<T, V>(p, s.x0, d); ++d; }
+    if (V::norm != 0 && p.obs_select) { /* keep the selected columns, in order (gym/wrappers.py:30-38) */
+        int j = 0;
+#pragma unroll
+        for (int k = 0; k < MBT_MAX_OBS_DIM; ++k)
+            if (k < d && ((p.obs_select >> k) & 1)) row[j++] = row[k];
+        return j;
+    }
     return d;
 }
 
@@ -208,7 +224,7 @@ __device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i, bool
         T row[MBT_MAX_OBS_DIM];
         make_obs_row<T, V>(p, s, g.ck.t_next, row);
         const int D = obs_width<T, V>(p);
-        if (D != 4 && full_warp)
+        if (D != 4 && D != 2 && full_warp)
             store_rows_staged<T>(g.obs, i - (long long)(threadIdx.x & 31u), D, row, warp_smem, threadIdx.x & 31u);
         else
             store_row<T>(g.obs, i, D, row, VEC);
@@ -227,12 +243,13 @@ __device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i, bool
 template <typename T, class V, bool VEC>
 __global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_constant__ StepArgs<T> g) {
     /* staging for non-power-of-two observation rows: one 32 x MBT_MAX_OBS_DIM tile per warp (unused when D == 4) */
-    constexpr int SW = V::D ? V::D : MBT_MAX_OBS_DIM; /* staged row width */
-    __shared__ T smem[(V::D == 4) ? 1 : (MBT_BLOCK / 32) * 32 * SW];
+    constexpr bool FIXED_W = V::D && V::norm == 0;          /* emitted row width known at compile time */
+    constexpr int SW = FIXED_W ? V::D : MBT_MAX_OBS_DIM;     /* staged row width */
+    __shared__ T smem[(FIXED_W && V::D == 4) ? 1 : (MBT_BLOCK / 32) * 32 * SW];
     const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
     const long long warp_row0 = i - (long long)(threadIdx.x & 31u);
-    const bool full_warp = (V::D != 4) && (warp_row0 + 32 <= g.n); /* warp-uniform */
-    T *warp_smem = (V::D == 4) ? smem : smem + (threadIdx.x >> 5) * 32 * SW;
+    const bool full_warp = !(FIXED_W && V::D == 4) && (warp_row0 + 32 <= g.n); /* warp-uniform */
+    T *warp_smem = (FIXED_W && V::D == 4) ? smem : smem + (threadIdx.x >> 5) * 32 * SW;
     pdl_launch_dependents();
     if (i < g.n) step_row<T, V, VEC>(g, i, full_warp, warp_smem);
     else pdl_wait();
@@ -293,6 +310,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_gather_state_kernel(StepParams<
     load_traj<T, VariantGeneric>(p, st, i, s);
     StepParams<T> raw = p;
     raw.normalise_obs = 0;
+    raw.obs_select = 0;
     T row[MBT_MAX_OBS_DIM];
     const int d = make_obs_row<T, VariantGeneric>(raw, s, t, row);
     store_row<T>(out, i, d, row, false);

@@ -55,6 +55,7 @@ struct StepParams {
     /* model selectors (runtime copies; compile-time Variant wins when >= 0) */
     int dyn, mid, arr, imp, rew;
     int action_dim, obs_dim;
+    int obs_select, obs_out_dim; /* ReduceStateSizeWrapper fused into the store: column bitmask (0 = all), emitted width */
     int normalise_action, normalise_obs, normalise_rewards;
     int q0_per_traj; /* 1: read q0 column (random initial inventories), 0: q0_uniform */
 

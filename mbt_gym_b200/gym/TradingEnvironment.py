@@ -53,7 +53,7 @@ class TradingEnvironment(_EnvBase):
                  initial_inventory=0, max_inventory=10_000, max_cash=None, max_stock_price=None, start_time=0.0,
                  info_calculator=None, seed=None, num_trajectories=1, normalise_action_space=True,
                  normalise_observation_space=True, normalise_rewards=False, *, precision="float64", device=0,
-                 traj_offset=0, copy_outputs=False):
+                 traj_offset=0, copy_outputs=False, obs_columns=None):
         super().__init__()
         self._native = None
         self._native_cfg_bytes = None
@@ -65,6 +65,7 @@ class TradingEnvironment(_EnvBase):
         self.precision = {"float64": _abi.MBT_F64, "f64": _abi.MBT_F64, "float32": _abi.MBT_F32, "f32": _abi.MBT_F32}[str(precision)]
         self.dtype = np.dtype(np.float64 if self.precision == _abi.MBT_F64 else np.float32)
         self.device, self.traj_offset, self.copy_outputs = int(device), int(traj_offset), bool(copy_outputs)
+        self._obs_columns = None
 
         self.terminal_time = terminal_time
         self.n_steps = n_steps
@@ -105,11 +106,31 @@ class TradingEnvironment(_EnvBase):
         if self.normalise_action_space_:
             self.original_action_space = copy(self.action_space)
             self.action_space = self._unit_box(self.action_space)
+        self._full_observation_space = self.observation_space
         if self.normalise_rewards_:
             assert isinstance(self.model_dynamics.arrival_model, PoissonArrivalModel) and isinstance(
                 self.model_dynamics.fill_probability_model, ExponentialFillFunction
             ), "Arrival model must be Poisson and fill probability model must be exponential to scale rewards"
             self.reward_scaling = 1 / self._get_inventory_neutral_rewards()
+        if obs_columns is not None:
+            self.select_observation_columns(obs_columns)
+
+    def select_observation_columns(self, columns):
+        """Emit only these observation columns (in increasing order) -- `ReduceStateSizeWrapper` fused into the kernel's
+        observation store (mbt_gym/gym/wrappers.py:10-43): no host-side fancy-index copy and proportionally fewer D2H
+        bytes.  `None` restores all columns.  `env.state` and the agents' `to_policy` forms are unaffected."""
+        if columns is None:
+            self._obs_columns = None
+        else:
+            cols = sorted({int(c) for c in columns})
+            d = self._full_observation_space.shape[0]
+            if not cols or cols[0] < 0 or cols[-1] >= d:
+                raise ValueError(f"observation columns must be within 0..{d - 1}")
+            self._obs_columns = cols
+        full = self._full_observation_space
+        idx = self._obs_columns if self._obs_columns is not None else list(range(full.shape[0]))
+        self.observation_space = Box(low=full.low[idx], high=full.high[idx], dtype=full.low.dtype)
+        self._ring = None
 
     # ------------------------------------------------------------------ reference surface: hot path
     def reset(self):
@@ -158,7 +179,7 @@ class TradingEnvironment(_EnvBase):
         if action.device.index != self.device:
             raise ValueError(f"action is on cuda:{action.device.index}, the environment on cuda:{self.device}")
         native.set_stream(torch.cuda.current_stream(action.device).cuda_stream)
-        obs = torch.empty((self.num_trajectories, native.D), dtype=tdt, device=action.device)
+        obs = torch.empty((self.num_trajectories, native.Dout), dtype=tdt, device=action.device)
         rew = torch.empty((self.num_trajectories,), dtype=tdt, device=action.device)
         done = native.step(action, obs, rew, mem=_abi.MBT_MEM_DEVICE)
         return obs, rew, self._dones(done), self._calculate_infos()
@@ -384,6 +405,7 @@ class TradingEnvironment(_EnvBase):
         cfg.normalise_obs = int(bool(self.normalise_observation_space_))
         cfg.normalise_rewards = int(bool(self.normalise_rewards_))
         cfg.reward_scaling = float(self.reward_scaling)
+        cfg.obs_select = sum(1 << c for c in self._obs_columns) if self._obs_columns else 0
         if self.normalise_action_space_:
             lo, gr = self._intercept_action_norm, self._gradient_action_norm
             for i in range(lo.shape[0]):
@@ -410,7 +432,7 @@ class TradingEnvironment(_EnvBase):
         return self._native
 
     def _out_buffers(self):
-        n, d = self.num_trajectories, self._native.D
+        n, d = self.num_trajectories, self._native.Dout
         if self.copy_outputs:
             return np.empty((n, d), self.dtype), np.empty((n,), self.dtype)
         if self._ring is None:

@@ -17,17 +17,26 @@ class _Wrapper:
 
 
 class ReduceStateSizeWrapper(_Wrapper):
-    """Keep only the listed observation columns (default: inventory and time)  (:10-43)."""
+    """Keep only the listed observation columns (default: inventory and time)  (:10-43).
 
-    def __init__(self, env, list_of_state_indices=(INVENTORY_INDEX, TIME_INDEX)):
+    On a `TradingEnvironment` with increasing column indices the selection is FUSED into the kernel's observation
+    store (`env.select_observation_columns`): no (N, D) -> (N, k) fancy-index copy on the host and k/D of the D2H bytes.
+    Anything else (another wrapper underneath, a permutation of columns) falls back to host-side indexing."""
+
+    def __init__(self, env, list_of_state_indices=(INVENTORY_INDEX, TIME_INDEX), fuse=True):
         super().__init__(env)
         self.list_of_state_indices = list(list_of_state_indices)
         space = env.observation_space
         self.observation_space = Box(low=space.low[self.list_of_state_indices],
                                      high=space.high[self.list_of_state_indices], dtype=np.float64)
+        idx = self.list_of_state_indices
+        self._fused = bool(fuse and hasattr(env, "select_observation_columns") and idx == sorted(set(idx))
+                           and getattr(env, "_obs_columns", None) is None)
+        if self._fused:
+            env.select_observation_columns(idx)
 
     def observation(self, observation):
-        return observation[:, self.list_of_state_indices]
+        return observation if self._fused else observation[:, self.list_of_state_indices]
 
     def reset(self):
         return self.observation(self.env.reset())

@@ -46,6 +46,13 @@ static int orc_dims(const mbt_config *c, int32_t *A, int32_t *D, int32_t *S) {
     return 0;
 }
 
+static int orc_obs_out_dim(const mbt_config *c, int D) {
+    if (!c->obs_select) return D;
+    int n = 0;
+    for (int d = 0; d < D; ++d) n += (c->obs_select >> d) & 1u;
+    return n;
+}
+
 #define REAL double
 #define SFX f64
 #define ORC_IS_F64 1
@@ -70,6 +77,11 @@ typedef struct orc_handle {
 } orc_handle;
 
 int orc_config_dims(const mbt_config *c, int32_t *A, int32_t *D, int32_t *S) { return orc_dims(c, A, D, S); }
+int orc_config_obs_out_dim(const mbt_config *c) {
+    int32_t A, D, S;
+    if (orc_dims(c, &A, &D, &S) != 0) return -1;
+    return orc_obs_out_dim(c, D);
+}
 
 orc_handle *orc_create(const mbt_config *cfg) {
     if (!cfg || cfg->struct_size != (int32_t)sizeof(mbt_config)) return NULL;

@@ -105,12 +105,16 @@ static void FN(orc_destroy)(FN(orc_env) * e) {
 /* observation = normalise_observation(state.copy())     TradingEnvironment.py:101,110,112-118 */
 static void FN(orc_write_obs)(const FN(orc_env) * e, REAL *obs) {
     const mbt_config *c = &e->cfg;
-    for (int64_t i = 0; i < e->N; ++i)
+    const int Dout = orc_obs_out_dim(c, e->D);
+    for (int64_t i = 0; i < e->N; ++i) {
+        int j = 0;
         for (int d = 0; d < e->D; ++d) {
             REAL x = e->state[i * e->D + d];
             if (c->normalise_obs) x = (x - (REAL)c->obs_low[d]) / (REAL)c->obs_grad[d] - (REAL)1;
-            obs[i * e->D + d] = x;
+            /* ReduceStateSizeWrapper: obs[:, list_of_state_indices]      gym/wrappers.py:30-38 */
+            if (!c->obs_select || ((c->obs_select >> d) & 1u)) obs[i * Dout + j++] = x;
         }
+    }
 }
 
 /* TradingEnvironment.reset: processes reset to their initial vector state, state = initial_state,

@@ -46,6 +46,7 @@ def lib():
         L.orc_get_clock.argtypes = [vp, C.POINTER(f64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
         L.orc_reward_eval.argtypes = [C.POINTER(_abi.mbt_config), i64, vp, vp, vp, C.c_int, f64, f64, vp]
         L.orc_config_dims.argtypes = [C.POINTER(_abi.mbt_config)] + [C.POINTER(C.c_int32)] * 3
+        L.orc_config_obs_out_dim.argtypes = [C.POINTER(_abi.mbt_config)]
         L.orc_philox.argtypes = [vp, vp, vp]
         for name in ("exp_f32", "log_f32", "exp_f64", "log_f64", "normal_f32", "normal_f64"):
             getattr(L, "orc_vec_" + name).argtypes = [i64, vp, vp]
@@ -72,6 +73,7 @@ class OracleEnv:
         self.cfg = cfg
         self.N = int(cfg.num_trajectories)
         self.A, self.D, _ = dims(cfg)
+        self.Dout = lib().orc_config_obs_out_dim(C.byref(cfg))
         self.dtype = np.float64 if cfg.precision == _abi.MBT_F64 else np.float32
         self._h = lib().orc_create(C.byref(cfg))
         if not self._h:
@@ -86,7 +88,7 @@ class OracleEnv:
         lib().orc_seed(self._h, C.c_uint64(int(seed)))
 
     def reset(self, args=None):
-        obs = np.empty((self.N, self.D), self.dtype)
+        obs = np.empty((self.N, self.Dout), self.dtype)
         lib().orc_reset(self._h, None if args is None else C.byref(args), _ptr(obs))
         return obs
 
@@ -97,7 +99,7 @@ class OracleEnv:
 
     def step(self, actions):
         a = self._check_actions(actions)
-        obs = np.empty((self.N, self.D), self.dtype)
+        obs = np.empty((self.N, self.Dout), self.dtype)
         rew = np.empty((self.N,), self.dtype)
         done = C.c_uint8(0)
         lib().orc_step(self._h, _ptr(a), _ptr(obs), _ptr(rew), C.byref(done))
@@ -108,7 +110,7 @@ class OracleEnv:
         u = np.ascontiguousarray(u, dtype=self.dtype)
         z = np.ascontiguousarray(z, dtype=self.dtype).reshape(-1)
         assert u.shape == (self.N, 4) and z.shape == (self.N,)
-        obs = np.empty((self.N, self.D), self.dtype)
+        obs = np.empty((self.N, self.Dout), self.dtype)
         rew = np.empty((self.N,), self.dtype)
         done = C.c_uint8(0)
         lib().orc_step_draws(self._h, _ptr(a), _ptr(u), _ptr(z), _ptr(obs), _ptr(rew), C.byref(done))

@@ -253,3 +253,29 @@ def test_generate_trajectory_fused_equals_stepwise_generate_trajectory():
         assert_same(o2, o1, what=f"{name} observations")
         assert_same(r2, r1, what=f"{name} rewards")
         env.close()
+
+
+@pytest.mark.parametrize("name,cols", [("as_pnl", [1, 2]), ("as_pnl_normalised", [1, 2]), ("hawkes_pnl", [1, 3, 5]),
+                                       ("oe_ou_cjoe", [0, 4]), ("oe_temp_transient", [1, 2, 3, 4])])
+@pytest.mark.parametrize("precision", ["float64", "float32"])
+def test_fused_column_select_equals_host_side_wrapper(name, cols, precision):
+    """`ReduceStateSizeWrapper` fused into the kernel's observation store == the reference behaviour (select on the host)."""
+    from mbt_gym_b200.gym.wrappers import ReduceStateSizeWrapper
+
+    g = Golden(name)
+    fused = ReduceStateSizeWrapper(build_facade_env(SPECS[name], precision=precision), cols)
+    plain = ReduceStateSizeWrapper(build_facade_env(SPECS[name], precision=precision), cols, fuse=False)
+    assert fused._fused and not plain._fused and fused.observation_space.shape == (len(cols),)
+    assert fused.env._native is None or True
+    o1, o2 = fused.reset(), plain.reset()
+    assert o1.shape == (g.cfg.num_trajectories, len(cols))
+    assert_same(o1, o2, what=f"{name} reset")
+    for k in range(12):
+        a = g.actions[k]
+        o1, r1, d1, _ = fused.step(a)
+        o2, r2, d2, _ = plain.step(a)
+        assert_same(o1, o2, what=f"{name} obs {k}"); assert_same(r1, r2, what=f"{name} rew {k}")
+        if precision == "float64":
+            assert_same(o1, g.obs[k][:, cols], exact=g.exact, what=f"{name} vs fixture {k}")
+    assert fused.env.state.shape[1] == g.obs.shape[2], "env.state keeps every column"
+    fused.env.close(); plain.env.close()

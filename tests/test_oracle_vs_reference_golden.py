@@ -37,3 +37,17 @@ def test_oracle_f32_tracks_f64(name):
         o32, r32, _ = b.step(g.actions[k])
         assert np.array_equal(o64[:, 1], o32[:, 1].astype(np.float64)) or name == "oe_ou_cjoe"  # inventories
         np.testing.assert_allclose(o32, o64, rtol=2e-6, atol=2e-3)
+
+
+@pytest.mark.parametrize("name,cols", [("as_pnl_normalised", [1, 2]), ("hawkes_pnl", [1, 3, 5]), ("oe_ou_cjoe", [0, 4])])
+def test_oracle_column_select_equals_reference_columns(name, cols):
+    """ReduceStateSizeWrapper fused into the observation store = the reference's observation with those columns kept."""
+    g = Golden(name)
+    cfg = g.config(_abi.MBT_F64, obs_select=sum(1 << c for c in cols))
+    orc = O.OracleEnv(cfg)
+    orc.seed(g.seed)
+    assert_same(orc.reset(), g.reset_obs[0][:, cols], what=f"{name} reset")
+    for k in range(10):
+        o, r, _ = orc.step(g.actions[k])
+        assert_same(o, g.obs[k][:, cols], what=f"{name} obs {k}")
+        assert_same(r, g.rew[k], what=f"{name} rew {k}")
