@@ -368,7 +368,7 @@ static bool host_path_zero_copy() {
     return zc;
 }
 
-/* number of pipeline chunks of the host-buffer path (MBT_PIPE_CHUNKS_ENV overrides for tuning; max 8) */
+/* number of pipeline chunks of the host-buffer path (env MBT_PIPE_CHUNKS overrides for tuning; 1..16, default 8) */
 static int pipe_chunks() {
     static const int n = [] {
         const char *v = getenv("MBT_PIPE_CHUNKS");
