@@ -37,7 +37,7 @@ L2_BYTES = 126e6
 WORKLOADS = ("as", "cjmm", "hawkes", "oe")
 
 
-def make_env(workload, precision, n_local, traj_offset, device):
+def make_env(workload, precision, n_local, traj_offset, device, io_dtype=None):
     """BASELINE.json configs[1..4] through the PUBLIC API (SURVEY.md 8d synthetic inputs), normalisation off."""
     from mbt_gym_b200.gym.ModelDynamics import LimitOrderModelDynamics, TradinghWithSpeedModelDynamics
     from mbt_gym_b200.gym.TradingEnvironment import TradingEnvironment
@@ -50,7 +50,8 @@ def make_env(workload, precision, n_local, traj_offset, device):
     n_steps, T, N = 200, 1.0, n_local
     dt = T / n_steps
     kw = dict(terminal_time=T, n_steps=n_steps, seed=1234, num_trajectories=N, normalise_action_space=False,
-              normalise_observation_space=False, precision=precision, device=device, traj_offset=traj_offset)
+              normalise_observation_space=False, precision=precision, device=device, traj_offset=traj_offset,
+              io_dtype=io_dtype)
     if workload in ("as", "cjmm", "hawkes"):
         mid = BrownianMotionMidpriceModel(volatility=2.0, initial_price=100.0, terminal_time=T, step_size=dt, num_trajectories=N)
         if workload == "hawkes":
@@ -333,6 +334,29 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
 
+    # ---- secondary: the same host path with float32 caller buffers over the same float64 arithmetic (io_dtype)
+    e2e_f32io = None
+    if args.precision == "f64" and world == 1 and not args.no_episode_stats:
+        f32io = make_env(args.workload, "float64", n_local, rank * n_local, local_rank, io_dtype=np.float32)
+        a32 = f32io.pinned_actions()
+        a32[:] = fixed_action_value(args.workload)
+        f32io.reset()
+        for _ in range(3):
+            f32io.step(a32)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(e2e_steps):
+            o, r, d, _i = f32io.step(a32)
+            checksum += float(r[0])
+            if d[0]:
+                f32io.reset()
+        torch.cuda.synchronize()
+        dt32 = time.perf_counter() - t1
+        e2e_f32io = {"value": N * e2e_steps / dt32, "unit": "env-steps/s", "ms_per_step": 1e3 * dt32 / e2e_steps,
+                     "h2d_bytes_per_step": N * A * 4, "d2h_bytes_per_step": N * (D + 1) * 4,
+                     "note": "io_dtype=float32: float64 state and arithmetic, float32 action/observation/reward arrays"}
+        f32io.close()
+
     # ---- per-episode statistics: fused on-device rollout, summary all-reduced / returns all-gathered over NCCL
     episode = None
     if not args.no_episode_stats:
@@ -418,6 +442,7 @@ def main():
                                                    "per launch (a 1-element kernel reads 6.5 us this way)"},
             "clocks": clocks,
             "episode_stats": episode,
+            "e2e_float32_io": e2e_f32io,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)

@@ -61,6 +61,9 @@ extern "C" {
 #define MBT_F64 0 /* the reference's type (every reference array is float64)               */
 #define MBT_F32 1 /* opt-in fast mode, same formulas evaluated in float                     */
 
+#define MBT_IO_SAME 0
+#define MBT_IO_F32 1
+
 /* ModelDynamics.py */
 #define MBT_DYN_LIMIT 0            /* LimitOrderModelDynamics              :87-131  A=2 */
 #define MBT_DYN_SPEED 1            /* TradinghWithSpeedModelDynamics       :243-275 A=1 */
@@ -179,7 +182,11 @@ typedef struct mbt_config {
     /* ReduceStateSizeWrapper fused into the observation store (gym/wrappers.py:10-43): bit d set = column d of the
      * (normalised) observation is emitted; 0 = all D columns.  Emitted rows are (N, popcount) row-major. */
     uint32_t obs_select;
-    uint32_t _pad2;
+    /* element type of the CALLER's action / observation / reward buffers of mbt_reset and mbt_step:
+     * MBT_IO_SAME = the handle's precision; MBT_IO_F32 = float32 buffers over float64 arithmetic (values converted
+     * with round-to-nearest at the boundary; SB3 keeps float32 buffers anyway and the host path moves half the bytes).
+     * State, rollout outputs, get/set_state and checkpoints stay in the handle's precision. */
+    uint32_t io_precision;
 } mbt_config;
 
 /* Per-reset overrides (start_time / initial_inventory may be callables on the host). */

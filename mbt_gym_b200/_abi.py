@@ -20,6 +20,9 @@ MBT_MEM_DEVICE = 1
 MBT_F64 = 0
 MBT_F32 = 1
 
+MBT_IO_SAME = 0
+MBT_IO_F32 = 1
+
 MBT_DYN_LIMIT = 0
 MBT_DYN_SPEED = 1
 MBT_DYN_AT_TOUCH = 2
@@ -125,7 +128,7 @@ class mbt_config(C.Structure):
         ("obs_grad", C.c_double * MBT_MAX_OBS_DIM),
         ("reward_scaling", C.c_double),
         ("obs_select", C.c_uint32),
-        ("_pad2", C.c_uint32),
+        ("io_precision", C.c_uint32),
     ]
 
 

@@ -138,6 +138,8 @@ class NativeEnv:
         _check(load().mbt_config_obs_out_dim(C.byref(cfg), C.byref(dout)))
         self.Dout = dout.value  # emitted observation width (D unless cfg.obs_select picks columns)
         self.dtype = np.dtype(np.float64 if cfg.precision == _abi.MBT_F64 else np.float32)
+        # element type of the action / observation / reward buffers of reset() and step()
+        self.io_dtype = np.dtype(np.float32) if cfg.io_precision == _abi.MBT_IO_F32 else self.dtype
         _check(load().mbt_create(C.byref(cfg), device, C.byref(self._h)))
 
     def close(self):

@@ -51,7 +51,8 @@ struct mbt_env {
     int A = 0, D = 0, S = 0;
     int Dout = 0; /* emitted observation width (D unless cfg.obs_select picks columns) */
     int sm_count = 1;
-    size_t esz = 8;
+    size_t esz = 8;    /* element size of the arithmetic / state type */
+    size_t io_esz = 8; /* element size of the caller's action / observation / reward buffers */
     long long N = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
 
@@ -231,10 +232,10 @@ static bool use_pdl() {
     return on;
 }
 
-template <typename T, class V, bool VEC>
-static void launch_step_k(mbt_env *e, const StepArgs<T> &g, bool allow_pdl) {
+template <typename T, typename E, class V, bool VEC>
+static void launch_step_k(mbt_env *e, const StepArgs<T, E> &g, bool allow_pdl) {
     if (!allow_pdl || !use_pdl()) {
-        mbt_step_kernel<T, V, VEC><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
+        mbt_step_kernel<T, E, V, VEC><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
         return;
     }
     /* programmatic stream serialization: this kernel may begin (up to its griddepcontrol.wait) while the previous
@@ -249,15 +250,15 @@ static void launch_step_k(mbt_env *e, const StepArgs<T> &g, bool allow_pdl) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, mbt_step_kernel<T, V, VEC>, g);
+    cudaLaunchKernelEx(&cfg, mbt_step_kernel<T, E, V, VEC>, g);
 }
 
-template <typename T, class V>
-static void launch_step_v(mbt_env *e, const StepArgs<T> &g, bool vec, bool allow_pdl) {
+template <typename T, typename E, class V>
+static void launch_step_v(mbt_env *e, const StepArgs<T, E> &g, bool vec, bool allow_pdl) {
     if (vec)
-        launch_step_k<T, V, true>(e, g, allow_pdl);
+        launch_step_k<T, E, V, true>(e, g, allow_pdl);
     else
-        launch_step_k<T, V, false>(e, g, allow_pdl);
+        launch_step_k<T, E, V, false>(e, g, allow_pdl);
 }
 
 /*
@@ -300,34 +301,34 @@ static int variant_of(const mbt_config &c) {
 
 /* may the step kernel use whole-row vector accesses on the caller's buffers?  (see load_row / store_row:
  * actions A=2 -> 2-element, A=4 -> 4-element vectors; observations D=4 -> 4-element, D=6 -> 2-element) */
-template <typename T>
+template <typename E>
 static bool rows_vector_aligned(const mbt_env *e, const void *actions, const void *obs) {
-    const size_t need_a = (size_t)(e->A == 2 ? 2 : e->A == 4 ? 4 : 1) * sizeof(T);
-    const size_t need_o = (size_t)(e->Dout == 4 ? 4 : (e->Dout == 6 || e->Dout == 2) ? 2 : 1) * sizeof(T);
+    const size_t need_a = (size_t)(e->A == 2 ? 2 : e->A == 4 ? 4 : 1) * sizeof(E);
+    const size_t need_o = (size_t)(e->Dout == 4 ? 4 : (e->Dout == 6 || e->Dout == 2) ? 2 : 1) * sizeof(E);
     return ((uintptr_t)actions % need_a) == 0 && (!obs || ((uintptr_t)obs % need_o) == 0);
 }
 
 /* launch the step kernel on rows [r0, r0+n) of the batch (base pointers address row 0) */
-template <typename T>
+template <typename T, typename E>
 static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<T> &ck, const void *actions, void *obs,
                             void *rew, long long r0, long long n, bool allow_pdl) {
     const mbt_config &c = e->cfg;
-    StepArgs<T> g;
+    StepArgs<T, E> g;
     g.p = p;
     g.ck = ck;
     g.st = dev_state<T>(e);
     g.st.cash += r0; g.st.inv += r0; g.st.mid += r0; g.st.x0 += r0; g.st.x1 += r0; g.st.q0 += r0;
-    g.actions = (const T *)actions + r0 * e->A;
-    g.obs = obs ? (T *)obs + r0 * e->Dout : nullptr;
-    g.rew = rew ? (T *)rew + r0 : nullptr;
+    g.actions = (const E *)actions + r0 * e->A;
+    g.obs = obs ? (E *)obs + r0 * e->Dout : nullptr;
+    g.rew = rew ? (E *)rew + r0 : nullptr;
     g.n = n;
     g.keys = mbt_philox_expand(e->seed);
     g.traj_offset = (unsigned long long)c.traj_offset + (unsigned long long)r0;
     g.n_step = (unsigned long long)e->n_step;
     g.clipped = e->d_clipped;
-    const bool vec = rows_vector_aligned<T>(e, g.actions, g.obs);
+    const bool vec = rows_vector_aligned<E>(e, g.actions, g.obs);
     switch (variant_of(c)) {
-#define X(id, ...) case id: launch_step_v<T, __VA_ARGS__>(e, g, vec, allow_pdl); break;
+#define X(id, ...) case id: launch_step_v<T, E, __VA_ARGS__>(e, g, vec, allow_pdl); break;
         MBT_FOR_EACH_VARIANT(X)
 #undef X
     }
@@ -342,7 +343,7 @@ static void advance_clock(mbt_env *e, double t_next) {
     e->n_step += 1;
 }
 
-template <typename T>
+template <typename T, typename E>
 static int do_step_device(mbt_env *e, const void *actions, void *obs, void *rew, uint8_t *done_out) {
     const mbt_config &c = e->cfg;
     const double t_next = e->t + c.step_size; /* state[:, TIME] += step_size   TradingEnvironment.py:216 */
@@ -350,7 +351,7 @@ static int do_step_device(mbt_env *e, const void *actions, void *obs, void *rew,
     const StepClock<T> ck = mbt_make_clock<T>(c, e->t, t_next, e->t0);
     int rc = timing_begin(e);
     if (rc) return rc;
-    rc = launch_step_rows<T>(e, p, ck, actions, obs, rew, 0, e->N, /*allow_pdl=*/true);
+    rc = launch_step_rows<T, E>(e, p, ck, actions, obs, rew, 0, e->N, /*allow_pdl=*/true);
     if (rc) return rc;
     rc = timing_end(e);
     if (rc) return rc;
@@ -384,7 +385,7 @@ static int pipe_chunks() {
  * chunk's results are in the caller's buffers.  `act_src`, `obs_dst`, `rew_dst` are pinned (caller's own pinned
  * buffers, or the handle's staging).
  */
-template <typename T>
+template <typename T, typename E>
 static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst, void *rew_dst, uint8_t *done_out) {
     const mbt_config &c = e->cfg;
     const double t_next = e->t + c.step_size;
@@ -393,7 +394,7 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
     const long long N = e->N;
     int chunks = N >= (1 << 17) ? pipe_chunks() : 1;
     long long rows = ((N + chunks - 1) / chunks + 255) & ~255ll;
-    const size_t arow = (size_t)e->A * sizeof(T), orow = (size_t)e->Dout * sizeof(T);
+    const size_t arow = (size_t)e->A * sizeof(E), orow = (size_t)e->Dout * sizeof(E);
     for (int k = 0; k < chunks; ++k) {
         const long long r0 = (long long)k * rows;
         if (r0 >= N) break;
@@ -402,7 +403,7 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
                            cudaMemcpyHostToDevice, e->copy_in));
         CU(cudaEventRecord(e->ev_in[k], e->copy_in));
         CU(cudaStreamWaitEvent(e->stream, e->ev_in[k], 0));
-        int rc = launch_step_rows<T>(e, p, ck, e->d_actions, obs_dst ? e->d_obs : nullptr, rew_dst ? e->d_rew : nullptr, r0, n,
+        int rc = launch_step_rows<T, E>(e, p, ck, e->d_actions, obs_dst ? e->d_obs : nullptr, rew_dst ? e->d_rew : nullptr, r0, n,
                                      /*allow_pdl=*/false); /* ordered by stream events, not by the previous kernel */
         if (rc) return rc;
         CU(cudaEventRecord(e->ev_k[k], e->stream));
@@ -411,7 +412,7 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
             CU(cudaMemcpyAsync((char *)obs_dst + r0 * orow, (const char *)e->d_obs + r0 * orow, n * orow,
                                cudaMemcpyDeviceToHost, e->copy_out));
         if (rew_dst)
-            CU(cudaMemcpyAsync((char *)rew_dst + r0 * sizeof(T), (const char *)e->d_rew + r0 * sizeof(T), n * sizeof(T),
+            CU(cudaMemcpyAsync((char *)rew_dst + r0 * sizeof(E), (const char *)e->d_rew + r0 * sizeof(E), n * sizeof(E),
                                cudaMemcpyDeviceToHost, e->copy_out));
     }
     CU(cudaStreamSynchronize(e->copy_out));
@@ -421,7 +422,7 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
     return MBT_OK;
 }
 
-template <typename T>
+template <typename T, typename E>
 static int do_reset_device(mbt_env *e, const mbt_reset_args *args, void *obs) {
     const mbt_config &c = e->cfg;
     const double t0 = args ? args->start_time : c.start_time;
@@ -431,10 +432,10 @@ static int do_reset_device(mbt_env *e, const mbt_reset_args *args, void *obs) {
     if (q0_mode == MBT_Q0_UNIFORM_INT && !(hi > lo)) return fail(MBT_E_INVALID_ARG, "initial inventory range needs hi > lo");
     if (!(t0 >= 0.0) || !(t0 < c.terminal_time))
         return fail(MBT_E_INVALID_ARG, "Start time is not within (0, env.terminal_time)."); /* TradingEnvironment.py:267 */
-    ResetArgs<T> g;
+    ResetArgs<T, E> g;
     g.p = mbt_make_params<T>(c, t0, q0_mode == MBT_Q0_UNIFORM_INT, q0_const);
     g.st = dev_state<T>(e);
-    g.obs = (T *)obs;
+    g.obs = (E *)obs;
     g.n = e->N;
     g.seed = e->seed;
     g.traj_offset = (unsigned long long)c.traj_offset;
@@ -449,7 +450,7 @@ static int do_reset_device(mbt_env *e, const mbt_reset_args *args, void *obs) {
     g.q0_const = (T)q0_const;
     g.q0_lo = lo;
     g.q0_span = (unsigned long long)(hi - lo);
-    mbt_reset_kernel<T><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
+    mbt_reset_kernel<T, E><<<grid_for(g.n), MBT_BLOCK, 0, e->stream>>>(g);
     CU(cudaGetLastError());
     e->launches += 1;
     e->t = t0;
@@ -461,6 +462,11 @@ static int do_reset_device(mbt_env *e, const mbt_reset_args *args, void *obs) {
     e->q0_uniform = q0_const;
     return MBT_OK;
 }
+
+/* (arithmetic type, caller-buffer element type) dispatch: (double,double), (double,float) or (float,float) */
+#define MBT_CALL_TE(e, fn, ...)                                                                          \
+    ((e)->cfg.precision == MBT_F64 ? ((e)->io_esz == 4 ? fn<double, float>(__VA_ARGS__) : fn<double, double>(__VA_ARGS__)) \
+                                   : fn<float, float>(__VA_ARGS__))
 
 /* ------------------------------------------------------------------ ABI */
 extern "C" {
@@ -559,6 +565,7 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     mbt_dims(cfg, &e->A, &e->D, &e->S);
     e->Dout = mbt_obs_out_dim(cfg, e->D);
     e->esz = cfg->precision == MBT_F64 ? 8 : 4;
+    e->io_esz = (cfg->precision == MBT_F64 && cfg->io_precision == MBT_IO_SAME) ? 8 : 4;
     auto bail = [&](int code) {
         std::string keep = g_err;
         mbt_destroy(e);
@@ -657,10 +664,10 @@ int mbt_reset(mbt_env *e, const mbt_reset_args *args, void *obs_out, int mem) {
         if (rc) return rc;
         dev_obs = e->d_obs;
     }
-    int rc = e->cfg.precision == MBT_F64 ? do_reset_device<double>(e, args, dev_obs) : do_reset_device<float>(e, args, dev_obs);
+    int rc = MBT_CALL_TE(e, do_reset_device, e, args, dev_obs);
     if (rc) return rc;
     if (obs_out && mem == MBT_MEM_HOST) {
-        const size_t ob = (size_t)e->N * e->Dout * e->esz;
+        const size_t ob = (size_t)e->N * e->Dout * e->io_esz;
         bool unstage = false;
         rc = d2h(e, obs_out, e->d_obs, e->h_obs, ob, &unstage);
         if (rc) return rc;
@@ -676,15 +683,12 @@ int mbt_step(mbt_env *e, const void *actions, void *obs_out, void *rew_out, uint
     if (mem != MBT_MEM_HOST && mem != MBT_MEM_DEVICE) return fail(MBT_E_INVALID_ARG, "mem must be MBT_MEM_HOST or MBT_MEM_DEVICE");
     if (!e->started) return fail(MBT_E_STATE, "mbt_step called before mbt_reset");
     CU(cudaSetDevice(e->device));
-    const bool f64 = e->cfg.precision == MBT_F64;
-    if (mem == MBT_MEM_DEVICE)
-        return f64 ? do_step_device<double>(e, actions, obs_out, rew_out, done_out)
-                   : do_step_device<float>(e, actions, obs_out, rew_out, done_out);
+    if (mem == MBT_MEM_DEVICE) return MBT_CALL_TE(e, do_step_device, e, actions, obs_out, rew_out, done_out);
 
     /* host buffers: H2D actions -> kernel -> D2H observations + rewards, pipelined, all inside this call */
     int rc = ensure_staging(e);
     if (rc) return rc;
-    const size_t ab = (size_t)e->N * e->A * e->esz, ob = (size_t)e->N * e->Dout * e->esz, rb = (size_t)e->N * e->esz;
+    const size_t ab = (size_t)e->N * e->A * e->io_esz, ob = (size_t)e->N * e->Dout * e->io_esz, rb = (size_t)e->N * e->io_esz;
     const void *src = actions;
     if (!host_ptr_is_pinned(actions)) { /* pageable caller memory: stage through the handle's pinned buffer */
         par_memcpy(e->h_actions, actions, ab);
@@ -700,12 +704,11 @@ int mbt_step(mbt_env *e, const void *actions, void *obs_out, void *rew_out, uint
         CU(cudaHostGetDevicePointer(&da, const_cast<void *>(src), 0));
         if (obs_dst) CU(cudaHostGetDevicePointer(&dobs, obs_dst, 0));
         if (rew_dst) CU(cudaHostGetDevicePointer(&drew, rew_dst, 0));
-        rc = f64 ? do_step_device<double>(e, da, dobs, drew, done_out) : do_step_device<float>(e, da, dobs, drew, done_out);
+        rc = MBT_CALL_TE(e, do_step_device, e, da, dobs, drew, done_out);
         if (rc) return rc;
         CU(cudaStreamSynchronize(e->stream));
     } else {
-        rc = f64 ? do_step_host_pipelined<double>(e, src, obs_dst, rew_dst, done_out)
-                 : do_step_host_pipelined<float>(e, src, obs_dst, rew_dst, done_out);
+        rc = MBT_CALL_TE(e, do_step_host_pipelined, e, src, obs_dst, rew_dst, done_out);
         if (rc) return rc;
     }
     if (un_obs) par_memcpy(obs_out, e->h_obs, ob);

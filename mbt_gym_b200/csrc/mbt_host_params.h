@@ -50,6 +50,7 @@ static inline int mbt_validate_config(const mbt_config *c, std::string &err) {
         return MBT_E_INVALID_ARG;
     }
     if (c->precision != MBT_F64 && c->precision != MBT_F32) { err = "precision must be MBT_F64 or MBT_F32"; return MBT_E_INVALID_ARG; }
+    if (c->io_precision != MBT_IO_SAME && c->io_precision != MBT_IO_F32) { err = "io_precision must be MBT_IO_SAME or MBT_IO_F32"; return MBT_E_INVALID_ARG; }
     if (c->num_trajectories <= 0) { err = "num_trajectories must be > 0"; return MBT_E_INVALID_ARG; }
     if (c->traj_offset < 0) { err = "traj_offset must be >= 0"; return MBT_E_INVALID_ARG; }
     if (c->n_steps <= 0 || !(c->step_size > 0) || !(c->terminal_time > 0)) {

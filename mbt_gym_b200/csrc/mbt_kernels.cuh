@@ -32,14 +32,16 @@ struct DevState {
     T *cash, *inv, *mid, *x0, *x1, *q0;
 };
 
-template <typename T>
+/* T = arithmetic / state type; E = element type of the CALLER's buffers (E = T, or float over double arithmetic:
+ * `io_precision = MBT_IO_F32`, values converted with round-to-nearest on the way in / out) */
+template <typename T, typename E = T>
 struct StepArgs {
     StepParams<T> p;
     StepClock<T> ck;
     DevState<T> st;
-    const T *actions; /* (N, A) */
-    T *obs;           /* (N, D) or NULL */
-    T *rew;           /* (N,)   or NULL */
+    const E *actions; /* (N, A) */
+    E *obs;           /* (N, D) or NULL */
+    E *rew;           /* (N,)   or NULL */
     long long n;
     mbt_philox_keys keys; /* the ten Philox round keys of the seed, expanded on the host */
     unsigned long long traj_offset, n_step;
@@ -197,18 +199,19 @@ __device__ __forceinline__ void store_traj(const StepParams<T> &p, const DevStat
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-template <typename T, class V, bool VEC>
-__device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i, bool full_warp, T *warp_smem) {
+template <typename T, typename E, class V, bool VEC>
+__device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, bool full_warp, E *warp_smem) {
     const StepParams<T> &p = g.p;
     /* state-independent prologue: the step's 128 random bits depend only on (seed, trajectory id, step index) */
     const mbt_u32x4 r = mbt_draw_keyed(g.keys, g.traj_offset + (unsigned long long)i, g.n_step, MBT_STREAM_STEP);
     pdl_wait(); /* everything below reads what the previous kernel (previous step, or the caller's policy) wrote */
     const int A = action_width<T, V>(p);
+    E a_io[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
+    load_row<E>(g.actions, i, A, a_io, VEC);
     T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
-    load_row<T>(g.actions, i, A, a, VEC);
 #pragma unroll
     for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j)
-        if (j < A) a[j] = denorm_action<T, V>(p, a[j], j);
+        if (j < A) a[j] = denorm_action<T, V>(p, (T)a_io[j], j);
 
     Traj<T> s;
     load_traj<T, V>(p, g.st, i, s);
@@ -224,12 +227,16 @@ __device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i, bool
         T row[MBT_MAX_OBS_DIM];
         make_obs_row<T, V>(p, s, g.ck.t_next, row);
         const int D = obs_width<T, V>(p);
+        E row_io[MBT_MAX_OBS_DIM];
+#pragma unroll
+        for (int d = 0; d < MBT_MAX_OBS_DIM; ++d)
+            if (d < D) row_io[d] = (E)row[d];
         if (D != 4 && D != 2 && full_warp)
-            store_rows_staged<T>(g.obs, i - (long long)(threadIdx.x & 31u), D, row, warp_smem, threadIdx.x & 31u);
+            store_rows_staged<E>(g.obs, i - (long long)(threadIdx.x & 31u), D, row_io, warp_smem, threadIdx.x & 31u);
         else
-            store_row<T>(g.obs, i, D, row, VEC);
+            store_row<E>(g.obs, i, D, row_io, VEC);
     }
-    if (g.rew) g.rew[i] = rwd;
+    if (g.rew) g.rew[i] = (E)rwd;
     if (clipped) atomicAdd(g.clipped, 1ull);
 }
 
@@ -240,27 +247,27 @@ __device__ __forceinline__ void step_row(const StepArgs<T> &g, long long i, bool
  * already equals the measured HBM rate; what is left at N = 2^20 is a fixed ~5 us of launch / ramp / drain.
  * VEC: the caller's action/obs pointers are aligned for whole-row vector access.
  */
-template <typename T, class V, bool VEC>
-__global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_constant__ StepArgs<T> g) {
+template <typename T, typename E, class V, bool VEC>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_constant__ StepArgs<T, E> g) {
     /* staging for non-power-of-two observation rows: one 32 x MBT_MAX_OBS_DIM tile per warp (unused when D == 4) */
     constexpr bool FIXED_W = V::D && V::norm == 0;          /* emitted row width known at compile time */
     constexpr int SW = FIXED_W ? V::D : MBT_MAX_OBS_DIM;     /* staged row width */
-    __shared__ T smem[(FIXED_W && V::D == 4) ? 1 : (MBT_BLOCK / 32) * 32 * SW];
+    __shared__ E smem[(FIXED_W && V::D == 4) ? 1 : (MBT_BLOCK / 32) * 32 * SW];
     const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
     const long long warp_row0 = i - (long long)(threadIdx.x & 31u);
     const bool full_warp = !(FIXED_W && V::D == 4) && (warp_row0 + 32 <= g.n); /* warp-uniform */
-    T *warp_smem = (FIXED_W && V::D == 4) ? smem : smem + (threadIdx.x >> 5) * 32 * SW;
+    E *warp_smem = (FIXED_W && V::D == 4) ? smem : smem + (threadIdx.x >> 5) * 32 * SW;
     pdl_launch_dependents();
-    if (i < g.n) step_row<T, V, VEC>(g, i, full_warp, warp_smem);
+    if (i < g.n) step_row<T, E, V, VEC>(g, i, full_warp, warp_smem);
     else pdl_wait();
 }
 
 /* ------------------------------------------------------------------ reset */
-template <typename T>
+template <typename T, typename E = T>
 struct ResetArgs {
     StepParams<T> p; /* for normalisation + model kinds */
     DevState<T> st;
-    T *obs;
+    E *obs;
     long long n;
     unsigned long long seed, traj_offset, n_episode;
     T cash0, t0, mid0, lam0[2], imp0;
@@ -270,8 +277,8 @@ struct ResetArgs {
     unsigned long long q0_span;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(MBT_BLOCK) mbt_reset_kernel(const __grid_constant__ ResetArgs<T> g) {
+template <typename T, typename E>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_reset_kernel(const __grid_constant__ ResetArgs<T, E> g) {
     const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
     if (i >= g.n) return;
     const StepParams<T> &p = g.p;
@@ -297,7 +304,11 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_reset_kernel(const __grid_const
     if (g.obs) {
         T row[MBT_MAX_OBS_DIM];
         const int d = make_obs_row<T, VariantGeneric>(p, s, g.t0, row);
-        store_row<T>(g.obs, i, d, row, false);
+        E row_io[MBT_MAX_OBS_DIM];
+#pragma unroll
+        for (int k = 0; k < MBT_MAX_OBS_DIM; ++k)
+            if (k < d) row_io[k] = (E)row[k];
+        store_row<E>(g.obs, i, d, row_io, false);
     }
 }
 

@@ -7,6 +7,8 @@ What differs is where the work happens: every `reset()` / `step()` is ONE call t
 
 Extra keyword-only arguments (all optional, defaults keep the reference behaviour):
     precision     "float64" (default, the reference's dtype) or "float32"
+    io_dtype      dtype of the action / observation / reward arrays exchanged with the caller: default = `precision`;
+                  `np.float32` with float64 arithmetic keeps the dynamics reference-exact and halves the host traffic
     device        CUDA device index
     traj_offset   global id of trajectory 0 (multi-GPU sharding: RNG counters use global ids)
     copy_outputs  False: `step()`/`reset()` return views of a ring of 4 pinned host buffers (valid until 4 more
@@ -53,7 +55,7 @@ class TradingEnvironment(_EnvBase):
                  initial_inventory=0, max_inventory=10_000, max_cash=None, max_stock_price=None, start_time=0.0,
                  info_calculator=None, seed=None, num_trajectories=1, normalise_action_space=True,
                  normalise_observation_space=True, normalise_rewards=False, *, precision="float64", device=0,
-                 traj_offset=0, copy_outputs=False, obs_columns=None):
+                 traj_offset=0, copy_outputs=False, obs_columns=None, io_dtype=None):
         super().__init__()
         self._native = None
         self._native_cfg_bytes = None
@@ -64,6 +66,11 @@ class TradingEnvironment(_EnvBase):
         self._dones_cache = None
         self.precision = {"float64": _abi.MBT_F64, "f64": _abi.MBT_F64, "float32": _abi.MBT_F32, "f32": _abi.MBT_F32}[str(precision)]
         self.dtype = np.dtype(np.float64 if self.precision == _abi.MBT_F64 else np.float32)
+        # dtype of the arrays step()/reset() exchange with the caller: the arithmetic dtype, or float32 over float64
+        # arithmetic (SB3's buffers are float32; the PCIe-bound host path then moves half the bytes)
+        self.io_dtype = self.dtype if io_dtype is None else np.dtype(io_dtype)
+        if self.io_dtype not in (self.dtype, np.dtype(np.float32)):
+            raise ValueError("io_dtype must be the environment's dtype or float32")
         self.device, self.traj_offset, self.copy_outputs = int(device), int(traj_offset), bool(copy_outputs)
         self._obs_columns = None
 
@@ -156,8 +163,8 @@ class TradingEnvironment(_EnvBase):
             raise RuntimeError("step() called before reset()")
         if hasattr(action, "is_cuda") and action.is_cuda:
             return self._step_device(native, action)
-        a = action if (type(action) is np.ndarray and action.dtype == self.dtype and action.flags.c_contiguous) \
-            else np.ascontiguousarray(action, dtype=self.dtype)
+        a = action if (type(action) is np.ndarray and action.dtype == self.io_dtype and action.flags.c_contiguous) \
+            else np.ascontiguousarray(action, dtype=self.io_dtype)
         if a.shape != (self.num_trajectories, native.A):
             if a.size == self.num_trajectories * native.A and self.num_trajectories == 1:
                 a = a.reshape(1, native.A)
@@ -171,7 +178,7 @@ class TradingEnvironment(_EnvBase):
     def _step_device(self, native, action):
         import torch
 
-        tdt = torch.float64 if self.precision == _abi.MBT_F64 else torch.float32
+        tdt = torch.float64 if self.io_dtype == np.float64 else torch.float32
         if action.dtype != tdt or not action.is_contiguous():
             action = action.to(tdt).contiguous()
         if tuple(action.shape) != (self.num_trajectories, native.A):
@@ -280,7 +287,7 @@ class TradingEnvironment(_EnvBase):
         """A page-locked (N, A) array in the environment's dtype: fill it and pass it to `step()` and the action copy
         is one direct DMA (any other host array is first staged through the handle's own pinned buffer)."""
         native = self._ensure_native()
-        self._pinned_actions = _lib.PinnedArray((self.num_trajectories, native.A), self.dtype, self.device)
+        self._pinned_actions = _lib.PinnedArray((self.num_trajectories, native.A), self.io_dtype, self.device)
         return self._pinned_actions.array
 
     def close(self):
@@ -406,6 +413,7 @@ class TradingEnvironment(_EnvBase):
         cfg.normalise_rewards = int(bool(self.normalise_rewards_))
         cfg.reward_scaling = float(self.reward_scaling)
         cfg.obs_select = sum(1 << c for c in self._obs_columns) if self._obs_columns else 0
+        cfg.io_precision = _abi.MBT_IO_F32 if (self.io_dtype == np.float32 and self.dtype == np.float64) else _abi.MBT_IO_SAME
         if self.normalise_action_space_:
             lo, gr = self._intercept_action_norm, self._gradient_action_norm
             for i in range(lo.shape[0]):
@@ -434,9 +442,9 @@ class TradingEnvironment(_EnvBase):
     def _out_buffers(self):
         n, d = self.num_trajectories, self._native.Dout
         if self.copy_outputs:
-            return np.empty((n, d), self.dtype), np.empty((n,), self.dtype)
+            return np.empty((n, d), self.io_dtype), np.empty((n,), self.io_dtype)
         if self._ring is None:
-            self._ring = [(_lib.PinnedArray((n, d), self.dtype, self.device), _lib.PinnedArray((n,), self.dtype, self.device))
+            self._ring = [(_lib.PinnedArray((n, d), self.io_dtype, self.device), _lib.PinnedArray((n,), self.io_dtype, self.device))
                           for _ in range(_RING)]
             self._ring_pos = 0
         o, r = self._ring[self._ring_pos]

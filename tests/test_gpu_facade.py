@@ -279,3 +279,24 @@ def test_fused_column_select_equals_host_side_wrapper(name, cols, precision):
             assert_same(o1, g.obs[k][:, cols], exact=g.exact, what=f"{name} vs fixture {k}")
     assert fused.env.state.shape[1] == g.obs.shape[2], "env.state keeps every column"
     fused.env.close(); plain.env.close()
+
+
+@pytest.mark.parametrize("name", ["as_pnl", "hawkes_normalised", "oe_ou_cjoe", "cjmm"])
+def test_float32_io_over_float64_arithmetic_is_the_rounded_float64_result(name):
+    """io_dtype=float32: actions arrive as float32, the dynamics run in float64 exactly as before, observations and
+    rewards leave rounded to float32 -- so they must equal np.float32(<float64 run fed the same float32 actions>)."""
+    g = Golden(name)
+    e32 = build_facade_env(SPECS[name], io_dtype=np.float32)
+    e64 = build_facade_env(SPECS[name])
+    o32, o64 = e32.reset(), e64.reset()
+    assert o32.dtype == np.float32 and o64.dtype == np.float64
+    assert_same(o32, o64.astype(np.float32), what=f"{name} reset")
+    for k in range(15):
+        a32 = g.actions[k].astype(np.float32)
+        o32, r32, d32, _ = e32.step(a32)
+        o64, r64, d64, _ = e64.step(a32.astype(np.float64))
+        assert o32.dtype == np.float32 and r32.dtype == np.float32
+        assert_same(o32, o64.astype(np.float32), what=f"{name} obs {k}")
+        assert_same(r32, r64.astype(np.float32), what=f"{name} rew {k}")
+    assert_same(e32.state, e64.state, what=f"{name} state stays float64 and identical")
+    e32.close(); e64.close()
