@@ -14,18 +14,26 @@ except Exception:  # noqa: BLE001
 
 
 class _TerminalInfos:
-    """Sequence of N dicts, each {"terminal_observation": terminal_obs[i]}, built on demand."""
+    """Sequence of N dicts built on demand: {"terminal_observation": terminal_obs[i]} and, with `monitor=True`,
+    {"episode": {"r": return, "l": length, "t": seconds}} -- the entries SB3's VecMonitor would add."""
 
-    def __init__(self, terminal_obs):
+    def __init__(self, terminal_obs, episode=None):
         self._obs = terminal_obs
+        self._episode = episode  # (returns (N,), length, elapsed seconds) or None
 
     def __len__(self):
-        return self._obs.shape[0]
+        return self._obs.shape[0] if self._obs is not None else self._episode[0].shape[0]
 
     def __getitem__(self, i):
         if isinstance(i, slice):
             return [self[j] for j in range(*i.indices(len(self)))]
-        return {"terminal_observation": self._obs[i, :]}
+        info = {}
+        if self._obs is not None:
+            info["terminal_observation"] = self._obs[i, :]
+        if self._episode is not None:
+            ret, length, elapsed = self._episode
+            info["episode"] = {"r": float(ret[i]), "l": int(length), "t": elapsed}
+        return info
 
     def __iter__(self):
         return (self[i] for i in range(len(self)))
@@ -35,9 +43,17 @@ class _TerminalInfos:
 
 
 class StableBaselinesTradingEnvironment(_VecEnvBase):
-    def __init__(self, trading_env, store_terminal_observation_info=True):
+    def __init__(self, trading_env, store_terminal_observation_info=True, monitor=False):
+        """monitor=True replaces SB3's VecMonitor (whose bookkeeping is a Python loop over all N environments at every
+        episode end): episode returns are accumulated with one vectorised add per step and surface as lazy
+        `info["episode"]` entries; `episode_returns` / `last_episode_statistics` expose them in bulk."""
         self.env = trading_env
         self.store_terminal_observation_info = store_terminal_observation_info
+        self.monitor = monitor
+        self.episode_returns = None
+        self.episode_length = 0
+        self.last_episode_statistics = None
+        self._t_start = None
         self.actions = self.env.action_space.sample()
         if _VecEnvBase is not object:
             super().__init__(self.env.num_trajectories, self.env.observation_space, self.env.action_space)
@@ -46,16 +62,39 @@ class StableBaselinesTradingEnvironment(_VecEnvBase):
             self.observation_space, self.action_space = self.env.observation_space, self.env.action_space
 
     def reset(self):
+        self._begin_episode()
         return self.env.reset()
+
+    def _begin_episode(self):
+        if self.monitor:
+            import time
+
+            self.episode_returns = np.zeros((self.env.num_trajectories,), dtype=np.float64)
+            self.episode_length = 0
+            self._t_start = time.time()
 
     def step_async(self, actions):
         self.actions = actions
 
     def step_wait(self):
         obs, rewards, dones, infos = self.env.step(self.actions)
+        if self.monitor:
+            if self.episode_returns is None:
+                self._begin_episode()
+            self.episode_returns += np.asarray(rewards)
+            self.episode_length += 1
         if dones.min():
-            if self.store_terminal_observation_info:
-                infos = _TerminalInfos(np.array(obs, copy=True))
+            episode = None
+            if self.monitor:
+                import time
+
+                r = self.episode_returns
+                episode = (r, self.episode_length, round(time.time() - self._t_start, 6))
+                self.last_episode_statistics = {"mean_return": float(r.mean()), "std_return": float(r.std()),
+                                                "length": self.episode_length, "num_episodes": int(r.shape[0])}
+            if self.store_terminal_observation_info or episode is not None:
+                infos = _TerminalInfos(np.array(obs, copy=True) if self.store_terminal_observation_info else None, episode)
+            self._begin_episode()
             obs = self.env.reset()  # SB3 convention: auto-reset, return the first observation of the new episode
         return obs, rewards, dones, infos
 

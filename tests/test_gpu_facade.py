@@ -131,6 +131,20 @@ def test_vecenv_adapter_autoreset_and_lazy_terminal_observation():
     obs, rew, dones, infos = venv.step_wait()
     assert not dones.any() and infos[0] == {}
     env.close()
+    # monitor=True: VecMonitor-style episode entries without a per-environment Python loop
+    env = build_facade_env(spec)
+    venv = StableBaselinesTradingEnvironment(env, monitor=True)
+    venv.reset()
+    total = np.zeros(64)
+    for k in range(5):
+        obs, rew, dones, infos = venv.step(act)
+        total += rew
+    assert dones.all()
+    ep = infos[7]["episode"]
+    assert ep["l"] == 5 and ep["r"] == pytest.approx(total[7]) and "terminal_observation" in infos[7]
+    assert venv.last_episode_statistics["mean_return"] == pytest.approx(total.mean())
+    assert np.all(venv.episode_returns == 0)
+    env.close()
 
 
 def test_reward_calculate_runs_on_device_and_matches_reference_unit_tests():
