@@ -369,7 +369,10 @@ def main():
         env.set_stream(stream.cuda_stream)
         ret = torch.empty((N,), dtype=tdt, device="cuda")
         env.reset(mem=_abi.MBT_MEM_DEVICE)
-        env.rollout(pol, ret, None, mem=_abi.MBT_MEM_DEVICE)  # warm-up episode
+        warm = env.rollout(pol, ret, None, mem=_abi.MBT_MEM_DEVICE)  # warm-up episode
+        if world > 1:  # first use of a collective sets up its NCCL channels: not part of the per-episode cost
+            sharding.allreduce_summary(warm, device=torch.device("cuda", local_rank))
+            sharding.allgather_returns(ret)
         env.reset(mem=_abi.MBT_MEM_DEVICE)
         barrier()
         r0, r1, r2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
