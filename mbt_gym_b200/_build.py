@@ -9,7 +9,7 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libmbt_b200.so")
 
 SOURCES = ["mbt_capi.cu"]
-DEPS = ["mbt_capi.cu", "mbt_kernels.cuh", "mbt_step_core.cuh", "mbt_host_params.h"]
+DEPS = ["mbt_capi.cu", "mbt_kernels.cuh", "mbt_step_core.cuh", "mbt_host_params.h", "mbt_variants.h"]
 HEADERS = ["mbt_b200.h", "mbt_math.h", "mbt_philox.h"]
 
 NVCC_FLAGS = [

@@ -20,6 +20,7 @@
 
 #include "../../include/mbt_b200.h"
 #include "mbt_host_params.h"
+#include "mbt_variants.h"
 #include "mbt_kernels.cuh"
 
 /* ------------------------------------------------------------------ errors */
@@ -259,44 +260,6 @@ static void launch_step_v(mbt_env *e, const StepArgs<T, E> &g, bool vec, bool al
         launch_step_k<T, E, V, true>(e, g, allow_pdl);
     else
         launch_step_k<T, E, V, false>(e, g, allow_pdl);
-}
-
-/*
- * Kernel variants.  The BASELINE.json configurations (and the reference's default-constructor market) get
- * instantiations with model kinds, row widths, reward kind and "no normalisation" fixed at compile time;
- * everything else runs the generic kernel with runtime switches (warp-uniform branches).
- */
-#define V_(d, m, a, i, r, n) Variant<d, m, a, i, r, n>
-#define MBT_FOR_EACH_VARIANT(X)                                                                                     \
-    X(0, VariantGeneric)                                                                                            \
-    X(1, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_PNL, 0))                              \
-    X(2, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_CJ_MM, 0))                            \
-    X(3, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_RUNNING_INVENTORY_PENALTY, 0))        \
-    X(4, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, -1, -1))                                      \
-    X(5, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, MBT_REW_PNL, 0))                               \
-    X(6, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, -1, -1))                                       \
-    X(7, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, MBT_REW_CJ_OE, 0))                          \
-    X(8, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, MBT_REW_PNL, 0))                            \
-    X(9, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, -1, -1))
-
-static int variant_of(const mbt_config &c) {
-    const bool plain = !c.normalise_action && !c.normalise_obs && !c.normalise_rewards && !c.obs_select;
-    if (c.dynamics == MBT_DYN_LIMIT && c.midprice == MBT_MID_BM && c.impact == MBT_IMP_NONE) {
-        if (c.arrival == MBT_ARR_POISSON) {
-            if (plain && c.reward == MBT_REW_PNL) return 1;
-            if (plain && c.reward == MBT_REW_CJ_MM) return 2;
-            if (plain && c.reward == MBT_REW_RUNNING_INVENTORY_PENALTY) return 3;
-            return 4;
-        }
-        if (c.arrival == MBT_ARR_HAWKES) return (plain && c.reward == MBT_REW_PNL) ? 5 : 6;
-    }
-    if (c.dynamics == MBT_DYN_SPEED && c.midprice == MBT_MID_OU && c.impact == MBT_IMP_TEMP_PERM &&
-        c.arrival == MBT_ARR_NONE) {
-        if (plain && c.reward == MBT_REW_CJ_OE) return 7;
-        if (plain && c.reward == MBT_REW_PNL) return 8;
-        return 9;
-    }
-    return 0;
 }
 
 /* may the step kernel use whole-row vector accesses on the caller's buffers?  (see load_row / store_row:

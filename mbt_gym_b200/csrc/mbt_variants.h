@@ -1,0 +1,49 @@
+/*
+ * mbt_variants.h -- the list of compile-time kernel specialisations and the rule that picks one for a config.
+ * Shared by mbt_capi.cu (the real launches) and tests/hostsim (the host compile of the same per-trajectory core), so the
+ * two cannot drift apart.
+ */
+#ifndef MBT_VARIANTS_H
+#define MBT_VARIANTS_H
+
+#include "mbt_step_core.cuh"
+
+/*
+ * Kernel variants.  The BASELINE.json configurations (and the reference's default-constructor market) get
+ * instantiations with model kinds, row widths, reward kind and "no normalisation" fixed at compile time;
+ * everything else runs the generic kernel with runtime switches (warp-uniform branches).
+ */
+#define V_(d, m, a, i, r, n) Variant<d, m, a, i, r, n>
+#define MBT_FOR_EACH_VARIANT(X)                                                                                     \
+    X(0, VariantGeneric)                                                                                            \
+    X(1, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_PNL, 0))                              \
+    X(2, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_CJ_MM, 0))                            \
+    X(3, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_RUNNING_INVENTORY_PENALTY, 0))        \
+    X(4, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, -1, -1))                                      \
+    X(5, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, MBT_REW_PNL, 0))                               \
+    X(6, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, -1, -1))                                       \
+    X(7, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, MBT_REW_CJ_OE, 0))                          \
+    X(8, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, MBT_REW_PNL, 0))                            \
+    X(9, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, -1, -1))
+
+static int variant_of(const mbt_config &c) {
+    const bool plain = !c.normalise_action && !c.normalise_obs && !c.normalise_rewards && !c.obs_select;
+    if (c.dynamics == MBT_DYN_LIMIT && c.midprice == MBT_MID_BM && c.impact == MBT_IMP_NONE) {
+        if (c.arrival == MBT_ARR_POISSON) {
+            if (plain && c.reward == MBT_REW_PNL) return 1;
+            if (plain && c.reward == MBT_REW_CJ_MM) return 2;
+            if (plain && c.reward == MBT_REW_RUNNING_INVENTORY_PENALTY) return 3;
+            return 4;
+        }
+        if (c.arrival == MBT_ARR_HAWKES) return (plain && c.reward == MBT_REW_PNL) ? 5 : 6;
+    }
+    if (c.dynamics == MBT_DYN_SPEED && c.midprice == MBT_MID_OU && c.impact == MBT_IMP_TEMP_PERM &&
+        c.arrival == MBT_ARR_NONE) {
+        if (plain && c.reward == MBT_REW_CJ_OE) return 7;
+        if (plain && c.reward == MBT_REW_PNL) return 8;
+        return 9;
+    }
+    return 0;
+}
+
+#endif /* MBT_VARIANTS_H */

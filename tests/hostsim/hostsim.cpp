@@ -11,20 +11,7 @@
 #include <vector>
 
 #include "../../mbt_gym_b200/csrc/mbt_host_params.h"
-
-/* the same specialisations mbt_capi.cu instantiates (MBT_FOR_EACH_VARIANT) */
-#define V_(d, m, a, i, r, n) Variant<d, m, a, i, r, n>
-#define HOSTSIM_VARIANTS(X)                                                                                  \
-    X(0, VariantGeneric)                                                                                     \
-    X(1, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_PNL, 0))                       \
-    X(2, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_CJ_MM, 0))                     \
-    X(3, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, MBT_REW_RUNNING_INVENTORY_PENALTY, 0)) \
-    X(4, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_POISSON, MBT_IMP_NONE, -1, -1))                               \
-    X(5, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, MBT_REW_PNL, 0))                        \
-    X(6, V_(MBT_DYN_LIMIT, MBT_MID_BM, MBT_ARR_HAWKES, MBT_IMP_NONE, -1, -1))                                \
-    X(7, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, MBT_REW_CJ_OE, 0))                   \
-    X(8, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, MBT_REW_PNL, 0))                     \
-    X(9, V_(MBT_DYN_SPEED, MBT_MID_OU, MBT_ARR_NONE, MBT_IMP_TEMP_PERM, -1, -1))
+#include "../../mbt_gym_b200/csrc/mbt_variants.h" /* MBT_FOR_EACH_VARIANT, variant_of: the table mbt_capi.cu launches from */
 
 template <typename T, class V>
 static void run(const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, double t_start, int q0_per_traj,
@@ -68,12 +55,15 @@ static void dispatch(int variant, const mbt_config &c, uint64_t seed, int64_t n_
 #define GO(...) run<T, __VA_ARGS__>(c, seed, n_step0, t0, t_start, q0_per_traj, q0_uniform, (T *)state, (const T *)q0, steps, (const T *)actions, (T *)obs, (T *)rew, dones)
     switch (variant) {
 #define X(id, ...) case id: GO(__VA_ARGS__); break;
-        HOSTSIM_VARIANTS(X)
+        MBT_FOR_EACH_VARIANT(X)
 #undef X
     default: GO(VariantGeneric); break;
     }
 #undef GO
 }
+
+/* the variant the library would launch for this config (variant < 0 in hostsim_run selects it) */
+extern "C" int hostsim_variant_of(const mbt_config *c) { return variant_of(*c); }
 
 extern "C" int hostsim_run(const mbt_config *c, int variant, uint64_t seed, int64_t n_step0, double t0, double t_start,
                            int q0_per_traj, double q0_uniform, void *state, const void *q0, int steps,

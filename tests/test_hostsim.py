@@ -28,34 +28,10 @@ def hostsim():
                     SRC, "-o", SO], check=True)
     lib = C.CDLL(SO)
     vp = C.c_void_p
+    lib.hostsim_variant_of.argtypes = [C.POINTER(_abi.mbt_config)]
     lib.hostsim_run.argtypes = [C.POINTER(_abi.mbt_config), C.c_int, C.c_uint64, C.c_int64, C.c_double, C.c_double,
                                 C.c_int, C.c_double, vp, vp, C.c_int, vp, vp, vp, vp]
     return lib
-
-
-def variant_of(cfg):
-    """Mirror of variant_of() in mbt_gym_b200/csrc/mbt_capi.cu."""
-    A = _abi
-    plain = not (cfg.normalise_action or cfg.normalise_obs or cfg.normalise_rewards)
-    if cfg.dynamics == A.MBT_DYN_LIMIT and cfg.midprice == A.MBT_MID_BM and cfg.impact == A.MBT_IMP_NONE:
-        if cfg.arrival == A.MBT_ARR_POISSON:
-            if plain and cfg.reward == A.MBT_REW_PNL:
-                return 1
-            if plain and cfg.reward == A.MBT_REW_CJ_MM:
-                return 2
-            if plain and cfg.reward == A.MBT_REW_RUNNING_INVENTORY_PENALTY:
-                return 3
-            return 4
-        if cfg.arrival == A.MBT_ARR_HAWKES:
-            return 5 if (plain and cfg.reward == A.MBT_REW_PNL) else 6
-    if (cfg.dynamics == A.MBT_DYN_SPEED and cfg.midprice == A.MBT_MID_OU and cfg.impact == A.MBT_IMP_TEMP_PERM
-            and cfg.arrival == A.MBT_ARR_NONE):
-        if plain and cfg.reward == A.MBT_REW_CJ_OE:
-            return 7
-        if plain and cfg.reward == A.MBT_REW_PNL:
-            return 8
-        return 9
-    return 0
 
 
 def run_hostsim(lib, g, precision, variant):
@@ -91,7 +67,7 @@ def run_hostsim(lib, g, precision, variant):
 @pytest.mark.parametrize("name", golden_names())
 def test_kernel_core_f64_matches_reference_fixture(hostsim, name):
     g = Golden(name)
-    for variant in sorted({0, variant_of(g.cfg)}):
+    for variant in sorted({0, hostsim.hostsim_variant_of(C.byref(g.cfg))}):
         obs, rew, done, _, _ = run_hostsim(hostsim, g, _abi.MBT_F64, variant)
         assert_same(obs, g.obs, exact=g.exact, what=f"{name} obs (variant {variant})")
         assert_same(rew, g.rew, exact=g.exact, what=f"{name} rew (variant {variant})")
@@ -101,7 +77,7 @@ def test_kernel_core_f64_matches_reference_fixture(hostsim, name):
 @pytest.mark.parametrize("name", golden_names())
 def test_kernel_core_f32_matches_oracle_f32(hostsim, name):
     g = Golden(name)
-    for variant in sorted({0, variant_of(g.cfg)}):
+    for variant in sorted({0, hostsim.hostsim_variant_of(C.byref(g.cfg))}):
         obs, rew, done, oobs, orew = run_hostsim(hostsim, g, _abi.MBT_F32, variant)
         assert_same(obs, oobs, exact=True, what=f"{name} f32 obs (variant {variant})")
         assert_same(rew, orew, exact=True, what=f"{name} f32 rew (variant {variant})")
