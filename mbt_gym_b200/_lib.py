@@ -10,7 +10,7 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmbt_b200.so")
+LIB_PATH = os.environ.get("MBT_LIB_PATH") or os.path.join(_HERE, "libmbt_b200.so")  # MBT_LIB_PATH: tuning builds only
 
 # every symbol include/mbt_b200.h declares (checked by tests/test_abi_symbols.py)
 ABI_SYMBOLS = [

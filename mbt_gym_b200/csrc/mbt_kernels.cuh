@@ -25,7 +25,10 @@
 
 #include "mbt_step_core.cuh"
 
-constexpr int MBT_BLOCK = 256;
+#ifndef MBT_BLOCK_THREADS
+#define MBT_BLOCK_THREADS 256 /* tuned on B200: 128 / 256 / 512 measured in profiles/r1_step_kernel_history.md */
+#endif
+constexpr int MBT_BLOCK = MBT_BLOCK_THREADS;
 
 template <typename T>
 struct DevState {
