@@ -250,7 +250,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: mbt_gym_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("MBT_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner there at any NCCL_DEBUG level >= VERSION
+        if "MBT_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["MBT_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
