@@ -125,7 +125,8 @@ class TradingEnvironment(_EnvBase):
     def select_observation_columns(self, columns):
         """Emit only these observation columns (in increasing order) -- `ReduceStateSizeWrapper` fused into the kernel's
         observation store (mbt_gym/gym/wrappers.py:10-43): no host-side fancy-index copy and proportionally fewer D2H
-        bytes.  `None` restores all columns.  `env.state` and the agents' `to_policy` forms are unaffected."""
+        bytes.  `None` restores all columns.  Takes effect at the next `reset()` (the device handle is rebuilt from the
+        Python attributes there).  `env.state` and the agents' `to_policy` forms are unaffected."""
         if columns is None:
             self._obs_columns = None
         else:
