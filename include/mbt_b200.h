@@ -12,7 +12,7 @@
  *   mbt_reset       <- TradingEnvironment.reset/initial_state TradingEnvironment.py:96-101,131-140
  *   mbt_step        <- TradingEnvironment.step                TradingEnvironment.py:103-110
  *                      (+ everything it calls: ModelDynamics.py:108-131,262-267;
- *                       arrival_models.py:54-56,110-123; fill_probability_models.py:28-34,57-58;
+ *                       arrival_models.py:54-56,110-123; fill_probability_models.py:28-34,57-58,82,113;
  *                       midprice_models.py:60-65,97-105,140-143; price_impact_models.py:88-92;
  *                       RewardFunctions.py:23-33,55-70,96-109,128-138)
  *   mbt_get_state   <- TradingEnvironment.state (property)    TradingEnvironment.py:142-144
@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MBT_ABI_VERSION 1
+#define MBT_ABI_VERSION 2
 
 /* error codes */
 #define MBT_OK 0
@@ -86,7 +86,15 @@ extern "C" {
 
 /* fill_probability_models.py */
 #define MBT_FILL_NONE 0
-#define MBT_FILL_EXPONENTIAL 1 /* ExponentialFillFunction :42-65 */
+#define MBT_FILL_EXPONENTIAL 1 /* ExponentialFillFunction :42-65  p = exp(-kappa*depth), per trajectory and side */
+/* The next two are implemented AS WRITTEN in the reference: `np.max(depths, 0)` there is a reduction over the
+ * TRAJECTORY axis (not an elementwise maximum with 0), so the fill probability of a step is a function of the
+ * deepest quote of the whole batch -- one value per side (Power), or one value for both sides (Triangular, whose
+ * outer `np.max(..., 0)` reduces the two sides as well).  The step therefore has a batch reduction in front of it
+ * (mbt_fill_batch_kernel).  "Batch" = the trajectories of this handle, like one worker of the reference's
+ * MultiprocessTradingEnv. */
+#define MBT_FILL_TRIANGULAR 2 /* TriangularFillFunction  :68-91  p = max_side(1 - max_traj(depth)/max_fill_depth)        */
+#define MBT_FILL_POWER 3      /* PowerFillFunction       :94-123 p_side = 1/(1 + (multiplier*max_traj(depth))^exponent)  */
 
 /* price_impact_models.py */
 #define MBT_IMP_NONE 0
@@ -149,7 +157,9 @@ typedef struct mbt_config {
     double hawkes_speed; /* mean_reversion_speed */
 
     /* fill model */
-    double fill_exponent; /* ExponentialFillFunction.fill_exponent */
+    double fill_exponent;   /* ExponentialFillFunction.fill_exponent / PowerFillFunction.fill_exponent */
+    double fill_max_depth;  /* TriangularFillFunction.max_fill_depth */
+    double fill_multiplier; /* PowerFillFunction.fill_multiplier */
 
     /* price impact model */
     double imp_temp;     /* temporary_impact_coefficient */

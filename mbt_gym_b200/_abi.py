@@ -5,7 +5,7 @@ Kept in one place so the product binding (`_lib.py`) and the test oracle's loade
 """
 import ctypes as C
 
-MBT_ABI_VERSION = 1
+MBT_ABI_VERSION = 2
 
 MBT_OK = 0
 MBT_E_INVALID_ARG = -1
@@ -42,6 +42,9 @@ MBT_ARR_HAWKES = 3
 
 MBT_FILL_NONE = 0
 MBT_FILL_EXPONENTIAL = 1
+MBT_FILL_TRIANGULAR = 2
+MBT_FILL_POWER = 3
+FILLS_WITH_BATCH_REDUCTION = (MBT_FILL_TRIANGULAR, MBT_FILL_POWER)
 
 MBT_IMP_NONE = 0
 MBT_IMP_TEMP_PERM = 1
@@ -104,6 +107,8 @@ class mbt_config(C.Structure):
         ("hawkes_jump", C.c_double),
         ("hawkes_speed", C.c_double),
         ("fill_exponent", C.c_double),
+        ("fill_max_depth", C.c_double),
+        ("fill_multiplier", C.c_double),
         ("imp_temp", C.c_double),
         ("imp_perm", C.c_double),
         ("imp_exponent", C.c_double),

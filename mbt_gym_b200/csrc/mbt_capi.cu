@@ -68,6 +68,11 @@ struct mbt_env {
     cudaStream_t copy_in = nullptr, copy_out = nullptr; /* H2D / D2H copy engines for the pipelined host path */
     cudaEvent_t ev_in[MBT_PIPE_CHUNKS] = {}, ev_k[MBT_PIPE_CHUNKS] = {};
 
+    /* batch reduction in front of the step (Triangular / Power fill functions): partial maxima, ticket, thresholds */
+    void *d_fill_partial = nullptr, *d_fill_thr = nullptr;
+    unsigned int *d_fill_ticket = nullptr;
+    int fill_blocks = 1;
+
     /* rollout scratch */
     double *d_times = nullptr;
     int times_cap = 0;
@@ -105,6 +110,11 @@ static DevState<T> dev_state(mbt_env *e) {
 }
 
 static inline unsigned grid_for(long long n) { return (unsigned)((n + MBT_BLOCK - 1) / MBT_BLOCK); }
+
+/* does a step of this config start with the batch reduction of the quoted depths? */
+static inline bool needs_fill_batch(const mbt_config &c) {
+    return fill_is_batch(c.fill) && (c.dynamics == MBT_DYN_LIMIT || c.dynamics == MBT_DYN_LIMIT_AND_MARKET);
+}
 
 static int timing_begin(mbt_env *e) {
     if (!e->timing || e->timed >= MBT_TIMING_RING) return MBT_OK;
@@ -289,12 +299,30 @@ static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<
     g.traj_offset = (unsigned long long)c.traj_offset + (unsigned long long)r0;
     g.n_step = (unsigned long long)e->n_step;
     g.clipped = e->d_clipped;
+    g.fill_thr = (const T *)e->d_fill_thr;
     const bool vec = rows_vector_aligned<E>(e, g.actions, g.obs);
     switch (variant_of(c)) {
 #define X(id, ...) case id: launch_step_v<T, E, __VA_ARGS__>(e, g, vec, allow_pdl); break;
         MBT_FOR_EACH_VARIANT(X)
 #undef X
     }
+    CU(cudaGetLastError());
+    e->launches += 1;
+    return MBT_OK;
+}
+
+/* the batch reduction of the quoted depths (mbt_fill_batch_kernel) over ALL rows of the action matrix */
+template <typename T, typename E>
+static int launch_fill_batch(mbt_env *e, const StepParams<T> &p, const void *actions) {
+    FillBatchArgs<T, E> g;
+    g.p = p;
+    g.actions = (const E *)actions;
+    g.n = e->N;
+    g.partial = (T *)e->d_fill_partial;
+    g.ticket = e->d_fill_ticket;
+    g.thr = (T *)e->d_fill_thr;
+    const unsigned blocks = std::min<unsigned>(grid_for(e->N), (unsigned)e->fill_blocks);
+    mbt_fill_batch_kernel<T, E><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
     CU(cudaGetLastError());
     e->launches += 1;
     return MBT_OK;
@@ -314,7 +342,12 @@ static int do_step_device(mbt_env *e, const void *actions, void *obs, void *rew,
     const StepClock<T> ck = mbt_make_clock<T>(c, e->t, t_next, e->t0);
     int rc = timing_begin(e);
     if (rc) return rc;
-    rc = launch_step_rows<T, E>(e, p, ck, actions, obs, rew, 0, e->N, /*allow_pdl=*/true);
+    const bool batch = needs_fill_batch(c);
+    if (batch) {
+        rc = launch_fill_batch<T, E>(e, p, actions);
+        if (rc) return rc;
+    }
+    rc = launch_step_rows<T, E>(e, p, ck, actions, obs, rew, 0, e->N, /*allow_pdl=*/!batch);
     if (rc) return rc;
     rc = timing_end(e);
     if (rc) return rc;
@@ -355,7 +388,8 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
     const StepParams<T> p = mbt_make_params<T>(c, e->t0, e->q0_per_traj, e->q0_uniform);
     const StepClock<T> ck = mbt_make_clock<T>(c, e->t, t_next, e->t0);
     const long long N = e->N;
-    int chunks = N >= (1 << 17) ? pipe_chunks() : 1;
+    const bool batch = needs_fill_batch(c); /* the reduction needs every action row on the device first */
+    int chunks = (N >= (1 << 17) && !batch) ? pipe_chunks() : 1;
     long long rows = ((N + chunks - 1) / chunks + 255) & ~255ll;
     const size_t arow = (size_t)e->A * sizeof(E), orow = (size_t)e->Dout * sizeof(E);
     for (int k = 0; k < chunks; ++k) {
@@ -366,6 +400,10 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
                            cudaMemcpyHostToDevice, e->copy_in));
         CU(cudaEventRecord(e->ev_in[k], e->copy_in));
         CU(cudaStreamWaitEvent(e->stream, e->ev_in[k], 0));
+        if (batch) {
+            int rcb = launch_fill_batch<T, E>(e, p, e->d_actions);
+            if (rcb) return rcb;
+        }
         int rc = launch_step_rows<T, E>(e, p, ck, e->d_actions, obs_dst ? e->d_obs : nullptr, rew_dst ? e->d_rew : nullptr, r0, n,
                                      /*allow_pdl=*/false); /* ordered by stream events, not by the previous kernel */
         if (rc) return rc;
@@ -481,6 +519,9 @@ int mbt_destroy(mbt_env *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->state_block);
     cudaFree(e->d_clipped);
+    cudaFree(e->d_fill_partial);
+    cudaFree(e->d_fill_thr);
+    cudaFree(e->d_fill_ticket);
     cudaFree(e->d_actions);
     cudaFree(e->d_obs);
     cudaFree(e->d_rew);
@@ -560,6 +601,14 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     for (int i = 0; i < 6; ++i) e->col[i] = (char *)e->state_block + col_bytes * i;
     CUB(cudaMalloc(&e->d_clipped, sizeof(unsigned long long)));
     CUB(cudaMemsetAsync(e->d_clipped, 0, sizeof(unsigned long long), e->stream));
+    if (needs_fill_batch(*cfg)) {
+        e->fill_blocks = std::max(1, e->sm_count * 8);
+        CUB(cudaMalloc(&e->d_fill_partial, (size_t)e->fill_blocks * 2 * sizeof(double)));
+        CUB(cudaMalloc(&e->d_fill_thr, 2 * sizeof(double)));
+        CUB(cudaMalloc((void **)&e->d_fill_ticket, sizeof(unsigned int)));
+        CUB(cudaMemsetAsync(e->d_fill_thr, 0, 2 * sizeof(double), e->stream));
+        CUB(cudaMemsetAsync(e->d_fill_ticket, 0, sizeof(unsigned int), e->stream));
+    }
     CUB(cudaStreamSynchronize(e->stream));
 #undef CUB
     *out = e;
@@ -925,6 +974,10 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
         return fail(MBT_E_UNSUPPORTED, "unknown policy kind");
     }
     if (pol->kind == MBT_POL_AVELLANEDA_STOIKOV && e->A != 2) return fail(MBT_E_UNSUPPORTED, "Avellaneda-Stoikov policy needs a 2-d action");
+    if (needs_fill_batch(c) && (pol->kind == MBT_POL_AVELLANEDA_STOIKOV || pol->kind == MBT_POL_CJ_MM_TABLE))
+        return fail(MBT_E_UNSUPPORTED,
+                    "triangular / power fill functions couple the trajectories of a step (np.max(depths, 0) in the reference): the "
+                    "fused rollout supports them only with policies that are uniform over the batch (fixed, schedule); use step()");
     g.returns = (T *)returns;
     g.term_q = (T *)term_q;
     if (rec) {

@@ -74,8 +74,8 @@ static inline int mbt_validate_config(const mbt_config *c, std::string &err) {
     } else {
         /* ModelDynamics.py:123-125,163-165,234-236: arrival (+ fill) models required */
         if (c->arrival < MBT_ARR_POISSON || c->arrival > MBT_ARR_HAWKES) { err = "limit-order dynamics need an arrival model"; return MBT_E_UNSUPPORTED; }
-        if (c->dynamics != MBT_DYN_AT_TOUCH && c->fill != MBT_FILL_EXPONENTIAL) {
-            err = "limit-order dynamics need the exponential fill model";
+        if (c->dynamics != MBT_DYN_AT_TOUCH && (c->fill < MBT_FILL_EXPONENTIAL || c->fill > MBT_FILL_POWER)) {
+            err = "limit-order dynamics need a fill probability model (exponential, triangular or power)";
             return MBT_E_UNSUPPORTED;
         }
         if (c->impact != MBT_IMP_NONE) { err = "price impact models only combine with speed dynamics"; return MBT_E_UNSUPPORTED; }
@@ -113,6 +113,8 @@ static inline StepParams<T> mbt_make_params(const mbt_config &c, double t0, int 
     int32_t A, D, S;
     mbt_dims(&c, &A, &D, &S);
     p.dyn = c.dynamics; p.mid = c.midprice; p.arr = c.arrival; p.imp = c.impact; p.rew = c.reward;
+    /* only dynamics that draw fills from the fill model look at its kind (AtTheTouch / speed dynamics ignore it) */
+    p.fill = (c.dynamics == MBT_DYN_LIMIT || c.dynamics == MBT_DYN_LIMIT_AND_MARKET) ? c.fill : MBT_FILL_NONE;
     p.action_dim = A; p.obs_dim = D;
     p.obs_select = (int)c.obs_select; p.obs_out_dim = mbt_obs_out_dim(&c, D);
     p.normalise_action = c.normalise_action; p.normalise_obs = c.normalise_obs; p.normalise_rewards = c.normalise_rewards;
@@ -136,6 +138,7 @@ static inline StepParams<T> mbt_make_params(const mbt_config &c, double t0, int 
     p.arr_step = (T)c.arr_step; p.arr_rate[0] = (T)c.arr_rate[0]; p.arr_rate[1] = (T)c.arr_rate[1];
     p.hawkes_speed = (T)c.hawkes_speed; p.hawkes_jump = (T)c.hawkes_jump;
     p.neg_kappa = -(T)c.fill_exponent;
+    p.fill_max_depth = (T)c.fill_max_depth; p.fill_mult = (T)c.fill_multiplier; p.fill_pexp = (T)c.fill_exponent;
     p.drift_dt = (T)(c.mid_drift * c.mid_step);
     p.vol_sqdt = (T)(c.mid_vol * std::sqrt(c.mid_step));
     p.sqdt = (T)std::sqrt(c.mid_step);

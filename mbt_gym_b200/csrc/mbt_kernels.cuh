@@ -49,6 +49,7 @@ struct StepArgs {
     mbt_philox_keys keys; /* the ten Philox round keys of the seed, expanded on the host */
     unsigned long long traj_offset, n_step;
     unsigned long long *clipped;
+    const T *fill_thr; /* batch-reduced fill models: the step's two thresholds, written by mbt_fill_batch_kernel */
 };
 
 /* the specialised variants know the row widths at compile time */
@@ -222,8 +223,14 @@ __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, b
     T q_init = p.q0_uniform;
     if ((rew_kind == MBT_REW_CJ_MM || rew_kind == MBT_REW_CJ_OE) && p.q0_per_traj) q_init = g.st.q0[i];
 
+    T fill_thr[2] = {(T)0, (T)0};
+    if (V::dyn < 0 && fill_is_batch(p.fill)) { /* two uniform scalars, L2-resident broadcast loads */
+        fill_thr[0] = g.fill_thr[0];
+        fill_thr[1] = g.fill_thr[1];
+    }
+
     int clipped = 0;
-    const T rwd = step_one<T, V>(p, g.ck, s, a, r, q_init, &clipped);
+    const T rwd = step_one<T, V>(p, g.ck, s, a, r, q_init, &clipped, fill_thr);
 
     store_traj<T, V>(p, g.st, i, s);
     if (g.obs) {
@@ -263,6 +270,82 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_consta
     pdl_launch_dependents();
     if (i < g.n) step_row<T, E, V, VEC>(g, i, full_warp, warp_smem);
     else pdl_wait();
+}
+
+/* ------------------------------------------------------------------ batch reduction in front of the step */
+/*
+ * Triangular / Power fill functions (fill_probability_models.py:82,113): the reference's `np.max(depths, 0)` reduces
+ * over the trajectory axis, so a step's fill probability depends on the deepest quote of the whole batch.  This kernel
+ * is that reduction: grid-stride NaN-propagating max of the (de-normalised) depth columns, warp shuffle -> shared ->
+ * one partial per block, and the LAST block to finish (ticket counter) folds the partials and writes the two
+ * thresholds the step kernel compares its fill uniforms with.  max is order-independent, so the result is
+ * deterministic and equal to numpy's.  One launch; the step kernel that follows is ordered after it by the stream.
+ */
+template <typename T, typename E>
+struct FillBatchArgs {
+    StepParams<T> p;
+    const E *actions; /* (N, A) */
+    long long n;
+    T *partial;           /* (gridDim.x, 2) scratch */
+    unsigned int *ticket; /* zero on entry, zero again on exit */
+    T *thr;               /* out: p_bid * 2^24, p_ask * 2^24 */
+};
+
+template <typename T>
+__device__ __forceinline__ T warp_nanmax(T v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = nanmax<T>(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+template <typename T, typename E>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_constant__ FillBatchArgs<T, E> g) {
+    const StepParams<T> &p = g.p;
+    const int A = p.action_dim;
+    const T neg_inf = -(T)INFINITY; /* identity of the NaN-propagating max */
+    T m0 = neg_inf, m1 = neg_inf;
+    for (long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x; i < g.n; i += (long long)gridDim.x * MBT_BLOCK) {
+        const E *row = g.actions + i * A; /* depths = action[:, 0:2]   ModelDynamics.py:50-51,128-130 */
+        m0 = nanmax<T>(m0, denorm_action<T, VariantGeneric>(p, (T)__ldg(row + 0), 0));
+        m1 = nanmax<T>(m1, denorm_action<T, VariantGeneric>(p, (T)__ldg(row + 1), 1));
+    }
+    __shared__ T sm[MBT_BLOCK / 32][2];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    m0 = warp_nanmax<T>(m0);
+    m1 = warp_nanmax<T>(m1);
+    if (lane == 0) { sm[warp][0] = m0; sm[warp][1] = m1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T b0 = sm[0][0], b1 = sm[0][1];
+        for (int w = 1; w < MBT_BLOCK / 32; ++w) { b0 = nanmax<T>(b0, sm[w][0]); b1 = nanmax<T>(b1, sm[w][1]); }
+        g.partial[2 * blockIdx.x + 0] = b0;
+        g.partial[2 * blockIdx.x + 1] = b1;
+        __threadfence(); /* the partial is visible before the ticket is taken */
+        is_last = atomicAdd(g.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    m0 = neg_inf; m1 = neg_inf;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += MBT_BLOCK) {
+        m0 = nanmax<T>(m0, __ldcg(g.partial + 2 * b + 0));
+        m1 = nanmax<T>(m1, __ldcg(g.partial + 2 * b + 1));
+    }
+    m0 = warp_nanmax<T>(m0);
+    m1 = warp_nanmax<T>(m1);
+    __syncthreads(); /* sm[] is reused */
+    if (lane == 0) { sm[warp][0] = m0; sm[warp][1] = m1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T b0 = sm[0][0], b1 = sm[0][1];
+        for (int w = 1; w < MBT_BLOCK / 32; ++w) { b0 = nanmax<T>(b0, sm[w][0]); b1 = nanmax<T>(b1, sm[w][1]); }
+        T thr[2];
+        fill_batch_thresholds<T>(p, b0, b1, thr);
+        g.thr[0] = thr[0];
+        g.thr[1] = thr[1];
+        *g.ticket = 0u; /* ready for the next step */
+    }
 }
 
 /* ------------------------------------------------------------------ reset */
@@ -456,7 +539,11 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
                     a[j] = denorm_action<T, V>(p, a[j], j);
                 }
             const mbt_u32x4 r = mbt_draw_keyed(g.keys, g.traj_offset + (unsigned long long)i, g.n_step0 + (unsigned long long)k, MBT_STREAM_STEP);
-            const T rwd = step_one<T, V>(p, ck, s, a, r, q_init, &clipped);
+            /* batch-reduced fill models: only policies whose action is uniform over the batch reach here (do_rollout),
+             * so the deepest quote of the batch is this trajectory's own */
+            T fill_thr[2] = {(T)0, (T)0};
+            if (V::dyn < 0 && fill_is_batch(p.fill)) fill_batch_thresholds<T>(p, a[0], a[1], fill_thr);
+            const T rwd = step_one<T, V>(p, ck, s, a, r, q_init, &clipped, fill_thr);
             ret = ret + rwd;
             acc[5] += (double)rwd * (double)rwd;
             if (REC && g.rec_rew) g.rec_rew[(long long)k * g.n + i] = rwd;

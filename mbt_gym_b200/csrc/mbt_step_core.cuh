@@ -53,7 +53,7 @@ MBT_HD void mbt_real_t(uint32_t k, double *u) { *u = mbt_u24_to_real_f64(k); }
 template <typename T>
 struct StepParams {
     /* model selectors (runtime copies; compile-time Variant wins when >= 0) */
-    int dyn, mid, arr, imp, rew;
+    int dyn, mid, arr, imp, rew, fill;
     int action_dim, obs_dim;
     int obs_select, obs_out_dim; /* ReduceStateSizeWrapper fused into the store: column bitmask (0 = all), emitted width */
     int normalise_action, normalise_obs, normalise_rewards;
@@ -67,6 +67,7 @@ struct StepParams {
     uint32_t arr_thr[2]; /* ceil(p_arr * 2^24) clamped to [0, 2^24]:  k*2^-24 < p_arr  <=>  k < arr_thr */
     T arr_step, arr_step_2p24 /* arr_step * 2^24 */, arr_rate[2], hawkes_speed, hawkes_jump;
     T neg_kappa; /* -fill_exponent */
+    T fill_max_depth, fill_mult, fill_pexp; /* Triangular: max_fill_depth;  Power: fill_multiplier, fill_exponent */
     T drift_dt, vol_sqdt, sqdt, mid_drift, mid_vol, mid_step, ou_neg_speed, ou_speed, ou_level, mid_jump;
     T imp_temp, imp_perm, imp_exp, imp_step, imp_transient, imp_resilience, imp_kernel, half_spread;
     T phi, alpha, pexp, risk_aversion, reward_scaling;
@@ -109,6 +110,34 @@ MBT_HD int pick(int runtime) { return CT >= 0 ? CT : runtime; }
 /* price-impact models that carry one state column (permanent impact I, or transient impact Y) */
 MBT_HD bool imp_has_state(int imp) { return imp == MBT_IMP_TEMP_PERM || imp == MBT_IMP_TEMP_TRANSIENT || imp == MBT_IMP_TRANSIENT; }
 
+/* fill functions whose probability is a reduction over the whole batch (see include/mbt_b200.h, MBT_FILL_TRIANGULAR) */
+MBT_HD bool fill_is_batch(int fill) { return fill == MBT_FILL_TRIANGULAR || fill == MBT_FILL_POWER; }
+
+/* np.max / np.maximum of two values: NaN wins */
+template <typename T>
+MBT_HD T nanmax(T a, T b) {
+    if (a != a) return a;
+    if (b != b) return b;
+    return a > b ? a : b;
+}
+
+/*
+ * The step's fill probabilities from the deepest quote of the batch on each side (m_bid, m_ask = np.max(depths, 0)),
+ * scaled by 2^24 for the integer-valued uniforms (exact: power-of-two scaling; NaN stays NaN = never filled).
+ *   Triangular  np.max(1 - np.max(depths, 0) / max_fill_depth, 0)                 fill_probability_models.py:82
+ *   Power       (1 + (fill_multiplier * np.max(depths, 0)) ** fill_exponent) ** -1   (`** -1` is 1/x in numpy)  :113
+ */
+template <typename T>
+MBT_HD void fill_batch_thresholds(const StepParams<T> &p, T m_bid, T m_ask, T *thr) {
+    if (p.fill == MBT_FILL_TRIANGULAR) {
+        const T pb = (T)1 - m_bid / p.fill_max_depth, pa = (T)1 - m_ask / p.fill_max_depth;
+        thr[0] = thr[1] = nanmax<T>(pb, pa) * (T)16777216.0;
+    } else {
+        thr[0] = ((T)1 / ((T)1 + mbt_pow_t(p.fill_mult * m_bid, p.fill_pexp))) * (T)16777216.0;
+        thr[1] = ((T)1 / ((T)1 + mbt_pow_t(p.fill_mult * m_ask, p.fill_pexp))) * (T)16777216.0;
+    }
+}
+
 /* reward_function.calculate for one row; (c0, q_cur, S0) = current_state, s = next_state. */
 template <typename T, class V>
 MBT_HD T reward_one(const StepParams<T> &p, const StepClock<T> &ck, T c0, T q_cur, T S0, const Traj<T> &s, const T *a, T q_init) {
@@ -134,12 +163,16 @@ MBT_HD T reward_one(const StepParams<T> &p, const StepClock<T> &ck, T c0, T q_cu
  *   a       raw (de-normalised) action, p.action_dim values
  *   r       the 128 random bits of this (trajectory, step)   include/mbt_philox.h draw contract
  *   q_init  initial inventory of the episode (for CjMm / CjOe)
+ *   fill_thr  batch-reduced fill models only: the step's two fill probabilities * 2^24 (fill_batch_thresholds)
  * returns the (scaled) reward; *clipped is set when inventory or cash hit their bounds.
  */
 template <typename T, class V>
-MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, const T *a, mbt_u32x4 r, T q_init, int *clipped) {
+MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, const T *a, mbt_u32x4 r, T q_init, int *clipped,
+                  const T *fill_thr = nullptr) {
     const int dyn = pick<V::dyn>(p.dyn), mid = pick<V::mid>(p.mid), arr_kind = pick<V::arr>(p.arr),
               imp = pick<V::imp>(p.imp);
+    /* the specialised variants are only selected for the exponential fill function (variant_of) */
+    const int fill = V::dyn >= 0 ? MBT_FILL_EXPONENTIAL : p.fill;
     const T c0 = s.cash, q_cur = s.inv, S = s.mid; /* current_state = state.copy()   TradingEnvironment.py:105 */
     T arr_b = 0, arr_a = 0;
     T own_b = 0, own_a = 0; /* the agent's own executed fills (fill * arrival), for the jump midprice models */
@@ -169,8 +202,13 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
             T vb, va;
             mbt_real_t(mbt_uniform_bits24(r.z), &vb);
             mbt_real_t(mbt_uniform_bits24(r.w), &va);
-            fil_b = (vb < mbt_exp2k_t(p.neg_kappa * a[0], 24)) ? (T)1 : (T)0;
-            fil_a = (va < mbt_exp2k_t(p.neg_kappa * a[1], 24)) ? (T)1 : (T)0;
+            if (fill_is_batch(fill)) { /* unif < p, p one value per side for the whole batch   :82,113 */
+                fil_b = (vb < fill_thr[0]) ? (T)1 : (T)0;
+                fil_a = (va < fill_thr[1]) ? (T)1 : (T)0;
+            } else {
+                fil_b = (vb < mbt_exp2k_t(p.neg_kappa * a[0], 24)) ? (T)1 : (T)0;
+                fil_a = (va < mbt_exp2k_t(p.neg_kappa * a[1], 24)) ? (T)1 : (T)0;
+            }
             off_b = a[0];
             off_a = a[1];
         }

@@ -28,7 +28,8 @@
 
 static int variant_of(const mbt_config &c) {
     const bool plain = !c.normalise_action && !c.normalise_obs && !c.normalise_rewards && !c.obs_select;
-    if (c.dynamics == MBT_DYN_LIMIT && c.midprice == MBT_MID_BM && c.impact == MBT_IMP_NONE) {
+    if (c.dynamics == MBT_DYN_LIMIT && c.midprice == MBT_MID_BM && c.impact == MBT_IMP_NONE &&
+        c.fill == MBT_FILL_EXPONENTIAL) {
         if (c.arrival == MBT_ARR_POISSON) {
             if (plain && c.reward == MBT_REW_PNL) return 1;
             if (plain && c.reward == MBT_REW_CJ_MM) return 2;

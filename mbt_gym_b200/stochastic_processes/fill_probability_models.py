@@ -34,3 +34,52 @@ class ExponentialFillFunction(FillProbabilityModel):
     def _flatten(self, cfg):
         cfg.fill = self.KIND
         cfg.fill_exponent = float(self.fill_exponent)
+
+
+class TriangularFillFunction(FillProbabilityModel):
+    """Reference :68-91, implemented as written there: `np.max(1 - np.max(depths, 0) / max_fill_depth, 0)` reduces over
+    the TRAJECTORY axis (and then over the two sides), so every quote of a step is filled with ONE probability that
+    follows the deepest quote of the batch.  On the device this is a batch reduction in front of the step kernel
+    (`mbt_fill_batch_kernel`).  `max_depth = 1.5 * max_fill_depth` (:84-86)."""
+    KIND = _abi.MBT_FILL_TRIANGULAR
+
+    def __init__(self, max_fill_depth=1.0, step_size=0.1, num_trajectories=1, seed=None):
+        self.max_fill_depth = max_fill_depth
+        super().__init__([[]], [[]], step_size, 0.0, [[]], num_trajectories, seed)
+
+    def _get_fill_probabilities(self, depths):
+        """Host helper for analysis only; same expression as the reference (a scalar)."""
+        return np.max(1 - np.max(np.asarray(depths), 0) / self.max_fill_depth, 0)
+
+    @property
+    def max_depth(self):
+        return 1.5 * self.max_fill_depth
+
+    def _flatten(self, cfg):
+        cfg.fill = self.KIND
+        cfg.fill_max_depth = float(self.max_fill_depth)
+
+
+class PowerFillFunction(FillProbabilityModel):
+    """Reference :94-123, implemented as written there: `(1 + (fill_multiplier * np.max(depths, 0)) ** fill_exponent) ** -1`
+    with `np.max(depths, 0)` over the TRAJECTORY axis -- one fill probability per side for the whole batch.
+    `max_depth = 0.01 ** (-1 / fill_exponent) - 1` (:115-117)."""
+    KIND = _abi.MBT_FILL_POWER
+
+    def __init__(self, fill_exponent=1.5, fill_multiplier=1.5, step_size=0.1, num_trajectories=1, seed=None):
+        self.fill_exponent = fill_exponent
+        self.fill_multiplier = fill_multiplier
+        super().__init__([[]], [[]], step_size, 0.0, [[]], num_trajectories, seed)
+
+    def _get_fill_probabilities(self, depths):
+        """Host helper for analysis only; same expression as the reference (one value per side)."""
+        return (1 + (self.fill_multiplier * np.max(np.asarray(depths), 0)) ** self.fill_exponent) ** -1
+
+    @property
+    def max_depth(self):
+        return 0.01 ** (-1 / self.fill_exponent) - 1
+
+    def _flatten(self, cfg):
+        cfg.fill = self.KIND
+        cfg.fill_exponent = float(self.fill_exponent)
+        cfg.fill_multiplier = float(self.fill_multiplier)

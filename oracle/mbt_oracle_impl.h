@@ -48,6 +48,11 @@ static REAL FN(orc_normal)(uint32_t bits) {
     /* draw contract (include/mbt_philox.h): the float quantile in both precisions, widened for float64 */
     return (REAL)mbt_normal_from_bits_f32(bits);
 }
+static REAL FN(orc_nanmax)(REAL a, REAL b) { /* np.max / np.maximum: NaN wins */
+    if (a != a) return a;
+    if (b != b) return b;
+    return a > b ? a : b;
+}
 static REAL FN(orc_clip)(REAL x, REAL lo, REAL hi) { /* np.clip = minimum(maximum(x, lo), hi) */
     REAL y = x < lo ? lo : x;
     return y > hi ? hi : y;
@@ -183,6 +188,26 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
         p_arr[1] = (REAL)(1.0 - mbt_exp_f64(-c->arr_rate[1] * c->arr_step));
     }
 
+    /* Triangular / Power fill functions: `np.max(depths, 0)` is a reduction over the trajectory axis, so the step's
+     * fill probabilities are batch-wide scalars             fill_probability_models.py:82,113 */
+    REAL p_fill_batch[2] = {0, 0};
+    if ((c->fill == MBT_FILL_TRIANGULAR || c->fill == MBT_FILL_POWER) &&
+        (c->dynamics == MBT_DYN_LIMIT || c->dynamics == MBT_DYN_LIMIT_AND_MARKET)) {
+        REAL m[2] = {0, 0};
+        for (int64_t i = 0; i < e->N; ++i)
+            for (int j = 0; j < 2; ++j) { /* depths = action[:, 0:2], de-normalised   ModelDynamics.py:50-51,128-130 */
+                REAL x = actions_in[i * A + j];
+                if (c->normalise_action) x = (x + (REAL)1) * (REAL)c->act_grad[j] + (REAL)c->act_low[j];
+                m[j] = (i == 0) ? x : FN(orc_nanmax)(m[j], x); /* np.max(depths, 0): NaN propagates */
+            }
+        if (c->fill == MBT_FILL_TRIANGULAR) { /* np.max(1 - np.max(depths, 0) / max_fill_depth, 0): a scalar  :82 */
+            REAL pb = (REAL)1 - m[0] / (REAL)c->fill_max_depth, pa = (REAL)1 - m[1] / (REAL)c->fill_max_depth;
+            p_fill_batch[0] = p_fill_batch[1] = FN(orc_nanmax)(pb, pa);
+        } else /* (1 + (fill_multiplier * np.max(depths, 0)) ** fill_exponent) ** -1: one value per side  :113 */
+            for (int j = 0; j < 2; ++j)
+                p_fill_batch[j] = (REAL)1 / ((REAL)1 + FN(orc_pow)((REAL)c->fill_multiplier * m[j], (REAL)c->fill_exponent));
+    }
+
     for (int64_t i = 0; i < e->N; ++i) {
         REAL *s = e->state + i * D;
         const REAL *cs = e->cur + i * D;
@@ -209,7 +234,8 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
                 fil[1] = a[1];
             } else {
                 for (int j = 0; j < 2; ++j) { /* unif < exp(-kappa * depth)   fill_probability_models.py:33,58 */
-                    REAL p = FN(orc_exp)(-(REAL)c->fill_exponent * a[j]);
+                    REAL p = (c->fill == MBT_FILL_EXPONENTIAL) ? FN(orc_exp)(-(REAL)c->fill_exponent * a[j])
+                                                               : p_fill_batch[j];
                     fil[j] = (u[i * 4 + 2 + j] < p) ? (REAL)1 : (REAL)0;
                 }
             }

@@ -129,7 +129,13 @@ def build_reference_env(spec):
                                         num_trajectories=N)
     f = spec.get("fill")
     if f:
-        fill = FM.ExponentialFillFunction(fill_exponent=f["fill_exponent"], step_size=dt, num_trajectories=N)
+        if f.get("kind", "exp") == "triangular":
+            fill = FM.TriangularFillFunction(max_fill_depth=f["max_fill_depth"], step_size=dt, num_trajectories=N)
+        elif f.get("kind", "exp") == "power":
+            fill = FM.PowerFillFunction(fill_exponent=f["fill_exponent"], fill_multiplier=f["fill_multiplier"],
+                                        step_size=dt, num_trajectories=N)
+        else:
+            fill = FM.ExponentialFillFunction(fill_exponent=f["fill_exponent"], step_size=dt, num_trajectories=N)
     p = spec.get("impact")
     if p:
         if p["kind"] == "temp_perm":
@@ -229,8 +235,11 @@ def config_from_reference_env(spec, env, precision=_abi.MBT_F64, traj_offset=0):
             cfg.arr_rate[0], cfg.arr_rate[1] = (float(x) for x in arr.intensity)
     fill = md.fill_probability_model
     if fill is not None:
-        cfg.fill = _abi.MBT_FILL_EXPONENTIAL
-        cfg.fill_exponent = float(fill.fill_exponent)
+        cfg.fill = {"exp": _abi.MBT_FILL_EXPONENTIAL, "triangular": _abi.MBT_FILL_TRIANGULAR,
+                    "power": _abi.MBT_FILL_POWER}[spec["fill"].get("kind", "exp")]
+        cfg.fill_exponent = float(getattr(fill, "fill_exponent", 0.0))
+        cfg.fill_max_depth = float(getattr(fill, "max_fill_depth", 0.0))
+        cfg.fill_multiplier = float(getattr(fill, "fill_multiplier", 0.0))
     imp = md.price_impact_model
     if imp is not None:
         kind = spec["impact"]["kind"]
@@ -290,6 +299,17 @@ def make_actions(spec, env, n_steps_run, action_seed):
     A = lo.shape[0]
     span = hi - lo
     acts = rng.uniform(lo - 0.15 * span, hi + 0.05 * span, size=(n_steps_run, N, A))  # slightly out of range too
+    if "depth_range" in spec:
+        # batch-reduced fill functions: the step's fill probability follows the DEEPEST quote of the batch, so the
+        # depths are drawn below a per-step ceiling that sweeps the interesting range (and sometimes beyond it)
+        d_lo, d_hi = spec["depth_range"]
+        ceil_k = rng.uniform(d_lo, d_hi, size=(n_steps_run, 1, 1))
+        depths = d_lo + rng.uniform(0.0, 1.0, size=(n_steps_run, N, 2)) * (ceil_k - d_lo)
+        if spec.get("normalise_action"):  # given in normalised units, de-normalised by the env
+            o_lo = np.asarray(env.original_action_space.low, float)[:2]
+            o_hi = np.asarray(env.original_action_space.high, float)[:2]
+            depths = (depths - o_lo) / ((o_hi - o_lo) / 2) - 1
+        acts[:, :, :2] = depths
     if spec["dynamics"] == "touch":
         acts = rng.integers(0, 2, size=(n_steps_run, N, 2)).astype(float)
     if spec["dynamics"] == "limit_and_market":

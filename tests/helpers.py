@@ -110,8 +110,14 @@ def build_facade_env(spec, **extra):
             arr = AM.HawkesArrivalModel(baseline_arrival_rate=np.array([a["baseline"]], float), step_size=dt,
                                         jump_size=a["jump"], mean_reversion_speed=a["speed"], terminal_time=T,
                                         num_trajectories=N)
-    if spec.get("fill"):
-        fill = FM.ExponentialFillFunction(fill_exponent=spec["fill"]["fill_exponent"], step_size=dt, num_trajectories=N)
+    f = spec.get("fill")
+    if f and f.get("kind", "exp") == "triangular":
+        fill = FM.TriangularFillFunction(max_fill_depth=f["max_fill_depth"], step_size=dt, num_trajectories=N)
+    elif f and f.get("kind", "exp") == "power":
+        fill = FM.PowerFillFunction(fill_exponent=f["fill_exponent"], fill_multiplier=f["fill_multiplier"], step_size=dt,
+                                    num_trajectories=N)
+    elif f:
+        fill = FM.ExponentialFillFunction(fill_exponent=f["fill_exponent"], step_size=dt, num_trajectories=N)
     p = spec.get("impact")
     if p:
         if p["kind"] == "temp_perm":

@@ -26,6 +26,17 @@ static void run(const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, 
     for (int k = 0; k < steps; ++k) {
         const double t_next = t + c.step_size;
         StepClock<T> ck = mbt_make_clock<T>(c, t, t_next, t0);
+        /* what mbt_fill_batch_kernel does in front of the step kernel: deepest quote of the batch -> thresholds */
+        T fill_thr[2] = {0, 0};
+        if (fill_is_batch(c.fill) && c.dynamics != MBT_DYN_AT_TOUCH && c.dynamics != MBT_DYN_SPEED) {
+            T m[2] = {0, 0};
+            for (int64_t i = 0; i < N; ++i)
+                for (int j = 0; j < 2; ++j) {
+                    const T x = denorm_action<T, V>(p, actions[((int64_t)k * N + i) * A + j], j);
+                    m[j] = i == 0 ? x : nanmax<T>(m[j], x);
+                }
+            fill_batch_thresholds<T>(p, m[0], m[1], fill_thr);
+        }
         for (int64_t i = 0; i < N; ++i) {
             T *row = state + i * D;
             Traj<T> s;
@@ -36,7 +47,7 @@ static void run(const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, 
             for (int j = 0; j < A; ++j) a[j] = denorm_action<T, V>(p, actions[((int64_t)k * N + i) * A + j], j);
             mbt_u32x4 r = mbt_draw_keyed(keys, (uint64_t)(c.traj_offset + i), (uint64_t)(n_step0 + k), MBT_STREAM_STEP);
             int clipped = 0;
-            T rw = step_one<T, V>(p, ck, s, a, r, q0_per_traj ? q0[i] : (T)q0_uniform, &clipped);
+            T rw = step_one<T, V>(p, ck, s, a, r, q0_per_traj ? q0[i] : (T)q0_uniform, &clipped, fill_thr);
             row[0] = s.cash; row[1] = s.inv; row[2] = ck.t_next; row[3] = s.mid;
             if (c.arrival == MBT_ARR_HAWKES) { row[4] = s.x0; row[5] = s.x1; }
             if (imp_has_state(c.impact)) row[4] = s.x0;

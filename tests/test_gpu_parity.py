@@ -103,7 +103,8 @@ def test_f32_matches_oracle_bitwise(name):
         assert_same(a, b, exact=True, what=f"{name} f32 {what}")
 
 
-@pytest.mark.parametrize("name", ["as_pnl", "hawkes_normalised", "oe_ou_cjoe", "limit_and_market"])
+@pytest.mark.parametrize("name", ["as_pnl", "hawkes_normalised", "oe_ou_cjoe", "limit_and_market", "power_fill",
+                                  "triangular_fill"])
 @pytest.mark.parametrize("precision", [_abi.MBT_F64, _abi.MBT_F32])
 def test_device_pointer_mode_equals_host_mode(name, precision):
     g = Golden(name)
@@ -177,6 +178,75 @@ def test_set_get_state_roundtrip_and_unaligned_buffers():
     e2.step(np.full((e.N, e.A), 0.5), ob2, rb2)
     assert_same(ob, ob2, what="misaligned obs"); assert_same(rb, rb2, what="misaligned rew")
     e.close(); e2.close()
+
+
+# --------------------------------------------------------------------------- batch-reduced fill functions
+@pytest.mark.parametrize("name", ["triangular_fill", "power_fill"])
+@pytest.mark.parametrize("precision", [_abi.MBT_F64, _abi.MBT_F32])
+def test_batch_fill_reduction_at_many_blocks(name, precision):
+    """Triangular / Power fill functions (reference: np.max(depths, 0) over the TRAJECTORY axis): the reduction kernel
+    in front of the step must find the deepest quote wherever it sits -- first row, last row, a row only the grid-stride
+    loop reaches -- at a size that needs every block of its grid, propagate NaN like np.max, and match the oracle
+    bit-for-bit.  N = 700 001 > 148 * 8 blocks * 256 threads, and not a multiple of anything."""
+    g = Golden(name)
+    dt = np.float64 if precision == _abi.MBT_F64 else np.float32
+    N = 700_001
+    cfg = g.config(precision, num_trajectories=N, normalise_action=0, normalise_obs=0)
+    e = _lib.NativeEnv(cfg)
+    orc = O.OracleEnv(cfg)
+    e.seed(5); orc.seed(5)
+    ob = np.empty((N, e.D), dt); rb = np.empty(N, dt)
+    e.reset(ob)
+    assert_same(ob, orc.reset(), what="reset")
+    rng = np.random.default_rng(1)
+    peaks = [0, N - 1, N // 2 + 17, 303_104 + 5, None, "nan"]
+    for k, where in enumerate(peaks):
+        a = rng.uniform(0.0, 0.4, size=(N, 2)).astype(dt)
+        if where == "nan":
+            a[N // 3, 1] = np.nan  # np.max -> NaN -> `unif < NaN` is False: nothing fills (on that side, or at all)
+        elif where is not None:
+            a[where, 0] = 0.55 + 0.05 * k
+            a[(where * 7 + 3) % N, 1] = 0.75 - 0.05 * k
+        e.step(a, ob, rb)
+        o, r, _d = orc.step(a)
+        assert_same(ob, o, what=f"{name} obs, peak at {where}")
+        assert_same(rb, r, what=f"{name} rew, peak at {where}")
+    assert len(np.unique(ob[:, 1])) > 3, "the fills must actually happen for the comparison to mean anything"
+    e.close()
+
+
+@pytest.mark.parametrize("precision", [_abi.MBT_F64, _abi.MBT_F32])
+def test_batch_fill_fused_rollout_uniform_policies_only(precision):
+    """With a batch-reduced fill function the fused rollout runs policies that are uniform over the batch (the deepest
+    quote of the batch is then every trajectory's own) and refuses the state-dependent ones with MBT_E_UNSUPPORTED."""
+    g = Golden("power_fill")
+    dt = np.float64 if precision == _abi.MBT_F64 else np.float32
+    cfg = g.config(precision, num_trajectories=777)
+    e = _lib.NativeEnv(cfg)
+    orc = O.OracleEnv(cfg)
+    e.seed(8); orc.seed(8)
+    e.reset(); orc.reset()
+    pol = _abi.mbt_policy()
+    pol.kind = _abi.MBT_POL_FIXED
+    pol.fixed[0], pol.fixed[1] = -0.6, -0.4  # normalised action units (the fixture normalises actions)
+    ret = np.empty(e.N, dt); qT = np.empty(e.N, dt)
+    e.rollout(pol, ret, qT)
+    R = np.zeros(e.N, dt)
+    done = False
+    a = np.tile(np.array([[-0.6, -0.4]], dt), (e.N, 1))
+    while not done:
+        _o, r, done = orc.step(a)
+        R = R + r
+    assert_same(ret, R, what="per-trajectory returns")
+    assert_same(e.get_state(), orc.state, what="terminal state")
+    assert len(np.unique(qT)) > 3
+    e.reset()
+    pol.kind = _abi.MBT_POL_AVELLANEDA_STOIKOV
+    pol.as_gamma, pol.as_sigma_sq, pol.as_fill_comp, pol.as_terminal_time = 0.1, 4.0, 1.0, 1.0
+    with pytest.raises(_lib.MbtError) as ei:
+        e.rollout(pol, ret)
+    assert ei.value.code == _abi.MBT_E_UNSUPPORTED
+    e.close()
 
 
 # --------------------------------------------------------------------------- fused rollout

@@ -94,6 +94,20 @@ SPECS = {
                          midprice=dict(kind="gbm", drift=0.02, volatility=0.1, initial_price=80.0),
                          impact=dict(kind="transient", transient=0.8, resilience=1.0, initial=0.0, kernel=0.5),
                          reward=dict(kind="pnl"), initial_inventory=-15, max_inventory=1000, normalise_action=True),
+    # fill functions whose probability is a BATCH reduction in the reference (np.max(depths, 0) over trajectories,
+    # fill_probability_models.py:82,113)
+    "triangular_fill": dict(N=77, n_steps=40, terminal_time=1.0, seed=1249, dynamics="limit", reward=dict(kind="pnl"),
+                            max_inventory=6, midprice=AS["midprice"], arrival=AS["arrival"],
+                            fill=dict(kind="triangular", max_fill_depth=1.0), depth_range=[-0.2, 1.3]),
+    "power_fill": dict(N=85, n_steps=40, terminal_time=1.0, seed=1250, dynamics="limit",
+                       reward=dict(kind="rip", phi=0.01, alpha=0.1), max_inventory=8, midprice=AS["midprice"],
+                       arrival=AS["arrival"], fill=dict(kind="power", fill_exponent=1.5, fill_multiplier=1.5),
+                       depth_range=[0.0, 2.5], normalise_action=True, normalise_obs=True),
+    "power_fill_limit_and_market": dict(N=45, n_steps=30, terminal_time=1.0, seed=1251, dynamics="limit_and_market",
+                                        half_spread=0.25, reward=dict(kind="pnl"), max_inventory=5,
+                                        midprice=AS["midprice"], arrival=AS["arrival"],
+                                        fill=dict(kind="power", fill_exponent=2.0, fill_multiplier=0.8),
+                                        depth_range=[0.0, 3.0]),
     # two episodes back to back: RNG stream continues, reset redraws inventories
     "two_episodes": dict(N=59, n_steps=30, terminal_time=1.0, seed=1244, dynamics="limit",
                          reward=dict(kind="cjmm", phi=0.01, alpha=0.001), max_inventory=20,
