@@ -74,8 +74,8 @@ struct mbt_env {
     int fill_blocks = 1;
 
     /* rollout scratch */
-    double *d_times = nullptr;
-    int times_cap = 0;
+    void *d_clocks = nullptr; /* RolloutClock<T>[steps] */
+    size_t clocks_cap = 0;    /* bytes */
     void *d_table = nullptr;
     size_t table_cap = 0;
     double *d_block_sums = nullptr, *h_block_sums = nullptr;
@@ -528,7 +528,7 @@ int mbt_destroy(mbt_env *e) {
     cudaFreeHost(e->h_actions);
     cudaFreeHost(e->h_obs);
     cudaFreeHost(e->h_rew);
-    cudaFree(e->d_times);
+    cudaFree(e->d_clocks);
     cudaFree(e->d_table);
     cudaFree(e->d_block_sums);
     cudaFreeHost(e->h_block_sums);
@@ -924,13 +924,23 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
             if (t >= c.terminal_time - c.step_size / 2) break;
         }
     }
-    if ((int)times.size() > e->times_cap) {
-        cudaFree(e->d_times);
-        e->d_times = nullptr;
-        CU(cudaMalloc(&e->d_times, times.size() * sizeof(double)));
-        e->times_cap = (int)times.size();
+    /* every step's uniform clock, formed exactly like the step kernel's (mbt_make_clock): the fused rollout and a loop of
+     * mbt_step calls see bit-identical StepClock values */
+    std::vector<RolloutClock<T>> clocks((size_t)steps);
+    for (int k = 0; k < steps; ++k) {
+        clocks[k].ck = mbt_make_clock<T>(c, times[k], times[k + 1], e->t0);
+        clocks[k].t_cur = (T)times[k];
     }
-    CU(cudaMemcpyAsync(e->d_times, times.data(), times.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    const size_t clock_bytes = clocks.size() * sizeof(RolloutClock<T>);
+    if (clock_bytes > e->clocks_cap) {
+        cudaFree(e->d_clocks);
+        e->d_clocks = nullptr;
+        e->clocks_cap = 0;
+        CU(cudaMalloc(&e->d_clocks, clock_bytes));
+        e->clocks_cap = clock_bytes;
+    }
+    /* pageable source: the copy is staged before cudaMemcpyAsync returns, so `clocks` may go out of scope */
+    CU(cudaMemcpyAsync(e->d_clocks, clocks.data(), clock_bytes, cudaMemcpyHostToDevice, e->stream));
 
     RolloutArgs<T> g;
     memset(&g, 0, sizeof g);
@@ -941,9 +951,7 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
     g.traj_offset = (unsigned long long)c.traj_offset;
     g.n_step0 = (unsigned long long)e->n_step;
     g.steps = steps;
-    g.times = e->d_times;
-    g.terminal_time = c.terminal_time;
-    g.step_size = c.step_size;
+    g.clocks = (const RolloutClock<T> *)e->d_clocks;
     g.pol_kind = pol->kind;
     g.table_rows = pol->table_rows;
     g.table_cols = pol->table_cols;
@@ -1001,11 +1009,19 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
     CU(cudaMemcpyAsync(&clip_before, e->d_clipped, sizeof clip_before, cudaMemcpyDeviceToHost, e->stream));
     int rc = timing_begin(e);
     if (rc) return rc;
+    /* the fast path (no recording) has the policy kind compiled in; the recording kernels (store-bound) switch at run time */
     switch (variant_of(c)) {
-#define X(id, ...)                                                                                  \
-    case id:                                                                                        \
-        if (rec) mbt_rollout_kernel<T, __VA_ARGS__, true><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);  \
-        else mbt_rollout_kernel<T, __VA_ARGS__, false><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);     \
+#define X(id, ...)                                                                                                        \
+    case id:                                                                                                              \
+        if (rec) mbt_rollout_kernel<T, __VA_ARGS__, true, -1><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);                    \
+        else if (pol->kind == MBT_POL_FIXED)                                                                              \
+            mbt_rollout_kernel<T, __VA_ARGS__, false, MBT_POL_FIXED><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);             \
+        else if (pol->kind == MBT_POL_AVELLANEDA_STOIKOV)                                                                 \
+            mbt_rollout_kernel<T, __VA_ARGS__, false, MBT_POL_AVELLANEDA_STOIKOV><<<blocks, MBT_BLOCK, 0, e->stream>>>(g); \
+        else if (pol->kind == MBT_POL_CJ_MM_TABLE)                                                                        \
+            mbt_rollout_kernel<T, __VA_ARGS__, false, MBT_POL_CJ_MM_TABLE><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);       \
+        else                                                                                                              \
+            mbt_rollout_kernel<T, __VA_ARGS__, false, MBT_POL_SCHEDULE><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);          \
         break;
         MBT_FOR_EACH_VARIANT(X)
 #undef X

@@ -449,6 +449,12 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_reward_kernel(StepParams<T> p, 
 constexpr int MBT_SUMMARY_DOUBLES = 6; /* sum R, sum R^2, sum q, sum q^2, sum action, sum r^2 */
 
 template <typename T>
+struct RolloutClock {
+    StepClock<T> ck;
+    T t_cur; /* time column BEFORE the step: what the policy sees in its observation */
+};
+
+template <typename T>
 struct RolloutArgs {
     StepParams<T> p;
     DevState<T> st;
@@ -456,8 +462,9 @@ struct RolloutArgs {
     mbt_philox_keys keys;
     unsigned long long traj_offset, n_step0;
     int steps;            /* env-steps to run (until the episode ends) */
-    const double *times;  /* device, steps+1 entries: the clock as the host accumulates it (t += dt) */
-    double terminal_time, step_size;
+    /* device, `steps` entries: the uniform clock of every step, formed on the host exactly like the step kernel's
+     * (mbt_make_clock on the host-accumulated t += dt) -- the loop loads it instead of redoing the arithmetic per thread */
+    const RolloutClock<T> *clocks;
     /* policy */
     int pol_kind, table_rows, table_cols, inv_offset;
     T fixed[MBT_MAX_ACTION_DIM];
@@ -474,16 +481,18 @@ struct RolloutArgs {
     unsigned long long *clipped;
 };
 
-template <typename T>
-__device__ __forceinline__ void policy_action(const RolloutArgs<T> &g, int k, T t, const Traj<T> &s, T *a) {
-    const int A = g.p.action_dim;
-    if (g.pol_kind == MBT_POL_AVELLANEDA_STOIKOV) { /* BaselineAgents.py:62-83 */
+/* POL >= 0: the policy kind is known at compile time (the action row stays in registers, no branches per step);
+ * POL < 0: runtime g.pol_kind (the recording kernels) */
+template <typename T, int POL>
+__device__ __forceinline__ void policy_action(const RolloutArgs<T> &g, int A, int k, T t, const Traj<T> &s, T *a) {
+    const int kind = POL >= 0 ? POL : g.pol_kind;
+    if (kind == MBT_POL_AVELLANEDA_STOIKOV) { /* BaselineAgents.py:62-83 */
         const T tau = g.as_terminal_time - t;
         const T adj = ((s.inv * g.as_gamma) * g.as_sigma_sq) * tau;
         const T spread = (g.as_gamma == (T)0) ? g.as_fill_comp : (g.as_gamma * g.as_sigma_sq) * tau + g.as_fill_comp;
         a[0] = adj + spread / (T)2;
         a[1] = -adj + spread / (T)2;
-    } else if (g.pol_kind == MBT_POL_CJ_MM_TABLE) { /* BaselineAgents.py:116-137 */
+    } else if (kind == MBT_POL_CJ_MM_TABLE) { /* BaselineAgents.py:116-137 */
         T fi = (T)g.inv_offset + s.inv;
         const T hi = (T)(2 * g.inv_offset);
         fi = fi < (T)0 ? (T)0 : fi;
@@ -492,15 +501,19 @@ __device__ __forceinline__ void policy_action(const RolloutArgs<T> &g, int k, T 
         const T *e = g.table + ((long long)k * g.table_cols + idx) * 2;
         a[0] = e[0];
         a[1] = e[1];
-    } else if (g.pol_kind == MBT_POL_SCHEDULE) {
-        for (int j = 0; j < A; ++j) a[j] = g.table[(long long)k * A + j];
+    } else if (kind == MBT_POL_SCHEDULE) {
+#pragma unroll
+        for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j)
+            if (j < A) a[j] = g.table[(long long)k * A + j];
     } else { /* MBT_POL_FIXED  BaselineAgents.py:25-42 */
+#pragma unroll
         for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j) a[j] = g.fixed[j];
     }
 }
 
-/* REC: compile the trajectory-recording stores in (mbt_rollout_record) or out (mbt_rollout, the fast path) */
-template <typename T, class V, bool REC>
+/* REC: compile the trajectory-recording stores in (mbt_rollout_record) or out (mbt_rollout, the fast path);
+ * POL: policy kind fixed at compile time (fast path) or -1 = runtime */
+template <typename T, class V, bool REC, int POL>
 __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_constant__ RolloutArgs<T> g) {
     const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
     const bool live = i < g.n;
@@ -515,22 +528,16 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
         const int A = action_width<T, V>(p);
         T ret = (T)0;
         int clipped = 0;
-        double t_cur = g.times[0];
         const int D = obs_width<T, V>(p);
         if (REC && g.rec_obs) {
             T row[MBT_MAX_OBS_DIM];
-            make_obs_row<T, V>(p, s, (T)t_cur, row);
+            make_obs_row<T, V>(p, s, g.clocks[0].t_cur, row);
             store_row<T>(g.rec_obs, i, D, row, false);
         }
         for (int k = 0; k < g.steps; ++k) {
-            const double t_next = g.times[k + 1];
-            StepClock<T> ck;
-            ck.t_next = (T)t_next;
-            ck.dt_r = (T)(t_next - t_cur);
-            ck.done = t_next >= g.terminal_time - g.step_size / 2;
-            clock_derive<T>(ck, p.phi, p.alpha, p.ep_len);
+            const StepClock<T> ck = g.clocks[k].ck; /* warp-uniform loads (one transaction), L1-resident */
             T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
-            policy_action<T>(g, k, (T)t_cur, s, a);
+            policy_action<T, POL>(g, A, k, g.clocks[k].t_cur, s, a);
             if (REC && g.rec_act) store_row<T>(g.rec_act, (long long)k * g.n + i, A, a, false);
 #pragma unroll
             for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j)
@@ -552,7 +559,6 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
                 make_obs_row<T, V>(p, s, ck.t_next, row);
                 store_row<T>(g.rec_obs, (long long)(k + 1) * g.n + i, D, row, false);
             }
-            t_cur = t_next;
         }
         store_traj<T, V>(p, g.st, i, s);
         if (g.returns) g.returns[i] = ret;
