@@ -280,7 +280,8 @@ int mbt_step(mbt_env *env, const void *actions, void *obs_out, void *rew_out, ui
 int mbt_get_state(mbt_env *env, void *state_out, int mem);
 int mbt_set_state(mbt_env *env, const void *state_in, int mem);
 
-/* Clock / counters of the handle (uniform over trajectories, TradingEnvironment.py:216-220). */
+/* Clock / counters of the handle (uniform over trajectories, TradingEnvironment.py:216-220).  After graph replays the
+ * clock is the one of the last EAGER call; the counters include the device-resident base (reading it synchronises). */
 int mbt_get_clock(mbt_env *env, double *time, int64_t *steps_this_episode, int64_t *steps_since_seed,
                   int64_t *episodes_since_seed);
 
@@ -291,6 +292,21 @@ int mbt_get_clock(mbt_env *env, double *time, int64_t *steps_this_episode, int64
 int mbt_checkpoint_size(mbt_env *env, size_t *bytes);
 int mbt_checkpoint_save(mbt_env *env, void *host_buf, size_t capacity);
 int mbt_checkpoint_load(mbt_env *env, const void *host_buf, size_t bytes);
+
+/*
+ * CUDA-graph replay of whole episodes (policy network kernels + mbt_reset / mbt_step launches captured from the caller's
+ * stream, e.g. with torch.cuda.graph).  The launches bake the handle's HOST counters (env-steps and resets since
+ * mbt_seed -- the Philox draw indices) into their arguments, so a replayed graph would redraw the same random numbers.
+ * Launches made while the handle's stream is capturing therefore also add a DEVICE-resident base to the baked counters,
+ * and mbt_fold_counters -- called last inside the captured region -- enqueues a one-thread kernel that moves the host
+ * counters into that base (base += host; host = 0).  Effective counter = host + base at every launch, captured or not:
+ * R replays of a captured episode are bit-identical to R episodes stepped eagerly from the same seed, and eager calls
+ * after the replays continue the same streams.  Requirements inside the captured region: MBT_MEM_DEVICE buffers only
+ * (host-buffer calls synchronise), the handle already on the capturing stream (mbt_set_stream before capture), a
+ * constant start time / initial-inventory mode, and the region must span whole episodes (the clock values are baked).
+ * (No reference counterpart: the reference has no device path.)
+ */
+int mbt_fold_counters(mbt_env *env);
 
 /* Trajectories whose inventory or cash was clipped since mbt_create (the reference prints the arrays
  * instead, TradingEnvironment.py:283-297). */

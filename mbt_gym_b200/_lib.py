@@ -18,7 +18,7 @@ ABI_SYMBOLS = [
     "mbt_seed", "mbt_reset", "mbt_step", "mbt_get_state", "mbt_set_state", "mbt_get_clock", "mbt_get_clip_count",
     "mbt_reward_eval", "mbt_rollout", "mbt_rollout_record", "mbt_get_launch_count", "mbt_enable_timing", "mbt_get_kernel_times",
     "mbt_host_alloc", "mbt_host_alloc_near", "mbt_host_free", "mbt_checkpoint_size", "mbt_checkpoint_save",
-    "mbt_checkpoint_load",
+    "mbt_checkpoint_load", "mbt_fold_counters",
 ]
 
 _lib = None
@@ -70,6 +70,7 @@ def load():
     L.mbt_checkpoint_size.argtypes = [vp, C.POINTER(C.c_size_t)]
     L.mbt_checkpoint_save.argtypes = [vp, vp, C.c_size_t]
     L.mbt_checkpoint_load.argtypes = [vp, vp, C.c_size_t]
+    L.mbt_fold_counters.argtypes = [vp]
     if L.mbt_abi_version() != _abi.MBT_ABI_VERSION:
         raise ImportError(f"libmbt_b200.so ABI {L.mbt_abi_version()} != binding ABI {_abi.MBT_ABI_VERSION}")
     _lib = L
@@ -164,6 +165,11 @@ class NativeEnv:
     def set_stream(self, stream_ptr):
         """cudaStream_t as an int (0 = legacy default stream, torch's default); None = the handle's own stream."""
         _check(load().mbt_set_stream(self._h, C.c_void_p(-1 if stream_ptr is None else int(stream_ptr))))
+
+    def fold_counters(self):
+        """Last call inside a CUDA-graph captured episode: moves the step / episode counters to the device so every
+        replay draws fresh random numbers (include/mbt_b200.h, mbt_fold_counters)."""
+        _check(load().mbt_fold_counters(self._h))
 
     # -- hot path
     def reset(self, obs_out=None, args=None, mem=_abi.MBT_MEM_HOST):

@@ -73,6 +73,11 @@ struct mbt_env {
     unsigned int *d_fill_ticket = nullptr;
     int fill_blocks = 1;
 
+    /* CUDA-graph replay: device-resident base of the (step, episode) counters; effective counter = host + base.
+     * `device_counters` turns on the first time a call is made while the stream is capturing, or by mbt_fold_counters */
+    unsigned long long *d_counter_base = nullptr;
+    bool device_counters = false;
+
     /* rollout scratch */
     void *d_clocks = nullptr; /* RolloutClock<T>[steps] */
     size_t clocks_cap = 0;    /* bytes */
@@ -234,6 +239,23 @@ static void par_memcpy(void *dst, const void *src, size_t bytes) {
 }
 
 /* ------------------------------------------------------------------ launchers */
+/* is the handle's stream being captured into a CUDA graph right now? */
+static bool stream_is_capturing(mbt_env *e) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(e->stream, &st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return st == cudaStreamCaptureStatusActive;
+}
+
+/* kernels read the device-resident counter base once the handle has been used under stream capture (or folded) */
+static const unsigned long long *counter_base_for_launch(mbt_env *e) {
+    if (!e->device_counters && stream_is_capturing(e)) e->device_counters = true;
+    return e->device_counters ? e->d_counter_base : nullptr;
+}
+
+
 /* MBT_PDL=0 disables programmatic dependent launch of consecutive step kernels (default: on) */
 static bool use_pdl() {
     static const bool on = [] {
@@ -300,6 +322,8 @@ static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<
     g.n_step = (unsigned long long)e->n_step;
     g.clipped = e->d_clipped;
     g.fill_thr = (const T *)e->d_fill_thr;
+    g.counter_base = counter_base_for_launch(e);
+    if (g.counter_base) allow_pdl = false; /* the base is written by a kernel: order behind it */
     const bool vec = rows_vector_aligned<E>(e, g.actions, g.obs);
     switch (variant_of(c)) {
 #define X(id, ...) case id: launch_step_v<T, E, __VA_ARGS__>(e, g, vec, allow_pdl); break;
@@ -322,7 +346,12 @@ static int launch_fill_batch(mbt_env *e, const StepParams<T> &p, const void *act
     g.ticket = e->d_fill_ticket;
     g.thr = (T *)e->d_fill_thr;
     const unsigned blocks = std::min<unsigned>(grid_for(e->N), (unsigned)e->fill_blocks);
-    mbt_fill_batch_kernel<T, E><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
+    /* rows of 2 or 4 elements whose base is aligned to a 2-element vector: one vector load per row */
+    const bool vec = (e->A == 2 || e->A == 4) && ((uintptr_t)actions % (2 * sizeof(E))) == 0;
+    if (vec)
+        mbt_fill_batch_kernel<T, E, true><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
+    else
+        mbt_fill_batch_kernel<T, E, false><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
     CU(cudaGetLastError());
     e->launches += 1;
     return MBT_OK;
@@ -441,6 +470,7 @@ static int do_reset_device(mbt_env *e, const mbt_reset_args *args, void *obs) {
     g.seed = e->seed;
     g.traj_offset = (unsigned long long)c.traj_offset;
     g.n_episode = (unsigned long long)e->n_episode;
+    g.counter_base = counter_base_for_launch(e);
     g.cash0 = (T)c.initial_cash;
     g.t0 = (T)t0;
     g.mid0 = (T)c.mid_initial;
@@ -468,6 +498,14 @@ static int do_reset_device(mbt_env *e, const mbt_reset_args *args, void *obs) {
 #define MBT_CALL_TE(e, fn, ...)                                                                          \
     ((e)->cfg.precision == MBT_F64 ? ((e)->io_esz == 4 ? fn<double, float>(__VA_ARGS__) : fn<double, double>(__VA_ARGS__)) \
                                    : fn<float, float>(__VA_ARGS__))
+
+/* the device-resident counter base, read back (synchronises the stream; not capturable) */
+static int read_counter_base(mbt_env *e, unsigned long long base[2]) {
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(base, e->d_counter_base, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MBT_OK;
+}
 
 /* ------------------------------------------------------------------ ABI */
 extern "C" {
@@ -519,6 +557,7 @@ int mbt_destroy(mbt_env *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->state_block);
     cudaFree(e->d_clipped);
+    cudaFree(e->d_counter_base);
     cudaFree(e->d_fill_partial);
     cudaFree(e->d_fill_thr);
     cudaFree(e->d_fill_ticket);
@@ -601,6 +640,8 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     for (int i = 0; i < 6; ++i) e->col[i] = (char *)e->state_block + col_bytes * i;
     CUB(cudaMalloc(&e->d_clipped, sizeof(unsigned long long)));
     CUB(cudaMemsetAsync(e->d_clipped, 0, sizeof(unsigned long long), e->stream));
+    CUB(cudaMalloc((void **)&e->d_counter_base, 2 * sizeof(unsigned long long)));
+    CUB(cudaMemsetAsync(e->d_counter_base, 0, 2 * sizeof(unsigned long long), e->stream));
     if (needs_fill_batch(*cfg)) {
         e->fill_blocks = std::max(1, e->sm_count * 8);
         CUB(cudaMalloc(&e->d_fill_partial, (size_t)e->fill_blocks * 2 * sizeof(double)));
@@ -637,6 +678,10 @@ int mbt_seed(mbt_env *e, uint64_t seed) {
     e->seed = seed;
     e->n_step = 0;
     e->n_episode = 0;
+    if (e->device_counters) { /* the device-resident base restarts too */
+        CU(cudaSetDevice(e->device));
+        CU(cudaMemsetAsync(e->d_counter_base, 0, 2 * sizeof(unsigned long long), e->stream));
+    }
     return MBT_OK;
 }
 
@@ -787,10 +832,15 @@ int mbt_set_state(mbt_env *e, const void *state_in, int mem) {
 
 int mbt_get_clock(mbt_env *e, double *time, int64_t *steps_this_episode, int64_t *steps_since_seed, int64_t *episodes_since_seed) {
     if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    unsigned long long base[2] = {0, 0};
+    if (e->device_counters && (steps_since_seed || episodes_since_seed)) {
+        int rc = read_counter_base(e, base);
+        if (rc) return rc;
+    }
     if (time) *time = e->t;
     if (steps_this_episode) *steps_this_episode = e->k;
-    if (steps_since_seed) *steps_since_seed = e->n_step;
-    if (episodes_since_seed) *episodes_since_seed = e->n_episode;
+    if (steps_since_seed) *steps_since_seed = e->n_step + (int64_t)base[0];
+    if (episodes_since_seed) *episodes_since_seed = e->n_episode + (int64_t)base[1];
     return MBT_OK;
 }
 
@@ -830,7 +880,12 @@ int mbt_checkpoint_save(mbt_env *e, void *host_buf, size_t capacity) {
     h.obs_dim = e->D;
     h.seed = e->seed;
     h.t = e->t; h.t0 = e->t0; h.q0_uniform = e->q0_uniform;
-    h.k = e->k; h.n_step = e->n_step; h.n_episode = e->n_episode;
+    unsigned long long base[2] = {0, 0};
+    if (e->device_counters) {
+        int rc = read_counter_base(e, base);
+        if (rc) return rc;
+    }
+    h.k = e->k; h.n_step = e->n_step + (int64_t)base[0]; h.n_episode = e->n_episode + (int64_t)base[1];
     h.q0_per_traj = e->q0_per_traj; h.started = e->started ? 1 : 0;
     h.state_bytes = sb;
     memcpy(host_buf, &h, sizeof h);
@@ -850,6 +905,7 @@ int mbt_checkpoint_load(mbt_env *e, const void *host_buf, size_t bytes) {
         return fail(MBT_E_INVALID_ARG, "checkpoint does not match this handle (num_trajectories / precision / model layout)");
     CU(cudaSetDevice(e->device));
     CU(cudaMemcpyAsync(e->state_block, (const char *)host_buf + sizeof h, h.state_bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemsetAsync(e->d_counter_base, 0, 2 * sizeof(unsigned long long), e->stream)); /* counters come back on the host side */
     CU(cudaStreamSynchronize(e->stream));
     e->seed = h.seed;
     e->t = h.t; e->t0 = h.t0; e->q0_uniform = h.q0_uniform;
@@ -950,6 +1006,7 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
     g.keys = mbt_philox_expand(e->seed);
     g.traj_offset = (unsigned long long)c.traj_offset;
     g.n_step0 = (unsigned long long)e->n_step;
+    g.counter_base = e->device_counters ? e->d_counter_base : nullptr;
     g.steps = steps;
     g.clocks = (const RolloutClock<T> *)e->d_clocks;
     g.pol_kind = pol->kind;
@@ -1114,6 +1171,18 @@ int mbt_rollout_record(mbt_env *e, const mbt_policy *policy, mbt_summary *summar
     }
     if (tmp) cudaFree(tmp);
     return rc;
+}
+
+int mbt_fold_counters(mbt_env *e) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    CU(cudaSetDevice(e->device));
+    e->device_counters = true;
+    mbt_fold_counters_kernel<<<1, 1, 0, e->stream>>>(e->d_counter_base, (unsigned long long)e->n_step, (unsigned long long)e->n_episode);
+    CU(cudaGetLastError());
+    e->launches += 1;
+    e->n_step = 0;
+    e->n_episode = 0;
+    return MBT_OK;
 }
 
 int mbt_get_launch_count(mbt_env *e, int64_t *launches) {

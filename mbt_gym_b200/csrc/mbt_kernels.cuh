@@ -50,6 +50,9 @@ struct StepArgs {
     unsigned long long traj_offset, n_step;
     unsigned long long *clipped;
     const T *fill_thr; /* batch-reduced fill models: the step's two thresholds, written by mbt_fill_batch_kernel */
+    /* CUDA-graph replay (mbt_fold_counters): NULL, or the device-resident base {steps, episodes} that is added to the
+     * counters baked into this launch -- a captured episode replays with fresh random numbers every time */
+    const unsigned long long *counter_base;
 };
 
 /* the specialised variants know the row widths at compile time */
@@ -207,7 +210,12 @@ template <typename T, typename E, class V, bool VEC>
 __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, bool full_warp, E *warp_smem) {
     const StepParams<T> &p = g.p;
     /* state-independent prologue: the step's 128 random bits depend only on (seed, trajectory id, step index) */
-    const mbt_u32x4 r = mbt_draw_keyed(g.keys, g.traj_offset + (unsigned long long)i, g.n_step, MBT_STREAM_STEP);
+    unsigned long long n_step = g.n_step;
+    if (g.counter_base) { /* warp-uniform; such launches are never programmatic (the base is written by a kernel) */
+        pdl_wait();
+        n_step += g.counter_base[0];
+    }
+    const mbt_u32x4 r = mbt_draw_keyed(g.keys, g.traj_offset + (unsigned long long)i, n_step, MBT_STREAM_STEP);
     pdl_wait(); /* everything below reads what the previous kernel (previous step, or the caller's policy) wrote */
     const int A = action_width<T, V>(p);
     E a_io[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
@@ -298,16 +306,48 @@ __device__ __forceinline__ T warp_nanmax(T v) {
     return v;
 }
 
-template <typename T, typename E>
+/* the two depths of row i: one 2-element vector load when the rows are aligned for it (A = 2 or 4), else two scalars */
+template <typename E, bool VEC>
+__device__ __forceinline__ void load_depths(const E *__restrict__ actions, long long i, int A, E &d0, E &d1) {
+    const E *row = actions + i * A;
+    if constexpr (VEC) {
+        if constexpr (sizeof(E) == 4) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(row));
+            d0 = v.x; d1 = v.y;
+        } else {
+            const double2 v = __ldg(reinterpret_cast<const double2 *>(row));
+            d0 = v.x; d1 = v.y;
+        }
+    } else {
+        d0 = __ldg(row + 0);
+        d1 = __ldg(row + 1);
+    }
+}
+
+template <typename T, typename E, bool VEC>
 __global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_constant__ FillBatchArgs<T, E> g) {
     const StepParams<T> &p = g.p;
     const int A = p.action_dim;
     const T neg_inf = -(T)INFINITY; /* identity of the NaN-propagating max */
     T m0 = neg_inf, m1 = neg_inf;
-    for (long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x; i < g.n; i += (long long)gridDim.x * MBT_BLOCK) {
-        const E *row = g.actions + i * A; /* depths = action[:, 0:2]   ModelDynamics.py:50-51,128-130 */
-        m0 = nanmax<T>(m0, denorm_action<T, VariantGeneric>(p, (T)__ldg(row + 0), 0));
-        m1 = nanmax<T>(m1, denorm_action<T, VariantGeneric>(p, (T)__ldg(row + 1), 1));
+    /* four independent row loads in flight per thread and iteration (the reduction is latency-bound otherwise:
+     * 15.4 us for 16.8 MB with one row per iteration, profiles/r1b_targets_f64.ncu_summary.csv) */
+    constexpr int UNROLL = 4;
+    const long long nth = (long long)gridDim.x * MBT_BLOCK;
+    for (long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x; i < g.n; i += UNROLL * nth) {
+        E d0[UNROLL], d1[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) { /* depths = action[:, 0:2]   ModelDynamics.py:50-51,128-130 */
+            const long long r = i + u * nth;
+            d0[u] = d1[u] = (E)0;
+            if (r < g.n) load_depths<E, VEC>(g.actions, r, A, d0[u], d1[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            if (i + u * nth < g.n) {
+                m0 = nanmax<T>(m0, denorm_action<T, VariantGeneric>(p, (T)d0[u], 0));
+                m1 = nanmax<T>(m1, denorm_action<T, VariantGeneric>(p, (T)d1[u], 1));
+            }
     }
     __shared__ T sm[MBT_BLOCK / 32][2];
     __shared__ bool is_last;
@@ -356,6 +396,7 @@ struct ResetArgs {
     E *obs;
     long long n;
     unsigned long long seed, traj_offset, n_episode;
+    const unsigned long long *counter_base; /* see StepArgs */
     T cash0, t0, mid0, lam0[2], imp0;
     int q0_mode;
     T q0_const;
@@ -371,7 +412,8 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_reset_kernel(const __grid_const
     Traj<T> s;
     s.cash = g.cash0;
     if (g.q0_mode == MBT_Q0_UNIFORM_INT) { /* rng.integers(lo, hi)   TradingEnvironment.py:271-272 */
-        const mbt_u32x4 r = mbt_draw(g.seed, g.traj_offset + (unsigned long long)i, g.n_episode, MBT_STREAM_RESET);
+        const unsigned long long n_episode = g.n_episode + (g.counter_base ? g.counter_base[1] : 0ull);
+        const mbt_u32x4 r = mbt_draw(g.seed, g.traj_offset + (unsigned long long)i, n_episode, MBT_STREAM_RESET);
         s.inv = (T)(g.q0_lo + (long long)(((unsigned long long)r.x * g.q0_span) >> 32));
     } else {
         s.inv = g.q0_const;
@@ -396,6 +438,13 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_reset_kernel(const __grid_const
             if (k < d) row_io[k] = (E)row[k];
         store_row<E>(g.obs, i, d, row_io, false);
     }
+}
+
+/* ------------------------------------------------------------------ counters for CUDA-graph replay */
+/* base[0] += steps, base[1] += episodes: what mbt_fold_counters enqueues (one thread; capturable) */
+__global__ void mbt_fold_counters_kernel(unsigned long long *base, unsigned long long steps, unsigned long long episodes) {
+    base[0] += steps;
+    base[1] += episodes;
 }
 
 /* ------------------------------------------------------------------ state gather / scatter */
@@ -461,6 +510,7 @@ struct RolloutArgs {
     long long n;
     mbt_philox_keys keys;
     unsigned long long traj_offset, n_step0;
+    const unsigned long long *counter_base; /* see StepArgs */
     int steps;            /* env-steps to run (until the episode ends) */
     /* device, `steps` entries: the uniform clock of every step, formed on the host exactly like the step kernel's
      * (mbt_make_clock on the host-accumulated t += dt) -- the loop loads it instead of redoing the arithmetic per thread */
@@ -529,6 +579,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
         T ret = (T)0;
         int clipped = 0;
         const int D = obs_width<T, V>(p);
+        const unsigned long long n_step0 = g.n_step0 + (g.counter_base ? g.counter_base[0] : 0ull);
         if (REC && g.rec_obs) {
             T row[MBT_MAX_OBS_DIM];
             make_obs_row<T, V>(p, s, g.clocks[0].t_cur, row);
@@ -545,7 +596,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
                     acc[4] += (double)a[j];
                     a[j] = denorm_action<T, V>(p, a[j], j);
                 }
-            const mbt_u32x4 r = mbt_draw_keyed(g.keys, g.traj_offset + (unsigned long long)i, g.n_step0 + (unsigned long long)k, MBT_STREAM_STEP);
+            const mbt_u32x4 r = mbt_draw_keyed(g.keys, g.traj_offset + (unsigned long long)i, n_step0 + (unsigned long long)k, MBT_STREAM_STEP);
             /* batch-reduced fill models: only policies whose action is uniform over the batch reach here (do_rollout),
              * so the deepest quote of the batch is this trajectory's own */
             T fill_thr[2] = {(T)0, (T)0};

@@ -156,6 +156,38 @@ class TradingEnvironment(_EnvBase):
             self.reward_function.initial_inventory = None if args.q0_mode == _abi.MBT_Q0_UNIFORM_INT else args.q0_const
         return out
 
+    def reset_device(self, out=None):
+        """`reset()` that stays on the device: the first observation as a CUDA torch tensor (written into `out` when
+        given), enqueued on torch's current stream -- no host round-trip, so it can be captured into a CUDA graph
+        together with `step(cuda_tensor)` calls (see `fold_counters`)."""
+        import torch
+
+        native = self._ensure_native()
+        args = _abi.mbt_reset_args()
+        args.start_time = float(self._get_start_time())
+        self._fill_initial_inventory(args)
+        tdt = torch.float64 if self.io_dtype == np.float64 else torch.float32
+        dev = torch.device("cuda", self.device)
+        if out is None:
+            out = torch.empty((self.num_trajectories, native.Dout), dtype=tdt, device=dev)
+        elif out.dtype != tdt or not out.is_contiguous() or tuple(out.shape) != (self.num_trajectories, native.Dout):
+            raise ValueError(f"out must be a contiguous {tdt} tensor of shape ({self.num_trajectories}, {native.Dout})")
+        native.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        native.reset(out, args, mem=_abi.MBT_MEM_DEVICE)
+        self._started = True
+        if getattr(self.reward_function, "terminal_time", None) is not None:
+            self.reward_function.episode_length = self.reward_function.terminal_time - args.start_time
+            self.reward_function.initial_inventory = None if args.q0_mode == _abi.MBT_Q0_UNIFORM_INT else args.q0_const
+        return out
+
+    def fold_counters(self):
+        """Call LAST inside a `torch.cuda.graph` capture that spans whole episodes (`reset_device`, then policy and
+        `step(cuda_tensor)` until done): the random-number counters move to the device, so every `graph.replay()` is a
+        NEW episode -- bit-identical to stepping the same episodes eagerly -- instead of a repeat of the captured one.
+        Bind the environment to the capture stream first (a warm-up `reset_device()` under `torch.cuda.stream(s)`) and
+        capture with `torch.cuda.graph(g, stream=s)`.  C ABI: `mbt_fold_counters` (include/mbt_b200.h)."""
+        self._ensure_native().fold_counters()
+
     def step(self, action):
         """One env-step for all trajectories  (TradingEnvironment.py:103-110).
         action (N, A) -> observations (N, D), rewards (N,), dones (N,) bool, infos."""

@@ -314,3 +314,73 @@ def test_float32_io_over_float64_arithmetic_is_the_rounded_float64_result(name):
         assert_same(r32, r64.astype(np.float32), what=f"{name} rew {k}")
     assert_same(e32.state, e64.state, what=f"{name} state stays float64 and identical")
     e32.close(); e64.close()
+
+
+def test_cuda_graph_replay_of_captured_episodes_equals_eager_episodes():
+    """Whole episodes (reset + a torch policy + step, all on the device) captured into ONE CUDA graph: thanks to the
+    device-resident counter base (mbt_fold_counters) every replay is a new episode with fresh random numbers, and R
+    replays are bit-identical to R episodes stepped eagerly from the same seed; eager calls afterwards continue the
+    same random streams."""
+    import torch
+
+    # random initial inventories: the reset draws random numbers too
+    spec = dict(golden_specs()["cjmm"], N=5000, n_steps=12, seed=99, start_time=0.0)
+    sign = torch.tensor([[1.0, -1.0]], dtype=torch.float64, device="cuda")
+
+    def policy(obs):  # any torch function of the observation; (N, 2) depths
+        return 0.6 + 0.2 * torch.tanh(obs[:, 1:2]) * sign
+
+    def eager_episode(env):
+        obs = env.reset_device()
+        ret = torch.zeros(spec["N"], dtype=torch.float64, device="cuda")
+        for _ in range(spec["n_steps"]):
+            obs, rew, dones, _ = env.step(policy(obs))
+            ret = ret + rew
+        assert bool(dones[0])
+        torch.cuda.synchronize()
+        return obs.cpu().numpy(), ret.cpu().numpy()
+
+    eager_env = build_facade_env(spec)
+    want = [eager_episode(eager_env) for _ in range(5)]
+    eager_env.close()
+    assert not np.array_equal(want[0][1], want[1][1])
+
+    env = build_facade_env(spec)
+    s = torch.cuda.Stream()
+    obs_t = torch.empty((spec["N"], 4), dtype=torch.float64, device="cuda")
+    ret_t = torch.zeros(spec["N"], dtype=torch.float64, device="cuda")
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):  # binds the handle to the capture stream and warms torch up; consumes no random numbers
+        env._ensure_native().set_stream(s.cuda_stream)
+        policy(obs_t.zero_())
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        env.reset_device(out=obs_t)
+        ret_t.zero_()
+        for _ in range(spec["n_steps"]):
+            o, rew, _d, _ = env.step(policy(obs_t))
+            obs_t.copy_(o)
+            ret_t += rew
+        env.fold_counters()
+    for r in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        assert_same(obs_t.cpu().numpy(), want[r][0], what=f"replay {r}: final observations")
+        assert_same(ret_t.cpu().numpy(), want[r][1], what=f"replay {r}: episode returns")
+    assert env._native.clock()["n_step"] == 3 * spec["n_steps"] and env._native.clock()["n_episode"] == 3
+    # eager continuation after the replays: episode 4 of the same streams; checkpoint / resume carries the counters
+    blob = env.save_checkpoint()
+    with torch.cuda.stream(s):
+        got = eager_episode(env)
+    assert_same(got[0], want[3][0], what="eager episode after replays: observations")
+    assert_same(got[1], want[3][1], what="eager episode after replays: returns")
+    env.load_checkpoint(blob)
+    with torch.cuda.stream(s):
+        got = eager_episode(env)
+    assert_same(got[1], want[3][1], what="episode after checkpoint restore")
+    with torch.cuda.stream(s):
+        got = eager_episode(env)
+    assert_same(got[1], want[4][1], what="next episode after checkpoint restore")
+    env.close()
