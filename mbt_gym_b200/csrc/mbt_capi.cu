@@ -68,7 +68,7 @@ struct mbt_env {
     cudaStream_t copy_in = nullptr, copy_out = nullptr; /* H2D / D2H copy engines for the pipelined host path */
     cudaEvent_t ev_in[MBT_PIPE_CHUNKS] = {}, ev_k[MBT_PIPE_CHUNKS] = {};
 
-    /* batch reduction in front of the step (Triangular / Power fill functions): partial maxima, ticket, thresholds */
+    /* batch reduction in front of the step (Triangular / Power fill functions): running maxima (keys), ticket, thresholds */
     void *d_fill_partial = nullptr, *d_fill_thr = nullptr;
     unsigned int *d_fill_ticket = nullptr;
     int fill_blocks = 1;
@@ -115,6 +115,13 @@ static DevState<T> dev_state(mbt_env *e) {
 }
 
 static inline unsigned grid_for(long long n) { return (unsigned)((n + MBT_BLOCK - 1) / MBT_BLOCK); }
+
+/* blocks per SM of the batch reduction (env MBT_FILL_BLOCKS_PER_SM overrides for tuning).  Measured at N = 2^20, f64, cold cache (ncu): 1 / 2 / 4 / 8 blocks per SM -> 12.3 / 10.9 / 10.3 / 12.9 us */
+static int fill_blocks_per_sm() {
+    const char *v = getenv("MBT_FILL_BLOCKS_PER_SM");
+    int k = v ? atoi(v) : 4;
+    return k < 1 ? 1 : (k > 8 ? 8 : k);
+}
 
 /* does a step of this config start with the batch reduction of the quoted depths? */
 static inline bool needs_fill_batch(const mbt_config &c) {
@@ -342,7 +349,7 @@ static int launch_fill_batch(mbt_env *e, const StepParams<T> &p, const void *act
     g.p = p;
     g.actions = (const E *)actions;
     g.n = e->N;
-    g.partial = (T *)e->d_fill_partial;
+    g.cells = (unsigned long long *)e->d_fill_partial;
     g.ticket = e->d_fill_ticket;
     g.thr = (T *)e->d_fill_thr;
     const unsigned blocks = std::min<unsigned>(grid_for(e->N), (unsigned)e->fill_blocks);
@@ -643,8 +650,9 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     CUB(cudaMalloc((void **)&e->d_counter_base, 2 * sizeof(unsigned long long)));
     CUB(cudaMemsetAsync(e->d_counter_base, 0, 2 * sizeof(unsigned long long), e->stream));
     if (needs_fill_batch(*cfg)) {
-        e->fill_blocks = std::max(1, e->sm_count * 8);
-        CUB(cudaMalloc(&e->d_fill_partial, (size_t)e->fill_blocks * 2 * sizeof(double)));
+        e->fill_blocks = std::max(1, e->sm_count * fill_blocks_per_sm()); /* every block ends in 3 same-address atomics */
+        CUB(cudaMalloc(&e->d_fill_partial, 2 * sizeof(unsigned long long)));
+        CUB(cudaMemsetAsync(e->d_fill_partial, 0, 2 * sizeof(unsigned long long), e->stream));
         CUB(cudaMalloc(&e->d_fill_thr, 2 * sizeof(double)));
         CUB(cudaMalloc((void **)&e->d_fill_ticket, sizeof(unsigned int)));
         CUB(cudaMemsetAsync(e->d_fill_thr, 0, 2 * sizeof(double), e->stream));

@@ -284,9 +284,10 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_consta
 /*
  * Triangular / Power fill functions (fill_probability_models.py:82,113): the reference's `np.max(depths, 0)` reduces
  * over the trajectory axis, so a step's fill probability depends on the deepest quote of the whole batch.  This kernel
- * is that reduction: grid-stride NaN-propagating max of the (de-normalised) depth columns, warp shuffle -> shared ->
- * one partial per block, and the LAST block to finish (ticket counter) folds the partials and writes the two
- * thresholds the step kernel compares its fill uniforms with.  max is order-independent, so the result is
+ * is that reduction: NaN-propagating max of the (de-normalised) depth columns, eight independent row loads in flight per
+ * thread, warp shuffle -> shared -> ONE 64-bit atomicMax per block and side on an order-preserving integer key of the
+ * value (NaN = the largest key, like np.max), and the LAST block to finish (ticket counter) decodes the two maxima and
+ * writes the thresholds the step kernel compares its fill uniforms with.  max is order-independent, so the result is
  * deterministic and equal to numpy's.  One launch; the step kernel that follows is ordered after it by the stream.
  */
 template <typename T, typename E>
@@ -294,10 +295,21 @@ struct FillBatchArgs {
     StepParams<T> p;
     const E *actions; /* (N, A) */
     long long n;
-    T *partial;           /* (gridDim.x, 2) scratch */
-    unsigned int *ticket; /* zero on entry, zero again on exit */
-    T *thr;               /* out: p_bid * 2^24, p_ask * 2^24 */
+    unsigned long long *cells; /* [2] running maxima as keys; zero on entry, zero again on exit */
+    unsigned int *ticket;      /* zero on entry, zero again on exit */
+    T *thr;                    /* out: p_bid * 2^24, p_ask * 2^24 */
 };
+
+/* order-preserving key of a real (float widens exactly): key(a) < key(b) <=> a < b; every NaN -> the largest key */
+__device__ __forceinline__ unsigned long long real_to_key(double x) {
+    if (x != x) return ~0ull;
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_to_real(unsigned long long k) {
+    if (k == ~0ull) return __longlong_as_double(0x7ff8000000000000ll); /* NaN */
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
 
 template <typename T>
 __device__ __forceinline__ T warp_nanmax(T v) {
@@ -330,9 +342,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_
     const int A = p.action_dim;
     const T neg_inf = -(T)INFINITY; /* identity of the NaN-propagating max */
     T m0 = neg_inf, m1 = neg_inf;
-    /* four independent row loads in flight per thread and iteration (the reduction is latency-bound otherwise:
-     * 15.4 us for 16.8 MB with one row per iteration, profiles/r1b_targets_f64.ncu_summary.csv) */
-    constexpr int UNROLL = 4;
+    constexpr int UNROLL = 8; /* independent row loads in flight per thread: few blocks (few atomics), deep loads */
     const long long nth = (long long)gridDim.x * MBT_BLOCK;
     for (long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x; i < g.n; i += UNROLL * nth) {
         E d0[UNROLL], d1[UNROLL];
@@ -350,42 +360,27 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_
             }
     }
     __shared__ T sm[MBT_BLOCK / 32][2];
-    __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     m0 = warp_nanmax<T>(m0);
     m1 = warp_nanmax<T>(m1);
     if (lane == 0) { sm[warp][0] = m0; sm[warp][1] = m1; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        T b0 = sm[0][0], b1 = sm[0][1];
-        for (int w = 1; w < MBT_BLOCK / 32; ++w) { b0 = nanmax<T>(b0, sm[w][0]); b1 = nanmax<T>(b1, sm[w][1]); }
-        g.partial[2 * blockIdx.x + 0] = b0;
-        g.partial[2 * blockIdx.x + 1] = b1;
-        __threadfence(); /* the partial is visible before the ticket is taken */
-        is_last = atomicAdd(g.ticket, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!is_last) return;
+    if (threadIdx.x != 0) return;
+    T b0 = sm[0][0], b1 = sm[0][1];
+    for (int w = 1; w < MBT_BLOCK / 32; ++w) { b0 = nanmax<T>(b0, sm[w][0]); b1 = nanmax<T>(b1, sm[w][1]); }
+    atomicMax(g.cells + 0, real_to_key((double)b0));
+    atomicMax(g.cells + 1, real_to_key((double)b1));
+    __threadfence(); /* this block's maxima are visible before its ticket is taken */
+    if (atomicAdd(g.ticket, 1u) != gridDim.x - 1) return;
+    /* last block: every other block's atomicMax happened before its ticket; read and clear for the next step */
     __threadfence();
-    m0 = neg_inf; m1 = neg_inf;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += MBT_BLOCK) {
-        m0 = nanmax<T>(m0, __ldcg(g.partial + 2 * b + 0));
-        m1 = nanmax<T>(m1, __ldcg(g.partial + 2 * b + 1));
-    }
-    m0 = warp_nanmax<T>(m0);
-    m1 = warp_nanmax<T>(m1);
-    __syncthreads(); /* sm[] is reused */
-    if (lane == 0) { sm[warp][0] = m0; sm[warp][1] = m1; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        T b0 = sm[0][0], b1 = sm[0][1];
-        for (int w = 1; w < MBT_BLOCK / 32; ++w) { b0 = nanmax<T>(b0, sm[w][0]); b1 = nanmax<T>(b1, sm[w][1]); }
-        T thr[2];
-        fill_batch_thresholds<T>(p, b0, b1, thr);
-        g.thr[0] = thr[0];
-        g.thr[1] = thr[1];
-        *g.ticket = 0u; /* ready for the next step */
-    }
+    const T a0 = (T)key_to_real(atomicExch(g.cells + 0, 0ull));
+    const T a1 = (T)key_to_real(atomicExch(g.cells + 1, 0ull));
+    T thr[2];
+    fill_batch_thresholds<T>(p, a0, a1, thr);
+    g.thr[0] = thr[0];
+    g.thr[1] = thr[1];
+    *g.ticket = 0u;
 }
 
 /* ------------------------------------------------------------------ reset */
