@@ -295,7 +295,7 @@ def test_fused_column_select_equals_host_side_wrapper(name, cols, precision):
     fused.env.close(); plain.env.close()
 
 
-@pytest.mark.parametrize("name", ["as_pnl", "hawkes_normalised", "oe_ou_cjoe", "cjmm"])
+@pytest.mark.parametrize("name", ["as_pnl", "hawkes_normalised", "oe_ou_cjoe", "cjmm", "power_fill", "triangular_fill"])
 def test_float32_io_over_float64_arithmetic_is_the_rounded_float64_result(name):
     """io_dtype=float32: actions arrive as float32, the dynamics run in float64 exactly as before, observations and
     rewards leave rounded to float32 -- so they must equal np.float32(<float64 run fed the same float32 actions>)."""
