@@ -127,6 +127,7 @@ class RunningInventoryPenalty(_InventoryAversion):
 
 
 CjCriterion = RunningInventoryPenalty  # the reference's alias (:141-143)
+InventoryAdjustedPnL = RunningInventoryPenalty  # the name BASELINE.json's north_star uses for the same criterion
 
 
 class ExponentialUtility(RewardFunction):
