@@ -4,6 +4,10 @@ SB3 is optional here: when it is importable the class derives from its `VecEnv`;
 with the same methods, which is what the conformance tests exercise.  Difference from the reference: the
 `terminal_observation` entries are not produced by an O(N) Python loop per episode (:31-35) -- `infos` is a lazy
 sequence whose items materialise `{"terminal_observation": obs[i]}` on access.
+
+Device mode: when `step_async` receives a CUDA torch tensor, observations and rewards stay CUDA tensors, the auto-reset
+uses `reset_device()`, and the monitor accumulates the episode returns on the device -- nothing crosses PCIe per step
+(`reset(device=True)` starts an episode that way).
 """
 import numpy as np
 
@@ -61,15 +65,22 @@ class StableBaselinesTradingEnvironment(_VecEnvBase):
             self.num_envs = self.env.num_trajectories
             self.observation_space, self.action_space = self.env.observation_space, self.env.action_space
 
-    def reset(self):
-        self._begin_episode()
-        return self.env.reset()
+    def reset(self, device=False):
+        """First observation of a new episode: a NumPy array, or with `device=True` a CUDA tensor (no host round-trip)."""
+        self._begin_episode(on_device=device)
+        return self.env.reset_device() if device else self.env.reset()
 
-    def _begin_episode(self):
+    def _begin_episode(self, on_device=False):
         if self.monitor:
             import time
 
-            self.episode_returns = np.zeros((self.env.num_trajectories,), dtype=np.float64)
+            if on_device:
+                import torch
+
+                self.episode_returns = torch.zeros((self.env.num_trajectories,), dtype=torch.float64,
+                                                   device=torch.device("cuda", self.env.device))
+            else:
+                self.episode_returns = np.zeros((self.env.num_trajectories,), dtype=np.float64)
             self.episode_length = 0
             self._t_start = time.time()
 
@@ -78,10 +89,11 @@ class StableBaselinesTradingEnvironment(_VecEnvBase):
 
     def step_wait(self):
         obs, rewards, dones, infos = self.env.step(self.actions)
+        on_device = bool(getattr(rewards, "is_cuda", False))  # CUDA tensors in -> CUDA tensors out
         if self.monitor:
-            if self.episode_returns is None:
-                self._begin_episode()
-            self.episode_returns += np.asarray(rewards)
+            if self.episode_returns is None or bool(getattr(self.episode_returns, "is_cuda", False)) != on_device:
+                self._begin_episode(on_device)
+            self.episode_returns += rewards if on_device else np.asarray(rewards)
             self.episode_length += 1
         if dones.min():
             episode = None
@@ -90,12 +102,17 @@ class StableBaselinesTradingEnvironment(_VecEnvBase):
 
                 r = self.episode_returns
                 episode = (r, self.episode_length, round(time.time() - self._t_start, 6))
-                self.last_episode_statistics = {"mean_return": float(r.mean()), "std_return": float(r.std()),
-                                                "length": self.episode_length, "num_episodes": int(r.shape[0])}
+                r_host = r.cpu().numpy() if on_device else r  # one (N,) copy per episode, for the summary only
+                self.last_episode_statistics = {"mean_return": float(r_host.mean()), "std_return": float(r_host.std()),
+                                                "length": self.episode_length, "num_episodes": int(r_host.shape[0])}
             if self.store_terminal_observation_info or episode is not None:
-                infos = _TerminalInfos(np.array(obs, copy=True) if self.store_terminal_observation_info else None, episode)
-            self._begin_episode()
-            obs = self.env.reset()  # SB3 convention: auto-reset, return the first observation of the new episode
+                terminal = None
+                if self.store_terminal_observation_info:
+                    terminal = obs.clone() if on_device else np.array(obs, copy=True)
+                infos = _TerminalInfos(terminal, episode)
+            self._begin_episode(on_device)
+            # SB3 convention: auto-reset, return the first observation of the new episode
+            obs = self.env.reset_device() if on_device else self.env.reset()
         return obs, rewards, dones, infos
 
     def step(self, actions):

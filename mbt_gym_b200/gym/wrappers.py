@@ -41,6 +41,10 @@ class ReduceStateSizeWrapper(_Wrapper):
     def reset(self):
         return self.observation(self.env.reset())
 
+    def reset_device(self):
+        """First observation as a CUDA tensor (see `TradingEnvironment.reset_device`), columns selected."""
+        return self.observation(self.env.reset_device())
+
     def step(self, action):
         obs, reward, done, info = self.env.step(action)
         return self.observation(obs), reward, done, info

@@ -147,6 +147,38 @@ def test_vecenv_adapter_autoreset_and_lazy_terminal_observation():
     env.close()
 
 
+def test_vecenv_adapter_device_mode_equals_host_mode():
+    """CUDA action tensors through the VecEnv adapter: observations / rewards stay on the device, the auto-reset and the
+    monitor too, and every value equals the NumPy-mode run of the same seed."""
+    import torch
+
+    from mbt_gym_b200.gym.StableBaselinesTradingEnvironment import StableBaselinesTradingEnvironment
+
+    spec = dict(SPECS["cjmm"], N=300, n_steps=6, start_time=0.0)
+    host = StableBaselinesTradingEnvironment(build_facade_env(spec), monitor=True)
+    dev = StableBaselinesTradingEnvironment(build_facade_env(spec), monitor=True)
+    o_h, o_d = host.reset(), dev.reset(device=True)
+    assert o_d.is_cuda
+    assert_same(o_d.cpu().numpy(), o_h, what="first observation")
+    rng = np.random.default_rng(3)
+    for k in range(15):  # two and a half episodes: two auto-resets
+        a = rng.uniform(0.1, 1.5, size=(300, 2))
+        o_h, r_h, d_h, i_h = host.step(a)
+        o_d, r_d, d_d, i_d = dev.step(torch.from_numpy(a).cuda())
+        assert o_d.is_cuda and r_d.is_cuda
+        assert_same(o_d.cpu().numpy(), o_h, what=f"obs {k}")
+        assert_same(r_d.cpu().numpy(), r_h, what=f"rew {k}")
+        assert np.array_equal(d_h, d_d)
+        if d_h.all():
+            assert_same(i_d[5]["terminal_observation"].cpu().numpy(), i_h[5]["terminal_observation"], what="terminal obs")
+            assert i_d[5]["episode"]["r"] == i_h[5]["episode"]["r"] and i_d[5]["episode"]["l"] == 6
+            assert dev.last_episode_statistics["mean_return"] == pytest.approx(host.last_episode_statistics["mean_return"], rel=1e-12)
+            assert dev.last_episode_statistics["std_return"] == pytest.approx(host.last_episode_statistics["std_return"], rel=1e-12)
+    assert dev.episode_returns.is_cuda
+    assert_same(dev.episode_returns.cpu().numpy(), host.episode_returns, what="running returns of the open episode")
+    host.env.close(); dev.env.close()
+
+
 def test_reward_calculate_runs_on_device_and_matches_reference_unit_tests():
     """mbt_gym/rewards/tests/testRewardFunctions.py restated through RewardFunction.calculate (mbt_reward_eval)."""
     from mbt_gym_b200.rewards.RewardFunctions import CjMmCriterion, PnL, RunningInventoryPenalty
