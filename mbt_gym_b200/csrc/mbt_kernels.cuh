@@ -60,8 +60,8 @@ template <typename T, class V>
 __device__ __forceinline__ int action_width(const StepParams<T> &p) { return V::A ? V::A : p.action_dim; }
 template <typename T, class V>
 __device__ __forceinline__ int obs_width(const StepParams<T> &p) {
-    /* the fully specialised variants (V::norm == 0) never select columns: variant_of() routes obs_select to the others */
-    return (V::D && V::norm == 0) ? V::D : p.obs_out_dim;
+    /* the fully specialised variants (V::norm >= 0) never select columns: variant_of() routes obs_select to the others */
+    return (V::D && V::norm >= 0) ? V::D : p.obs_out_dim;
 }
 
 /* ------------------------------------------------------------------ row access helpers */
@@ -166,7 +166,7 @@ __device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T
         row[d] = norm_obs<T, V>(p, s.x1, d); ++d;
     }
     if (imp_has_state(imp)) { row[d] = norm_obs<T, V>(p, s.x0, d); ++d; }
-    if (V::norm != 0 && p.obs_select) { /* keep the selected columns, in order (gym/wrappers.py:30-38) */
+    if (V::norm < 0 && p.obs_select) { /* keep the selected columns, in order (gym/wrappers.py:30-38) */
         int j = 0;
 #pragma unroll
         for (int k = 0; k < MBT_MAX_OBS_DIM; ++k)
@@ -268,7 +268,7 @@ __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, b
 template <typename T, typename E, class V, bool VEC>
 __global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_constant__ StepArgs<T, E> g) {
     /* staging for non-power-of-two observation rows: one 32 x MBT_MAX_OBS_DIM tile per warp (unused when D == 4) */
-    constexpr bool FIXED_W = V::D && V::norm == 0;          /* emitted row width known at compile time */
+    constexpr bool FIXED_W = V::D && V::norm >= 0;          /* emitted row width known at compile time */
     constexpr int SW = FIXED_W ? V::D : MBT_MAX_OBS_DIM;     /* staged row width */
     __shared__ E smem[(FIXED_W && V::D == 4) ? 1 : (MBT_BLOCK / 32) * 32 * SW];
     const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;

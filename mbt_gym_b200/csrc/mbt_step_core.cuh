@@ -23,7 +23,8 @@
 #include "../../include/mbt_math.h"
 #include "../../include/mbt_philox.h"
 
-/* NORM: 0 = no action/observation/reward normalisation compiled in; -1 = decided by runtime flags. */
+/* NORM: 0 = no action/observation/reward normalisation compiled in; 1 = action AND observation normalisation compiled in
+ * (the reference's default constructor, what SB3 sees), no reward scaling, all columns emitted; -1 = runtime flags. */
 template <int DYN, int MID, int ARR, int IMP, int REW, int NORM>
 struct Variant {
     static constexpr int dyn = DYN, mid = MID, arr = ARR, imp = IMP, rew = REW, norm = NORM;
@@ -271,7 +272,7 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
 
     /* rewards = reward_function.calculate(current_state, action, next_state, dones[0])   :108 */
     T rwd = reward_one<T, V>(p, ck, c0, q_cur, S, s, a, q_init);
-    if (V::norm == 0) return rwd;
+    if (V::norm >= 0) return rwd;
     return p.normalise_rewards ? p.reward_scaling * rwd : rwd; /* :128-129 */
 }
 
@@ -279,12 +280,14 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
 template <typename T, class V>
 MBT_HD T denorm_action(const StepParams<T> &p, T x, int j) {
     if (V::norm == 0) return x;
+    if (V::norm == 1) return (x + (T)1) * p.act_grad[j] + p.act_low[j];
     return p.normalise_action ? (x + (T)1) * p.act_grad[j] + p.act_low[j] : x;
 }
 /* normalise_observation                                                 TradingEnvironment.py:112-118 */
 template <typename T, class V>
 MBT_HD T norm_obs(const StepParams<T> &p, T x, int d) {
     if (V::norm == 0) return x;
+    if (V::norm == 1) return (x - p.obs_low[d]) / p.obs_grad[d] - (T)1;
     return p.normalise_obs ? (x - p.obs_low[d]) / p.obs_grad[d] - (T)1 : x;
 }
 

@@ -94,6 +94,14 @@ SPECS = {
                          midprice=dict(kind="gbm", drift=0.02, volatility=0.1, initial_price=80.0),
                          impact=dict(kind="transient", transient=0.8, resilience=1.0, initial=0.0, kernel=0.5),
                          reward=dict(kind="pnl"), initial_inventory=-15, max_inventory=1000, normalise_action=True),
+    # the reference's default-constructor flags (normalised actions + observations) with the inventory-averse rewards:
+    # the compile-time "normalised" kernel variants
+    "cjmm_normalised": dict(N=93, n_steps=40, terminal_time=1.0, seed=1252, dynamics="limit",
+                            reward=dict(kind="cjmm", phi=0.01, alpha=0.001), max_inventory=100, initial_inventory=[-4, 5],
+                            normalise_action=True, normalise_obs=True, **AS),
+    "rip_normalised": dict(N=87, n_steps=40, terminal_time=1.0, seed=1253, dynamics="limit",
+                           reward=dict(kind="rip", phi=0.02, alpha=0.3), max_inventory=7, normalise_action=True,
+                           normalise_obs=True, **AS),
     # fill functions whose probability is a BATCH reduction in the reference (np.max(depths, 0) over trajectories,
     # fill_probability_models.py:82,113)
     "triangular_fill": dict(N=77, n_steps=40, terminal_time=1.0, seed=1249, dynamics="limit", reward=dict(kind="pnl"),
@@ -119,7 +127,11 @@ def main():
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
     index = {}
+    only = set(sys.argv[1:])  # `python tools/make_golden.py name ...` rewrites just those fixtures (index.json always)
     for name, spec in SPECS.items():
+        index[name] = spec
+        if only and name not in only:
+            continue
         n_ep = spec.get("n_episodes", 1)
         out = R.run_pair(spec, n_episodes=n_ep)
         same = (np.array_equal(out["ref_obs"], out["orc_obs"]) and np.array_equal(out["ref_rew"], out["orc_rew"])
@@ -132,7 +144,6 @@ def main():
             seed=np.uint64(spec["seed"]), n_episodes=np.int64(n_ep), actions=out["actions"],
             reset_obs=out["ref_reset"], obs=out["ref_obs"], rew=out["ref_rew"],
             done=np.array(out["ref_done"], np.uint8), final_state=out["ref_state"])
-        index[name] = spec
     with open(os.path.join(outdir, "index.json"), "w") as f:
         json.dump(index, f, indent=1, sort_keys=True)
 
