@@ -156,21 +156,39 @@ __device__ __forceinline__ void store_rows_staged(T *__restrict__ base, long lon
 template <typename T, class V>
 __device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T> &s, T t, T *row) {
     const int arr = pick<V::arr>(p.arr), imp = pick<V::imp>(p.imp);
-    int d = 0;
-    row[d] = norm_obs<T, V>(p, s.cash, d); ++d;
-    row[d] = norm_obs<T, V>(p, s.inv, d); ++d;
-    row[d] = norm_obs<T, V>(p, t, d); ++d;
-    row[d] = norm_obs<T, V>(p, s.mid, d); ++d;
+    row[0] = norm_obs<T, V>(p, s.cash, 0);
+    row[1] = norm_obs<T, V>(p, s.inv, 1);
+    row[2] = norm_obs<T, V>(p, t, 2);
+    row[3] = norm_obs<T, V>(p, s.mid, 3);
+    /* model columns at FIXED positions (no `row[d++]` with a runtime d: that would put the row in local memory).  Hawkes
+     * intensities and a price-impact column never coexist: Hawkes needs limit-order dynamics, impact models need speed
+     * dynamics (mbt_validate_config) */
+    int d = 4;
     if (arr == MBT_ARR_HAWKES) {
-        row[d] = norm_obs<T, V>(p, s.x0, d); ++d;
-        row[d] = norm_obs<T, V>(p, s.x1, d); ++d;
+        row[4] = norm_obs<T, V>(p, s.x0, 4);
+        row[5] = norm_obs<T, V>(p, s.x1, 5);
+        d = 6;
+    } else if (imp_has_state(imp)) {
+        row[4] = norm_obs<T, V>(p, s.x0, 4);
+        d = 5;
     }
-    if (imp_has_state(imp)) { row[d] = norm_obs<T, V>(p, s.x0, d); ++d; }
     if (V::norm < 0 && p.obs_select) { /* keep the selected columns, in order (gym/wrappers.py:30-38) */
+        /* compaction without dynamically indexed registers (a runtime `row[j++]` would push the whole row into local
+         * memory for every launch of the runtime-flag variants, selecting or not): output slot j takes column k when k is
+         * the j-th set bit of the mask -- all indices below are compile-time after unrolling, the tests are warp-uniform */
+        T out[MBT_MAX_OBS_DIM];
         int j = 0;
 #pragma unroll
-        for (int k = 0; k < MBT_MAX_OBS_DIM; ++k)
-            if (k < d && ((p.obs_select >> k) & 1)) row[j++] = row[k];
+        for (int k = 0; k < MBT_MAX_OBS_DIM; ++k) {
+            const bool take = k < d && ((p.obs_select >> k) & 1);
+#pragma unroll
+            for (int slot = 0; slot < MBT_MAX_OBS_DIM; ++slot)
+                if (slot <= k && take && slot == j) out[slot] = row[k];
+            j += take ? 1 : 0;
+        }
+#pragma unroll
+        for (int slot = 0; slot < MBT_MAX_OBS_DIM; ++slot)
+            if (slot < j) row[slot] = out[slot];
         return j;
     }
     return d;
