@@ -346,6 +346,74 @@ def test_full_size_properties_2pow20():
     assert np.all(qT == np.round(qT))
 
 
+def _fixed_policy(values):
+    pol = _abi.mbt_policy()
+    pol.kind = _abi.MBT_POL_FIXED
+    for j, v in enumerate(values):
+        pol.fixed[j] = v
+    return pol
+
+
+def _episode(cfg, pol, seed=77):
+    e = _lib.NativeEnv(cfg)
+    e.seed(seed)
+    e.reset()
+    ret = np.empty(e.N); qT = np.empty(e.N)
+    summ = e.rollout(pol, ret, qT)
+    state = e.get_state()
+    e.close()
+    return ret, qT, state, summ
+
+
+def test_full_size_properties_cjmm_hawkes_oe_2pow20():
+    """BASELINE.json configs[2..4] at their full per-GPU size (2^20 trajectories), through size-independent properties:
+      C3  the reference's own unit-test identity (rewards/tests/testRewardFunctions.py:68-135): over an episode the
+          CjMmCriterion rewards sum to the RunningInventoryPenalty rewards -- random initial inventories, late start;
+      C4  Hawkes: integral inventories, positive finite intensities, and a shard holding global ids [a, a+4096) reproduces
+          that slice of the full batch bit-for-bit;
+      C5  optimal execution (8 x 2^20 trajectories sharded over 8 GPUs): inventory and permanent impact under a constant
+          trading speed are the same deterministic recurrences for every trajectory, and the LAST shard's slice
+          (global ids 7 * 2^20 + ...) is reproduced by a small handle with the same offset."""
+    N = 1 << 20
+    # ---- C3
+    g = Golden("cjmm")
+    pol = _fixed_policy([0.7, 0.9])
+    cfg_mm = g.config(_abi.MBT_F64, num_trajectories=N)
+    cfg_rip = g.config(_abi.MBT_F64, num_trajectories=N, reward=_abi.MBT_REW_RUNNING_INVENTORY_PENALTY)
+    r_mm, q_mm, st_mm, s_mm = _episode(cfg_mm, pol)
+    r_rip, q_rip, st_rip, _ = _episode(cfg_rip, pol)
+    assert np.array_equal(st_mm, st_rip), "the reward function must not influence the dynamics"
+    assert len(np.unique(q_mm)) > 20 and s_mm.steps == 90  # start_time 0.1 of 100 steps
+    np.testing.assert_allclose(r_mm, r_rip, rtol=0, atol=1e-9)  # telescoping identity, float64 accumulation error only
+    # ---- C4
+    g = Golden("hawkes_pnl")
+    pol = _fixed_policy([0.7, 0.7])
+    cfg = g.config(_abi.MBT_F64, num_trajectories=N)
+    ret, qT, st, summ = _episode(cfg, pol)
+    assert summ.steps == 200 and np.all(qT == np.round(qT))
+    lam = st[:, 4:6]
+    assert np.all(np.isfinite(lam)) and np.all(lam > 0) and 5.0 < lam.mean() < 60.0
+    a0 = 3 * (N // 4) + 123
+    part = g.config(_abi.MBT_F64, num_trajectories=4096, traj_offset=a0)
+    ret_p, qT_p, st_p, _ = _episode(part, pol)
+    assert np.array_equal(ret_p, ret[a0:a0 + 4096]) and np.array_equal(st_p, st[a0:a0 + 4096])
+    # ---- C5 (the shard of the last of 8 GPUs: global ids 7 * 2^20 ...)
+    g = Golden("oe_ou_cjoe")
+    pol = _fixed_policy([-1.0])
+    off = 7 * N
+    cfg = g.config(_abi.MBT_F64, num_trajectories=N, traj_offset=off)
+    ret, qT, st, summ = _episode(cfg, pol)
+    q, imp = cfg.q0_const, 0.0
+    for _ in range(summ.steps):  # ModelDynamics.py:262-267, price_impact_models.py:88-89 with nu = -1
+        q = q + (-1.0 * cfg.mid_step)
+        imp = imp + (cfg.imp_perm * -1.0) * cfg.imp_step
+    assert np.all(st[:, 1] == q) and np.all(st[:, 4] == imp) and np.all(qT == q)
+    assert len(np.unique(st[:, 3])) > N // 2 and np.all(np.isfinite(ret))
+    part = g.config(_abi.MBT_F64, num_trajectories=2048, traj_offset=off + N - 2048)
+    ret_p, _, st_p, _ = _episode(part, pol)
+    assert np.array_equal(ret_p, ret[N - 2048:]) and np.array_equal(st_p, st[N - 2048:])
+
+
 def test_inventory_distribution_and_reward_per_step_vs_numpy_port():
     """statistical parity of the Philox/CUDA path with the PCG64/NumPy path on the quantities
     BASELINE.json names -- terminal-inventory distribution (chi-square, p > 0.001), mean terminal PnL and mean reward per
