@@ -13,7 +13,7 @@
  *   mbt_step        <- TradingEnvironment.step                TradingEnvironment.py:103-110
  *                      (+ everything it calls: ModelDynamics.py:108-131,262-267;
  *                       arrival_models.py:54-56,110-123; fill_probability_models.py:28-34,57-58,82,113;
- *                       midprice_models.py:60-65,97-105,140-143; price_impact_models.py:88-92;
+ *                       midprice_models.py:60-65,97-105,140-143,354-369; price_impact_models.py:88-92;
  *                       RewardFunctions.py:23-33,55-70,96-109,128-138)
  *   mbt_get_state   <- TradingEnvironment.state (property)    TradingEnvironment.py:142-144
  *   mbt_set_state   <- `env.model_dynamics.state = ...`        ModelDynamics.py:39 (test injection / resume)
@@ -77,6 +77,7 @@ extern "C" {
 #define MBT_MID_OU 3       /* OuMidpriceModel                      :114-146 */
 #define MBT_MID_BM_JUMP 4  /* BrownianMotionJumpMidpriceModel      :193-230 (jumps on the agent's own fills) */
 #define MBT_MID_OU_JUMP 5  /* OuJumpMidpriceModel                  :233-273 */
+#define MBT_MID_HESTON 6   /* HestonMidpriceModel                  :322-372 state = (price, variance): D grows by 1 */
 
 /* arrival_models.py */
 #define MBT_ARR_NONE 0
@@ -149,6 +150,12 @@ typedef struct mbt_config {
     double ou_level;    /* mean_reversion_level */
     double ou_speed;    /* mean_reversion_speed */
     double mid_jump;    /* jump_size (jump models) */
+    /* HestonMidpriceModel (drift above) */
+    double heston_speed;  /* volatility_mean_reversion_rate  */
+    double heston_level;  /* volatility_mean_reversion_level */
+    double heston_corr;   /* weiner_correlation              */
+    double heston_volvol; /* volatility_of_volatility        */
+    double heston_var0;   /* initial_variance                */
 
     /* arrival model */
     double arr_rate[2];  /* Poisson intensity, or Hawkes baseline_arrival_rate (bid, ask) */

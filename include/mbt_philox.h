@@ -37,6 +37,7 @@
 
 #define MBT_STREAM_STEP 0u  /* per-step draws: arrivals, fills, midprice normal */
 #define MBT_STREAM_RESET 1u /* per-episode draws: random initial inventory      */
+#define MBT_STREAM_STEP2 2u /* per-step draws of models that need a second normal (Heston variance) */
 
 typedef struct mbt_u32x4 {
     uint32_t x, y, z, w;

@@ -34,6 +34,7 @@ MBT_MID_GBM = 2
 MBT_MID_OU = 3
 MBT_MID_BM_JUMP = 4
 MBT_MID_OU_JUMP = 5
+MBT_MID_HESTON = 6
 
 MBT_ARR_NONE = 0
 MBT_ARR_POISSON = 1
@@ -102,6 +103,11 @@ class mbt_config(C.Structure):
         ("ou_level", C.c_double),
         ("ou_speed", C.c_double),
         ("mid_jump", C.c_double),
+        ("heston_speed", C.c_double),
+        ("heston_level", C.c_double),
+        ("heston_corr", C.c_double),
+        ("heston_volvol", C.c_double),
+        ("heston_var0", C.c_double),
         ("arr_rate", C.c_double * 2),
         ("arr_step", C.c_double),
         ("hawkes_jump", C.c_double),

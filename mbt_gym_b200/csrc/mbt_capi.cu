@@ -43,6 +43,7 @@ static int fail(int code, const std::string &msg) {
 
 /* ------------------------------------------------------------------ handle */
 constexpr int MBT_TIMING_RING = 8192;
+constexpr int MBT_STATE_COLUMNS = 7; /* columns of the structure-of-arrays state block (DevState) */
 constexpr int MBT_PIPE_CHUNKS = 16;        /* capacity */
 constexpr int MBT_PIPE_CHUNKS_DEFAULT = 4;  /* measured: 2 / 4 / 8 / 16 chunks -> 0.965 / 0.931 / 0.950 / 1.026 ms per step */
 
@@ -59,7 +60,7 @@ struct mbt_env {
 
     /* device state, structure-of-arrays (one allocation, columns of N elements) */
     void *state_block = nullptr;
-    void *col[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; /* cash, inv, mid, x0, x1, q0 */
+    void *col[MBT_STATE_COLUMNS] = {}; /* cash, inv, mid, x0, x1, q0, var */
     unsigned long long *d_clipped = nullptr;
 
     /* device + pinned staging for MBT_MEM_HOST calls */
@@ -111,6 +112,7 @@ static DevState<T> dev_state(mbt_env *e) {
     st.x0 = (T *)e->col[3];
     st.x1 = (T *)e->col[4];
     st.q0 = (T *)e->col[5];
+    st.var = (T *)e->col[6];
     return st;
 }
 
@@ -319,7 +321,7 @@ static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<
     g.p = p;
     g.ck = ck;
     g.st = dev_state<T>(e);
-    g.st.cash += r0; g.st.inv += r0; g.st.mid += r0; g.st.x0 += r0; g.st.x1 += r0; g.st.q0 += r0;
+    g.st.cash += r0; g.st.inv += r0; g.st.mid += r0; g.st.x0 += r0; g.st.x1 += r0; g.st.q0 += r0; g.st.var += r0;
     g.actions = (const E *)actions + r0 * e->A;
     g.obs = obs ? (E *)obs + r0 * e->Dout : nullptr;
     g.rew = rew ? (E *)rew + r0 : nullptr;
@@ -484,6 +486,7 @@ static int do_reset_device(mbt_env *e, const mbt_reset_args *args, void *obs) {
     g.lam0[0] = (T)c.arr_rate[0];
     g.lam0[1] = (T)c.arr_rate[1];
     g.imp0 = c.impact == MBT_IMP_TEMP_PERM ? (T)0 : (T)c.imp_initial;
+    g.var0 = (T)c.heston_var0;
     g.q0_mode = q0_mode;
     g.q0_const = (T)q0_const;
     g.q0_lo = lo;
@@ -642,9 +645,9 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     }
     /* columns padded to 256 B so every column base is aligned for any vector width */
     const size_t col_bytes = (((size_t)e->N * e->esz) + 255) & ~(size_t)255;
-    CUB(cudaMalloc(&e->state_block, col_bytes * 6));
-    CUB(cudaMemsetAsync(e->state_block, 0, col_bytes * 6, e->stream));
-    for (int i = 0; i < 6; ++i) e->col[i] = (char *)e->state_block + col_bytes * i;
+    CUB(cudaMalloc(&e->state_block, col_bytes * MBT_STATE_COLUMNS));
+    CUB(cudaMemsetAsync(e->state_block, 0, col_bytes * MBT_STATE_COLUMNS, e->stream));
+    for (int i = 0; i < MBT_STATE_COLUMNS; ++i) e->col[i] = (char *)e->state_block + col_bytes * i;
     CUB(cudaMalloc(&e->d_clipped, sizeof(unsigned long long)));
     CUB(cudaMemsetAsync(e->d_clipped, 0, sizeof(unsigned long long), e->stream));
     CUB(cudaMalloc((void **)&e->d_counter_base, 2 * sizeof(unsigned long long)));
@@ -866,7 +869,7 @@ struct mbt_ckpt_header {
 static const uint64_t MBT_CKPT_MAGIC = 0x4D42543230304231ull; /* "MBT200B1" */
 
 static size_t state_block_bytes(const mbt_env *e) {
-    return ((((size_t)e->N * e->esz) + 255) & ~(size_t)255) * 6;
+    return ((((size_t)e->N * e->esz) + 255) & ~(size_t)255) * MBT_STATE_COLUMNS;
 }
 
 int mbt_checkpoint_size(mbt_env *e, size_t *bytes) {

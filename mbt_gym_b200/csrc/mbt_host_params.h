@@ -24,6 +24,7 @@ static inline int mbt_dims(const mbt_config *c, int32_t *A, int32_t *D, int32_t 
     case MBT_DYN_SPEED: a = 1; break;
     default: return MBT_E_UNSUPPORTED;
     }
+    if (c->midprice == MBT_MID_HESTON) d += 1; /* (price, variance)  midprice_models.py:346 */
     if (c->arrival == MBT_ARR_HAWKES) d += 2;
     if (c->impact == MBT_IMP_TEMP_PERM || c->impact == MBT_IMP_TEMP_TRANSIENT || c->impact == MBT_IMP_TRANSIENT) d += 1;
     if (A) *A = a;
@@ -58,7 +59,18 @@ static inline int mbt_validate_config(const mbt_config *c, std::string &err) {
         return MBT_E_INVALID_ARG;
     }
     if (mbt_dims(c, nullptr, nullptr, nullptr) != MBT_OK) { err = "unknown dynamics kind"; return MBT_E_UNSUPPORTED; }
-    if (c->midprice < MBT_MID_CONSTANT || c->midprice > MBT_MID_OU_JUMP) { err = "unknown midprice model"; return MBT_E_UNSUPPORTED; }
+    if (c->midprice < MBT_MID_CONSTANT || c->midprice > MBT_MID_HESTON) { err = "unknown midprice model"; return MBT_E_UNSUPPORTED; }
+    if (c->midprice == MBT_MID_HESTON && c->normalise_obs) {
+        /* the reference publishes bounds for ONE of the model's two state columns (midprice_models.py:343-346), so its
+         * normalise_observation fails to broadcast (N, D) against (D-1,) bounds */
+        err = "the Heston midprice model has no bounds for its variance column: observation normalisation is undefined "
+              "(the reference fails too)";
+        return MBT_E_UNSUPPORTED;
+    }
+    if (c->midprice == MBT_MID_HESTON && !(c->heston_corr >= -1.0 && c->heston_corr <= 1.0)) {
+        err = "heston_corr (weiner_correlation) must be within [-1, 1]";
+        return MBT_E_INVALID_ARG;
+    }
     if (c->reward < MBT_REW_PNL || c->reward > MBT_REW_EXP_UTILITY) { err = "unknown reward function"; return MBT_E_UNSUPPORTED; }
     if (c->dynamics == MBT_DYN_SPEED) {
         /* ModelDynamics.py:273-275: required_processes = ["price_impact_model"] */
@@ -143,6 +155,8 @@ static inline StepParams<T> mbt_make_params(const mbt_config &c, double t0, int 
     p.vol_sqdt = (T)(c.mid_vol * std::sqrt(c.mid_step));
     p.sqdt = (T)std::sqrt(c.mid_step);
     p.mid_drift = (T)c.mid_drift; p.mid_vol = (T)c.mid_vol; p.mid_step = (T)c.mid_step;
+    p.heston_speed = (T)c.heston_speed; p.heston_level = (T)c.heston_level; p.heston_rho = (T)c.heston_corr;
+    p.heston_rho_c = (T)std::sqrt(1.0 - c.heston_corr * c.heston_corr); p.heston_xi = (T)c.heston_volvol;
     p.ou_neg_speed = -(T)c.ou_speed; p.ou_speed = (T)c.ou_speed; p.ou_level = (T)c.ou_level; p.mid_jump = (T)c.mid_jump;
     p.imp_temp = (T)c.imp_temp; p.imp_perm = (T)c.imp_perm; p.imp_exp = (T)c.imp_exponent; p.imp_step = (T)c.imp_step;
     p.imp_transient = (T)c.imp_transient; p.imp_resilience = (T)c.imp_resilience; p.imp_kernel = (T)c.imp_kernel;

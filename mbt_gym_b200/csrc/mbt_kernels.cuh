@@ -32,7 +32,7 @@ constexpr int MBT_BLOCK = MBT_BLOCK_THREADS;
 
 template <typename T>
 struct DevState {
-    T *cash, *inv, *mid, *x0, *x1, *q0;
+    T *cash, *inv, *mid, *x0, *x1, *q0, *var; /* var: Heston variance */
 };
 
 /* T = arithmetic / state type; E = element type of the CALLER's buffers (E = T, or float over double arithmetic:
@@ -164,7 +164,18 @@ __device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T
      * intensities and a price-impact column never coexist: Hawkes needs limit-order dynamics, impact models need speed
      * dynamics (mbt_validate_config) */
     int d = 4;
-    if (arr == MBT_ARR_HAWKES) {
+    if (pick<V::mid>(p.mid) == MBT_MID_HESTON) { /* the midprice model owns two columns: (price, variance) */
+        row[4] = norm_obs<T, V>(p, s.var, 4);
+        d = 5;
+        if (arr == MBT_ARR_HAWKES) {
+            row[5] = norm_obs<T, V>(p, s.x0, 5);
+            row[6] = norm_obs<T, V>(p, s.x1, 6);
+            d = 7;
+        } else if (imp_has_state(imp)) {
+            row[5] = norm_obs<T, V>(p, s.x0, 5);
+            d = 6;
+        }
+    } else if (arr == MBT_ARR_HAWKES) {
         row[4] = norm_obs<T, V>(p, s.x0, 4);
         row[5] = norm_obs<T, V>(p, s.x1, 5);
         d = 6;
@@ -204,6 +215,8 @@ __device__ __forceinline__ void load_traj(const StepParams<T> &p, const DevState
     s.x1 = (T)0;
     if (arr == MBT_ARR_HAWKES) { s.x0 = st.x0[i]; s.x1 = st.x1[i]; }
     if (imp_has_state(imp)) s.x0 = st.x0[i];
+    s.var = (T)0;
+    if (pick<V::mid>(p.mid) == MBT_MID_HESTON) s.var = st.var[i];
 }
 
 template <typename T, class V>
@@ -214,6 +227,15 @@ __device__ __forceinline__ void store_traj(const StepParams<T> &p, const DevStat
     if (mid != MBT_MID_CONSTANT) st.mid[i] = s.mid;
     if (arr == MBT_ARR_HAWKES) { st.x0[i] = s.x0; st.x1[i] = s.x1; }
     if (imp_has_state(imp)) st.x0[i] = s.x0;
+    if (mid == MBT_MID_HESTON) st.var[i] = s.var;
+}
+
+/* the 32 normal bits of the step's SECOND Philox block, for the models that need a second normal (Heston) */
+template <typename T, class V>
+__device__ __forceinline__ uint32_t second_normal_bits(const StepParams<T> &p, const mbt_philox_keys &keys,
+                                                       unsigned long long traj, unsigned long long n_step) {
+    if (V::mid >= 0 || p.mid != MBT_MID_HESTON) return 0u; /* the specialised variants fix other midprice models */
+    return mbt_normal_bits(mbt_draw_keyed(keys, traj, n_step, MBT_STREAM_STEP2));
 }
 
 /* ------------------------------------------------------------------ step */
@@ -234,6 +256,7 @@ __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, b
         n_step += g.counter_base[0];
     }
     const mbt_u32x4 r = mbt_draw_keyed(g.keys, g.traj_offset + (unsigned long long)i, n_step, MBT_STREAM_STEP);
+    const uint32_t nbits2 = second_normal_bits<T, V>(p, g.keys, g.traj_offset + (unsigned long long)i, n_step);
     pdl_wait(); /* everything below reads what the previous kernel (previous step, or the caller's policy) wrote */
     const int A = action_width<T, V>(p);
     E a_io[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
@@ -256,7 +279,7 @@ __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, b
     }
 
     int clipped = 0;
-    const T rwd = step_one<T, V>(p, g.ck, s, a, r, q_init, &clipped, fill_thr);
+    const T rwd = step_one<T, V>(p, g.ck, s, a, r, q_init, &clipped, fill_thr, nbits2);
 
     store_traj<T, V>(p, g.st, i, s);
     if (g.obs) {
@@ -410,7 +433,7 @@ struct ResetArgs {
     long long n;
     unsigned long long seed, traj_offset, n_episode;
     const unsigned long long *counter_base; /* see StepArgs */
-    T cash0, t0, mid0, lam0[2], imp0;
+    T cash0, t0, mid0, lam0[2], imp0, var0;
     int q0_mode;
     T q0_const;
     long long q0_lo;
@@ -434,6 +457,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_reset_kernel(const __grid_const
     s.mid = g.mid0;
     s.x0 = (T)0;
     s.x1 = (T)0;
+    s.var = g.var0; /* Heston initial_variance (unused otherwise) */
     if (p.arr == MBT_ARR_HAWKES) { s.x0 = g.lam0[0]; s.x1 = g.lam0[1]; }
     if (imp_has_state(p.imp)) s.x0 = g.imp0; /* 0 for the permanent impact, initial_transient_impact otherwise */
     g.st.cash[i] = s.cash;
@@ -441,6 +465,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_reset_kernel(const __grid_const
     g.st.mid[i] = s.mid;
     if (p.arr == MBT_ARR_HAWKES) { g.st.x0[i] = s.x0; g.st.x1[i] = s.x1; }
     if (imp_has_state(p.imp)) g.st.x0[i] = s.x0;
+    if (p.mid == MBT_MID_HESTON) g.st.var[i] = s.var;
     if (g.q0_mode == MBT_Q0_UNIFORM_INT) g.st.q0[i] = s.inv; /* reward_function.reset  RewardFunctions.py:72,111 */
     if (g.obs) {
         T row[MBT_MAX_OBS_DIM];
@@ -484,6 +509,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_scatter_state_kernel(StepParams
     st.inv[i] = row[1];
     st.mid[i] = row[3];
     int d = 4;
+    if (p.mid == MBT_MID_HESTON) { st.var[i] = row[d]; d += 1; }
     if (p.arr == MBT_ARR_HAWKES) { st.x0[i] = row[d]; st.x1[i] = row[d + 1]; d += 2; }
     if (imp_has_state(p.imp)) st.x0[i] = row[d];
 }
@@ -498,7 +524,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_reward_kernel(StepParams<T> p, 
     T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
     for (int j = 0; j < p.action_dim; ++j) a[j] = act[i * p.action_dim + j];
     Traj<T> s;
-    s.cash = x[0]; s.inv = x[1]; s.mid = x[3]; s.x0 = 0; s.x1 = 0;
+    s.cash = x[0]; s.inv = x[1]; s.mid = x[3]; s.x0 = 0; s.x1 = 0; s.var = 0;
     StepClock<T> ck;
     ck.t_next = x[2];
     ck.dt_r = x[2] - c[2];
@@ -614,7 +640,8 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
              * so the deepest quote of the batch is this trajectory's own */
             T fill_thr[2] = {(T)0, (T)0};
             if (V::dyn < 0 && fill_is_batch(p.fill)) fill_batch_thresholds<T>(p, a[0], a[1], fill_thr);
-            const T rwd = step_one<T, V>(p, ck, s, a, r, q_init, &clipped, fill_thr);
+            const uint32_t nbits2 = second_normal_bits<T, V>(p, g.keys, g.traj_offset + (unsigned long long)i, n_step0 + (unsigned long long)k);
+            const T rwd = step_one<T, V>(p, ck, s, a, r, q_init, &clipped, fill_thr, nbits2);
             ret = ret + rwd;
             acc[5] += (double)rwd * (double)rwd;
             if (REC && g.rec_rew) g.rec_rew[(long long)k * g.n + i] = rwd;

@@ -31,7 +31,7 @@ struct Variant {
     /* action / observation widths when the model kinds are fixed (0 = runtime) */
     static constexpr int A = DYN < 0 ? 0 : (DYN == MBT_DYN_SPEED ? 1 : (DYN == MBT_DYN_LIMIT_AND_MARKET ? 4 : 2));
     static constexpr int D = (DYN < 0 || ARR < 0 || IMP < 0) ? 0
-                                                             : 4 + (ARR == MBT_ARR_HAWKES ? 2 : 0) +
+                                                             : 4 + (MID == MBT_MID_HESTON ? 1 : 0) + (ARR == MBT_ARR_HAWKES ? 2 : 0) +
                                                                    ((IMP == MBT_IMP_TEMP_PERM || IMP == MBT_IMP_TEMP_TRANSIENT || IMP == MBT_IMP_TRANSIENT) ? 1 : 0);
 };
 using VariantGeneric = Variant<-1, -1, -1, -1, -1, -1>;
@@ -43,6 +43,8 @@ MBT_HD float mbt_pow_t(float x, float p) { return mbt_pow_f32(x, p); }
 MBT_HD double mbt_pow_t(double x, double p) { return mbt_pow_f64(x, p); }
 MBT_HD float mbt_exp2k_t(float x, int k) { return mbt_exp2k_f32(x, k); }
 MBT_HD double mbt_exp2k_t(double x, int k) { return mbt_exp2k_f64(x, k); }
+MBT_HD float mbt_sqrt_t(float x) { return sqrtf(x); }
+MBT_HD double mbt_sqrt_t(double x) { return sqrt(x); }
 MBT_HD void mbt_real_t(uint32_t k, float *u) { *u = mbt_u24_to_real_f32(k); }
 MBT_HD void mbt_real_t(uint32_t k, double *u) { *u = mbt_u24_to_real_f64(k); }
 
@@ -70,6 +72,7 @@ struct StepParams {
     T neg_kappa; /* -fill_exponent */
     T fill_max_depth, fill_mult, fill_pexp; /* Triangular: max_fill_depth;  Power: fill_multiplier, fill_exponent */
     T drift_dt, vol_sqdt, sqdt, mid_drift, mid_vol, mid_step, ou_neg_speed, ou_speed, ou_level, mid_jump;
+    T heston_speed, heston_level, heston_rho, heston_rho_c /* sqrt(1 - rho^2) */, heston_xi;
     T imp_temp, imp_perm, imp_exp, imp_step, imp_transient, imp_resilience, imp_kernel, half_spread;
     T phi, alpha, pexp, risk_aversion, reward_scaling;
     T act_low[MBT_MAX_ACTION_DIM], act_grad[MBT_MAX_ACTION_DIM];
@@ -103,6 +106,7 @@ template <typename T>
 struct Traj {
     T cash, inv, mid;
     T x0, x1; /* Hawkes: (lambda_bid, lambda_ask);  Temp+Perm impact: x0 = accumulated permanent impact */
+    T var;    /* Heston: the variance column of the midprice model */
 };
 
 template <int CT>
@@ -165,11 +169,12 @@ MBT_HD T reward_one(const StepParams<T> &p, const StepClock<T> &ck, T c0, T q_cu
  *   r       the 128 random bits of this (trajectory, step)   include/mbt_philox.h draw contract
  *   q_init  initial inventory of the episode (for CjMm / CjOe)
  *   fill_thr  batch-reduced fill models only: the step's two fill probabilities * 2^24 (fill_batch_thresholds)
+ *   nbits2  Heston only: the 32 normal bits of the step's SECOND Philox block (stream MBT_STREAM_STEP2)
  * returns the (scaled) reward; *clipped is set when inventory or cash hit their bounds.
  */
 template <typename T, class V>
 MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, const T *a, mbt_u32x4 r, T q_init, int *clipped,
-                  const T *fill_thr = nullptr) {
+                  const T *fill_thr = nullptr, uint32_t nbits2 = 0u) {
     const int dyn = pick<V::dyn>(p.dyn), mid = pick<V::mid>(p.mid), arr_kind = pick<V::arr>(p.arr),
               imp = pick<V::imp>(p.imp);
     /* the specialised variants are only selected for the exponential fill function (variant_of) */
@@ -256,7 +261,18 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
             s.mid = (S + (p.mid_drift * S) * p.mid_step) + (((p.mid_vol * S) * p.sqdt) * z);
         else if (mid == MBT_MID_OU) /* midprice_models.py:140-143: drift not scaled by dt, as written there */
             s.mid = S + (p.ou_neg_speed * (S - p.ou_level) + p.vol_sqdt * z);
-        else if (mid == MBT_MID_BM_JUMP) /* midprice_models.py:222-230: jumps on the agent's own fills */
+        else if (mid == MBT_MID_HESTON) {
+            /* midprice_models.py:354-369.  The reference draws (W_S, W_v) ~ N(0, [[1, rho], [rho, 1]]) from the GLOBAL
+             * np.random; the draw contract here: W_S = z, W_v = rho * z + sqrt(1 - rho^2) * z2 (Cholesky), z2 the normal of
+             * the step's second Philox block.  Both updates use the variance BEFORE the step. */
+            const T z2 = (T)mbt_normal_from_bits_f32(nbits2);
+            const T w_v = p.heston_rho * z + p.heston_rho_c * z2;
+            const T v = s.var;
+            const T vol = mbt_sqrt_t(v * p.mid_step); /* np.sqrt(variance * step_size): correctly rounded on both sides */
+            s.mid = (S + (p.mid_drift * S) * p.mid_step) + ((vol * S) * z);
+            const T nv = (v + (p.heston_speed * (p.heston_level - v)) * p.mid_step) + ((p.heston_xi * vol) * w_v);
+            s.var = nv < (T)0 ? -nv : (nv == (T)0 ? (T)0 : nv); /* np.abs (also turns -0.0 into +0.0) */
+        } else if (mid == MBT_MID_BM_JUMP) /* midprice_models.py:222-230: jumps on the agent's own fills */
             s.mid = ((S + p.drift_dt) + p.vol_sqdt * z) + (p.mid_jump * own_a - p.mid_jump * own_b);
         else /* MBT_MID_OU_JUMP  midprice_models.py:262-270 */
             s.mid = ((S - p.ou_speed * (S - p.ou_level)) + p.vol_sqdt * z) + (p.mid_jump * own_a - p.mid_jump * own_b);

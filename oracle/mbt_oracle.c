@@ -37,6 +37,7 @@ static int orc_dims(const mbt_config *c, int32_t *A, int32_t *D, int32_t *S) {
     case MBT_DYN_SPEED: a = 1; break;            /* ModelDynamics.py:269-271 */
     default: return -1;
     }
+    if (c->midprice == MBT_MID_HESTON) d += 1;   /* (price, variance)  midprice_models.py:346 */
     if (c->arrival == MBT_ARR_HAWKES) d += 2;    /* arrival_models.py:99-103 */
     if (c->impact == MBT_IMP_TEMP_PERM || c->impact == MBT_IMP_TEMP_TRANSIENT || c->impact == MBT_IMP_TRANSIENT)
         d += 1; /* one state column: price_impact_models.py:79-83,119-127,162-170 */
@@ -111,15 +112,30 @@ void orc_step(orc_handle *h, const void *actions, void *obs_out, void *rew_out, 
 /* step with caller-supplied random numbers: u (N,4), z (N,) in the handle's precision */
 void orc_step_draws(orc_handle *h, const void *actions, const void *u, const void *z, void *obs_out, void *rew_out,
                     uint8_t *done_out) {
-    if (h->d) orc_step_core_f64(h->d, (const double *)actions, (const double *)u, (const double *)z, (double *)obs_out,
-                                (double *)rew_out, done_out);
-    else orc_step_core_f32(h->f, (const float *)actions, (const float *)u, (const float *)z, (float *)obs_out,
-                           (float *)rew_out, done_out);
+    /* the second normal (Heston only) always comes from the draw contract here */
+    if (h->d) {
+        double *z2 = h->d->cfg.midprice == MBT_MID_HESTON ? (double *)malloc(sizeof(double) * (size_t)h->d->N) : NULL;
+        if (z2) orc_fill_draws_f64(h->d->seed, h->d->cfg.traj_offset, h->d->N, h->d->n_step, NULL, NULL, z2);
+        orc_step_core_f64(h->d, (const double *)actions, (const double *)u, (const double *)z, z2, (double *)obs_out,
+                          (double *)rew_out, done_out);
+        free(z2);
+    } else {
+        float *z2 = h->f->cfg.midprice == MBT_MID_HESTON ? (float *)malloc(sizeof(float) * (size_t)h->f->N) : NULL;
+        if (z2) orc_fill_draws_f32(h->f->seed, h->f->cfg.traj_offset, h->f->N, h->f->n_step, NULL, NULL, z2);
+        orc_step_core_f32(h->f, (const float *)actions, (const float *)u, (const float *)z, z2, (float *)obs_out,
+                          (float *)rew_out, done_out);
+        free(z2);
+    }
 }
 /* the draws step `n_step` would use (so a test can hand the SAME numbers to the reference) */
 void orc_draws(int precision, uint64_t seed, int64_t traj_offset, int64_t N, int64_t n_step, void *u, void *z) {
-    if (precision == MBT_F64) orc_fill_draws_f64(seed, traj_offset, N, n_step, (double *)u, (double *)z);
-    else orc_fill_draws_f32(seed, traj_offset, N, n_step, (float *)u, (float *)z);
+    if (precision == MBT_F64) orc_fill_draws_f64(seed, traj_offset, N, n_step, (double *)u, (double *)z, NULL);
+    else orc_fill_draws_f32(seed, traj_offset, N, n_step, (float *)u, (float *)z, NULL);
+}
+/* the SECOND normal step `n_step` uses (Heston variance; stream MBT_STREAM_STEP2 of the draw contract) */
+void orc_draws2(int precision, uint64_t seed, int64_t traj_offset, int64_t N, int64_t n_step, void *z2) {
+    if (precision == MBT_F64) orc_fill_draws_f64(seed, traj_offset, N, n_step, NULL, NULL, (double *)z2);
+    else orc_fill_draws_f32(seed, traj_offset, N, n_step, NULL, NULL, (float *)z2);
 }
 /* the initial inventories reset number `n_episode` draws for MBT_Q0_UNIFORM_INT (same formula as orc_reset) */
 void orc_q0_draws(uint64_t seed, int64_t traj_offset, int64_t N, int64_t n_episode, int64_t lo, int64_t hi, int64_t *out) {

@@ -143,6 +143,7 @@ static void FN(orc_reset)(FN(orc_env) * e, const mbt_reset_args *args, REAL *obs
         s[2] = (REAL)t0;
         s[3] = (REAL)c->mid_initial; /* midprice initial_state */
         int col = 4;
+        if (c->midprice == MBT_MID_HESTON) s[col++] = (REAL)c->heston_var0; /* initial_state = [[price, variance]]  midprice_models.py:346 */
         if (c->arrival == MBT_ARR_HAWKES) { /* initial_state = baseline_arrival_rate  arrival_models.py:103 */
             s[col++] = (REAL)c->arr_rate[0];
             s[col++] = (REAL)c->arr_rate[1];
@@ -165,7 +166,7 @@ static void FN(orc_reset)(FN(orc_env) * e, const mbt_reset_args *args, REAL *obs
  *   u (N,4): [arrival bid, arrival ask, fill bid, fill ask] uniforms;  z (N,): midprice normal.
  * This is the function the reference is compared with draw-for-draw (oracle/ref_shim.py).
  */
-static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REAL *u, const REAL *z,
+static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REAL *u, const REAL *z, const REAL *z2,
                                REAL *obs_out, REAL *rew_out, uint8_t *done_out) {
     const mbt_config *c = &e->cfg;
     const int D = e->D, A = e->A;
@@ -179,6 +180,9 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
     const REAL drift_dt = (REAL)(c->mid_drift * c->mid_step);      /* midprice_models.py:63 */
     const REAL vol_sqdt = (REAL)(c->mid_vol * sqrt(c->mid_step));  /* midprice_models.py:64,143 */
     const REAL sqdt = (REAL)sqrt(c->mid_step);
+    /* state columns after [cash, inventory, time, price]: Heston's variance first, then the arrival / impact model's */
+    const int mc = 4 + (c->midprice == MBT_MID_HESTON ? 1 : 0);
+    const REAL rho = (REAL)c->heston_corr, rho_c = (REAL)sqrt(1.0 - c->heston_corr * c->heston_corr);
     REAL p_arr[2] = {0, 0};
     if (c->arrival == MBT_ARR_POISSON) { /* intensity * step_size  arrival_models.py:56 */
         p_arr[0] = (REAL)(c->arr_rate[0] * c->arr_step);
@@ -225,7 +229,7 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
             /* ---- get_arrivals_and_fills                                ModelDynamics.py:127-131,169-172 */
             REAL fil[2];
             for (int j = 0; j < 2; ++j) {
-                REAL p = (c->arrival == MBT_ARR_HAWKES) ? cs[4 + j] * (REAL)c->arr_step /* arrival_models.py:123 */
+                REAL p = (c->arrival == MBT_ARR_HAWKES) ? cs[mc + j] * (REAL)c->arr_step /* arrival_models.py:123 */
                                                         : p_arr[j];
                 arr[j] = (u[i * 4 + j] < p) ? (REAL)1 : (REAL)0; /* unif < p   arrival_models.py:55-56 */
             }
@@ -265,11 +269,11 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
             REAL nu = a[0];
             REAL impact;
             if (c->impact == MBT_IMP_TEMP_PERM)
-                impact = (REAL)c->imp_temp * nu + cs[4]; /* price_impact_models.py:91-92 */
+                impact = (REAL)c->imp_temp * nu + cs[mc]; /* price_impact_models.py:91-92 */
             else if (c->impact == MBT_IMP_TEMP_TRANSIENT) /* price_impact_models.py:133-134 */
-                impact = (REAL)c->imp_temp * nu + (REAL)c->imp_transient * cs[4];
+                impact = (REAL)c->imp_temp * nu + (REAL)c->imp_transient * cs[mc];
             else if (c->impact == MBT_IMP_TRANSIENT) /* price_impact_models.py:174-175 */
-                impact = (REAL)c->imp_transient * cs[4];
+                impact = (REAL)c->imp_transient * cs[mc];
             else
                 impact = (REAL)c->imp_temp * FN(orc_pow)(nu, (REAL)c->imp_exponent); /* :55-56 */
             REAL px = S + impact;
@@ -305,20 +309,34 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
                    ((REAL)c->mid_jump * fa - (REAL)c->mid_jump * fb);
             break;
         }
+        case MBT_MID_HESTON: { /* midprice_models.py:354-369; weiners = (z, rho z + sqrt(1-rho^2) z2): the draw contract
+                                * for np.random.multivariate_normal(0, [[1, rho], [rho, 1]]) */
+            REAL v = cs[4], w_s = z[i], w_v = rho * z[i] + rho_c * z2[i];
+#if ORC_IS_F64
+            REAL vol = sqrt(v * (REAL)c->mid_step);
+#else
+            REAL vol = sqrtf(v * (REAL)c->mid_step);
+#endif
+            s[3] = (S + ((REAL)c->mid_drift * S) * (REAL)c->mid_step) + ((vol * S) * w_s);
+            REAL nv = (v + ((REAL)c->heston_speed * ((REAL)c->heston_level - v)) * (REAL)c->mid_step) +
+                      (((REAL)c->heston_volvol * vol) * w_v);
+            s[4] = nv < (REAL)0 ? -nv : (nv == (REAL)0 ? (REAL)0 : nv); /* np.abs */
+            break;
+        }
         default: /* MBT_MID_CONSTANT  midprice_models.py:32-33 */
             break;
         }
         if (c->arrival == MBT_ARR_HAWKES) { /* arrival_models.py:110-119 */
             for (int j = 0; j < 2; ++j) {
-                REAL lam = cs[4 + j];
-                s[4 + j] = (lam + (((REAL)c->hawkes_speed * ((REAL)c->arr_rate[j] - lam)) * (REAL)c->arr_step)) +
+                REAL lam = cs[mc + j];
+                s[mc + j] = (lam + (((REAL)c->hawkes_speed * ((REAL)c->arr_rate[j] - lam)) * (REAL)c->arr_step)) +
                            (REAL)c->hawkes_jump * arr[j];
             }
         }
         if (c->impact == MBT_IMP_TEMP_PERM) /* price_impact_models.py:88-89 */
-            s[4] = cs[4] + ((REAL)c->imp_perm * a[0]) * (REAL)c->imp_step;
+            s[mc] = cs[mc] + ((REAL)c->imp_perm * a[0]) * (REAL)c->imp_step;
         if (c->impact == MBT_IMP_TEMP_TRANSIENT || c->impact == MBT_IMP_TRANSIENT) /* price_impact_models.py:129-131,170-172 */
-            s[4] = (cs[4] - ((REAL)c->imp_resilience * cs[4]) * (REAL)c->imp_step) +
+            s[mc] = (cs[mc] - ((REAL)c->imp_resilience * cs[mc]) * (REAL)c->imp_step) +
                    ((REAL)c->imp_kernel * a[0]) * (REAL)c->imp_step;
 
         /* ---- reward_function.calculate(current_state, action, next_state, dones[0])  :108 */
@@ -335,8 +353,11 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
 }
 
 /* The step's random numbers from the Philox draw contract (include/mbt_philox.h). */
-static void FN(orc_fill_draws)(uint64_t seed, int64_t traj_offset, int64_t N, int64_t n_step, REAL *u, REAL *z) {
+static void FN(orc_fill_draws)(uint64_t seed, int64_t traj_offset, int64_t N, int64_t n_step, REAL *u, REAL *z, REAL *z2) {
     for (int64_t i = 0; i < N; ++i) {
+        if (z2) /* second normal of the step (Heston variance): the normal bits of the block of stream STEP2 */
+            z2[i] = FN(orc_normal)(mbt_normal_bits(mbt_draw(seed, (uint64_t)(traj_offset + i), (uint64_t)n_step, MBT_STREAM_STEP2)));
+        if (!u) continue;
         mbt_u32x4 r = mbt_draw(seed, (uint64_t)(traj_offset + i), (uint64_t)n_step, MBT_STREAM_STEP);
         u[i * 4 + 0] = (REAL)mbt_uniform_bits24(r.x) * (REAL)5.9604644775390625e-08; /* 2^-24 */
         u[i * 4 + 1] = (REAL)mbt_uniform_bits24(r.y) * (REAL)5.9604644775390625e-08;
@@ -349,10 +370,12 @@ static void FN(orc_fill_draws)(uint64_t seed, int64_t traj_offset, int64_t N, in
 static void FN(orc_step)(FN(orc_env) * e, const REAL *actions, REAL *obs_out, REAL *rew_out, uint8_t *done_out) {
     REAL *u = (REAL *)malloc(sizeof(REAL) * 4 * (size_t)e->N);
     REAL *z = (REAL *)malloc(sizeof(REAL) * (size_t)e->N);
-    FN(orc_fill_draws)(e->seed, e->cfg.traj_offset, e->N, e->n_step, u, z);
-    FN(orc_step_core)(e, actions, u, z, obs_out, rew_out, done_out);
+    REAL *z2 = (e->cfg.midprice == MBT_MID_HESTON) ? (REAL *)malloc(sizeof(REAL) * (size_t)e->N) : NULL;
+    FN(orc_fill_draws)(e->seed, e->cfg.traj_offset, e->N, e->n_step, u, z, z2);
+    FN(orc_step_core)(e, actions, u, z, z2, obs_out, rew_out, done_out);
     free(u);
     free(z);
+    free(z2);
 }
 
 #undef FN

@@ -40,6 +40,7 @@ def lib():
         L.orc_step.argtypes = [vp, vp, vp, vp, u8p]
         L.orc_step_draws.argtypes = [vp, vp, vp, vp, vp, vp, u8p]
         L.orc_draws.argtypes = [C.c_int, C.c_uint64, i64, i64, i64, vp, vp]
+        L.orc_draws2.argtypes = [C.c_int, C.c_uint64, i64, i64, i64, vp]
         L.orc_q0_draws.argtypes = [C.c_uint64, i64, i64, i64, i64, i64, vp]
         L.orc_get_state.argtypes = [vp, vp]
         L.orc_set_state.argtypes = [vp, vp]
@@ -140,6 +141,13 @@ def draws(precision, seed, traj_offset, N, n_step):
     z = np.empty((N,), dt)
     lib().orc_draws(precision, C.c_uint64(int(seed)), traj_offset, N, n_step, _ptr(u), _ptr(z))
     return u, z
+
+
+def draws2(precision, seed, traj_offset, N, n_step):
+    """z2 (N,): the second normal of env-step `n_step` (Heston variance) under the Philox draw contract."""
+    z2 = np.empty((N,), np.float64 if precision == _abi.MBT_F64 else np.float32)
+    lib().orc_draws2(precision, C.c_uint64(int(seed)), traj_offset, N, n_step, _ptr(z2))
+    return z2
 
 
 def q0_draws(seed, traj_offset, N, n_episode, lo, hi):

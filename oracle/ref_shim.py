@@ -8,6 +8,8 @@ duck-typed object that serves, for env-step n, exactly the numbers the Philox dr
     fill_probability_model.rng.uniform(size=(N,2)) -> u[:, 2:4]     fill_probability_models.py:33
     midprice_model.rng.normal(size=(N,1))          -> z[:, None]    midprice_models.py:64,143
     env.rng.integers(lo, hi, size=N)               -> reset-stream  TradingEnvironment.py:272
+    np.random.multivariate_normal(0, corr, size=N) -> (z, rho z + sqrt(1-rho^2) z2)   midprice_models.py:357 (Heston draws
+                                                      from the GLOBAL numpy generator; patched while the pair runs)
 so `reference.step()` and `orc_step_core_f64` can be compared trajectory by trajectory.
 
 Only usable where /root/reference exists (the build container); tools/make_golden.py turns its output
@@ -53,7 +55,15 @@ class DrawSource:
 
     def load_step(self):
         self.u, self.z = O.draws(_abi.MBT_F64, self.seed, self.traj_offset, self.N, self.n_step)
+        self.z2 = O.draws2(_abi.MBT_F64, self.seed, self.traj_offset, self.N, self.n_step)
         self.n_step += 1
+
+    def multivariate_normal(self, mean, cov, size=None):
+        """Stands in for np.random.multivariate_normal in HestonMidpriceModel.update (midprice_models.py:355-357): the
+        correlated pair of the draw contract, W_S = z, W_v = rho z + sqrt(1 - rho^2) z2."""
+        assert int(size) == self.N and np.all(np.asarray(mean) == 0)
+        rho = float(np.asarray(cov)[0, 1])
+        return np.stack([self.z, rho * self.z + np.sqrt(1.0 - rho * rho) * self.z2], axis=1)
 
 
 class InjectedRng:
@@ -110,6 +120,12 @@ def build_reference_env(spec):
         mid = MM.OuJumpMidpriceModel(mean_reversion_level=m["level"], mean_reversion_speed=m["speed"],
                                      volatility=m["volatility"], jump_size=m["jump"], initial_price=m["initial_price"],
                                      terminal_time=T, step_size=dt, num_trajectories=N)
+    elif m["kind"] == "heston":
+        mid = MM.HestonMidpriceModel(drift=m["drift"], volatility_mean_reversion_rate=m["speed"],
+                                     volatility_mean_reversion_level=m["level"], weiner_correlation=m["corr"],
+                                     volatility_of_volatility=m["volvol"], initial_price=m["initial_price"],
+                                     initial_variance=m["initial_variance"], terminal_time=T, step_size=dt,
+                                     num_trajectories=N)
     elif m["kind"] == "constant":
         mid = MM.ConstantMidpriceModel(initial_price=m["initial_price"], terminal_time=T, step_size=dt,
                                        num_trajectories=N)
@@ -195,7 +211,7 @@ def build_reference_env(spec):
 _DYN = {"limit": _abi.MBT_DYN_LIMIT, "speed": _abi.MBT_DYN_SPEED, "touch": _abi.MBT_DYN_AT_TOUCH,
         "limit_and_market": _abi.MBT_DYN_LIMIT_AND_MARKET}
 _MID = {"constant": _abi.MBT_MID_CONSTANT, "bm": _abi.MBT_MID_BM, "gbm": _abi.MBT_MID_GBM, "ou": _abi.MBT_MID_OU,
-        "bm_jump": _abi.MBT_MID_BM_JUMP, "ou_jump": _abi.MBT_MID_OU_JUMP}
+        "bm_jump": _abi.MBT_MID_BM_JUMP, "ou_jump": _abi.MBT_MID_OU_JUMP, "heston": _abi.MBT_MID_HESTON}
 _ARR = {"poisson": _abi.MBT_ARR_POISSON, "poisson_nonlinear": _abi.MBT_ARR_POISSON_NONLINEAR,
         "hawkes": _abi.MBT_ARR_HAWKES}
 _REW = {"pnl": _abi.MBT_REW_PNL, "rip": _abi.MBT_REW_RUNNING_INVENTORY_PENALTY, "cjmm": _abi.MBT_REW_CJ_MM,
@@ -224,6 +240,12 @@ def config_from_reference_env(spec, env, precision=_abi.MBT_F64, traj_offset=0):
     cfg.ou_level = float(getattr(mid, "mean_reversion_level", 0.0))
     cfg.ou_speed = float(getattr(mid, "mean_reversion_speed", 0.0))
     cfg.mid_jump = float(getattr(mid, "jump_size", 0.0))
+    if cfg.midprice == _abi.MBT_MID_HESTON:
+        cfg.heston_speed = float(mid.volatility_mean_reversion_rate)
+        cfg.heston_level = float(mid.volatility_mean_reversion_level)
+        cfg.heston_corr = float(mid.weiner_correlation)
+        cfg.heston_volvol = float(mid.volatility_of_volatility)
+        cfg.heston_var0 = float(mid.initial_state[0, 1])
     arr = md.arrival_model
     if arr is not None:
         cfg.arrival = _ARR[spec["arrival"]["kind"]]
@@ -330,6 +352,20 @@ def run_pair(spec, n_steps_run=None, action_seed=7, actions=None, n_episodes=1):
         actions = make_actions(spec, env, n_run * n_episodes, action_seed)
     out = dict(cfg=cfg, actions=actions, ref_obs=[], ref_rew=[], ref_done=[], orc_obs=[], orc_rew=[], orc_done=[],
                ref_reset=[], orc_reset=[])
+    global_mvn = np.random.multivariate_normal
+    np.random.multivariate_normal = source.multivariate_normal  # only HestonMidpriceModel.update calls it
+    try:
+        _run_episodes(spec, env, orc, source, actions, out, n_run, n_episodes)
+    finally:
+        np.random.multivariate_normal = global_mvn
+    for key in ("ref_obs", "ref_rew", "orc_obs", "orc_rew", "ref_reset", "orc_reset"):
+        out[key] = np.stack(out[key])
+    out["ref_state"] = np.array(env.state, float)
+    out["orc_state"] = orc.state
+    return out
+
+
+def _run_episodes(spec, env, orc, source, actions, out, n_run, n_episodes):
     import contextlib
     import io
     k = 0
@@ -351,8 +387,3 @@ def run_pair(spec, n_steps_run=None, action_seed=7, actions=None, n_episodes=1):
             out["orc_rew"].append(orr)
             out["orc_done"].append(od)
             k += 1
-    for key in ("ref_obs", "ref_rew", "orc_obs", "orc_rew", "ref_reset", "orc_reset"):
-        out[key] = np.stack(out[key])
-    out["ref_state"] = np.array(env.state, float)
-    out["orc_state"] = orc.state
-    return out

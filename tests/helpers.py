@@ -97,6 +97,10 @@ def build_facade_env(spec, **extra):
     elif m["kind"] == "ou_jump":
         mid = MM.OuJumpMidpriceModel(mean_reversion_level=m["level"], mean_reversion_speed=m["speed"],
                                      volatility=m["volatility"], jump_size=m["jump"], **kw)
+    elif m["kind"] == "heston":
+        mid = MM.HestonMidpriceModel(drift=m["drift"], volatility_mean_reversion_rate=m["speed"],
+                                     volatility_mean_reversion_level=m["level"], weiner_correlation=m["corr"],
+                                     volatility_of_volatility=m["volvol"], initial_variance=m["initial_variance"], **kw)
     else:
         mid = MM.ConstantMidpriceModel(**kw)
     arr = fill = imp = None

@@ -40,17 +40,23 @@ static void run(const mbt_config &c, uint64_t seed, int64_t n_step0, double t0, 
         for (int64_t i = 0; i < N; ++i) {
             T *row = state + i * D;
             Traj<T> s;
-            s.cash = row[0]; s.inv = row[1]; s.mid = row[3]; s.x0 = 0; s.x1 = 0;
-            if (c.arrival == MBT_ARR_HAWKES) { s.x0 = row[4]; s.x1 = row[5]; }
-            if (imp_has_state(c.impact)) s.x0 = row[4];
+            s.cash = row[0]; s.inv = row[1]; s.mid = row[3]; s.x0 = 0; s.x1 = 0; s.var = 0;
+            const int mc = 4 + (c.midprice == MBT_MID_HESTON ? 1 : 0); /* first column of the arrival / impact model */
+            if (c.midprice == MBT_MID_HESTON) s.var = row[4];
+            if (c.arrival == MBT_ARR_HAWKES) { s.x0 = row[mc]; s.x1 = row[mc + 1]; }
+            if (imp_has_state(c.impact)) s.x0 = row[mc];
             T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
             for (int j = 0; j < A; ++j) a[j] = denorm_action<T, V>(p, actions[((int64_t)k * N + i) * A + j], j);
             mbt_u32x4 r = mbt_draw_keyed(keys, (uint64_t)(c.traj_offset + i), (uint64_t)(n_step0 + k), MBT_STREAM_STEP);
             int clipped = 0;
-            T rw = step_one<T, V>(p, ck, s, a, r, q0_per_traj ? q0[i] : (T)q0_uniform, &clipped, fill_thr);
+            uint32_t nbits2 = 0; /* second normal (Heston): what second_normal_bits() computes in the kernels */
+            if (V::mid < 0 && c.midprice == MBT_MID_HESTON)
+                nbits2 = mbt_normal_bits(mbt_draw_keyed(keys, (uint64_t)(c.traj_offset + i), (uint64_t)(n_step0 + k), MBT_STREAM_STEP2));
+            T rw = step_one<T, V>(p, ck, s, a, r, q0_per_traj ? q0[i] : (T)q0_uniform, &clipped, fill_thr, nbits2);
             row[0] = s.cash; row[1] = s.inv; row[2] = ck.t_next; row[3] = s.mid;
-            if (c.arrival == MBT_ARR_HAWKES) { row[4] = s.x0; row[5] = s.x1; }
-            if (imp_has_state(c.impact)) row[4] = s.x0;
+            if (c.midprice == MBT_MID_HESTON) row[4] = s.var;
+            if (c.arrival == MBT_ARR_HAWKES) { row[mc] = s.x0; row[mc + 1] = s.x1; }
+            if (imp_has_state(c.impact)) row[mc] = s.x0;
             for (int d = 0; d < D; ++d) obs[((int64_t)k * N + i) * D + d] = norm_obs<T, V>(p, row[d], d);
             rew[(int64_t)k * N + i] = rw;
         }

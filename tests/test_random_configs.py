@@ -93,9 +93,21 @@ def random_fill(spec, rng):
     return spec
 
 
+def random_heston(spec, rng):
+    """Swap some (geometric) Brownian midprices for the Heston model (separate generator, like `random_fill`)."""
+    heston = rng.random() < 0.35
+    pars = dict(kind="heston", drift=float(rng.uniform(-0.2, 0.2)), speed=float(rng.uniform(0.5, 5.0)),
+                level=float(rng.uniform(0.01, 0.3)), corr=float(rng.choice([-0.8, -0.3, 0.0, 0.5, 1.0])),
+                volvol=float(rng.uniform(0.1, 1.5)), initial_variance=float(rng.uniform(0.0, 0.4)))
+    if heston and spec["midprice"]["kind"] in ("bm", "gbm"):
+        spec["midprice"] = dict(pars, initial_price=spec["midprice"]["initial_price"])
+        spec["normalise_obs"] = False  # undefined for Heston in the reference (bounds for one of two columns)
+    return spec
+
+
 def random_specs(n, seed):
-    rng, rng_fill = np.random.default_rng(seed), np.random.default_rng(seed + 1)
-    return [random_fill(random_spec(rng), rng_fill) for _ in range(n)]
+    rng, rng_fill, rng_mid = np.random.default_rng(seed), np.random.default_rng(seed + 1), np.random.default_rng(seed + 2)
+    return [random_heston(random_fill(random_spec(rng), rng_fill), rng_mid) for _ in range(n)]
 
 
 @pytest.mark.reference

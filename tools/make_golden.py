@@ -102,6 +102,22 @@ SPECS = {
     "rip_normalised": dict(N=87, n_steps=40, terminal_time=1.0, seed=1253, dynamics="limit",
                            reward=dict(kind="rip", phi=0.02, alpha=0.3), max_inventory=7, normalise_action=True,
                            normalise_obs=True, **AS),
+    # Heston stochastic-volatility midprice: two state columns (price, variance), a second normal per step
+    "heston": dict(N=91, n_steps=40, terminal_time=1.0, seed=1254, dynamics="limit", reward=dict(kind="pnl"),
+                   max_inventory=20, arrival=AS["arrival"], fill=AS["fill"],
+                   midprice=dict(kind="heston", drift=0.05, speed=3.0, level=0.04, corr=-0.8, volvol=0.6,
+                                 initial_price=100.0, initial_variance=0.04)),
+    "heston_hawkes": dict(N=53, n_steps=30, terminal_time=1.0, seed=1255, dynamics="limit",
+                          reward=dict(kind="rip", phi=0.01, alpha=0.1), max_inventory=20, fill=AS["fill"],
+                          arrival=dict(kind="hawkes", baseline=[30.0, 20.0], jump=20.0, speed=25.0),
+                          normalise_action=True,
+                          midprice=dict(kind="heston", drift=0.05, speed=3.0, level=0.04, corr=0.3, volvol=1.5,
+                                        initial_price=100.0, initial_variance=0.5)),
+    "heston_oe": dict(N=47, n_steps=30, terminal_time=1.0, seed=1256, dynamics="speed",
+                      impact=dict(kind="temp_perm", temp=0.01, perm=0.01),
+                      reward=dict(kind="cjoe", phi=0.01, alpha=0.001), initial_inventory=20, max_inventory=1000,
+                      midprice=dict(kind="heston", drift=0.0, speed=2.0, level=0.09, corr=1.0, volvol=0.3,
+                                    initial_price=50.0, initial_variance=0.09)),
     # fill functions whose probability is a BATCH reduction in the reference (np.max(depths, 0) over trajectories,
     # fill_probability_models.py:82,113)
     "triangular_fill": dict(N=77, n_steps=40, terminal_time=1.0, seed=1249, dynamics="limit", reward=dict(kind="pnl"),
