@@ -96,6 +96,11 @@ extern "C" {
  * MultiprocessTradingEnv. */
 #define MBT_FILL_TRIANGULAR 2 /* TriangularFillFunction  :68-91  p = max_side(1 - max_traj(depth)/max_fill_depth)        */
 #define MBT_FILL_POWER 3      /* PowerFillFunction       :94-123 p_side = 1/(1 + (multiplier*max_traj(depth))^exponent)  */
+/* ExogenousMmFillProbabilityModel :126-170: p = base * exp(-kappa * (depth - d)) beyond the exogenous best depth d of the
+ * side, 1 at or inside it.  The model owns two state columns (one per side) that come after the arrival model's; in the
+ * reference they never leave their initial value -- update() advances the two depth processes but never copies their
+ * state (:168-170) -- so d is a per-side constant and the two columns are constants of the observation. */
+#define MBT_FILL_EXOGENOUS_MM 4
 
 /* price_impact_models.py */
 #define MBT_IMP_NONE 0
@@ -167,6 +172,8 @@ typedef struct mbt_config {
     double fill_exponent;   /* ExponentialFillFunction.fill_exponent / PowerFillFunction.fill_exponent */
     double fill_max_depth;  /* TriangularFillFunction.max_fill_depth */
     double fill_multiplier; /* PowerFillFunction.fill_multiplier */
+    double fill_base;       /* ExogenousMmFillProbabilityModel.base_fill_probability */
+    double fill_depth0[2];  /* ... initial state of its (bid, ask) exogenous best-depth processes */
 
     /* price impact model */
     double imp_temp;     /* temporary_impact_coefficient */

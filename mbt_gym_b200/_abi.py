@@ -45,6 +45,7 @@ MBT_FILL_NONE = 0
 MBT_FILL_EXPONENTIAL = 1
 MBT_FILL_TRIANGULAR = 2
 MBT_FILL_POWER = 3
+MBT_FILL_EXOGENOUS_MM = 4
 FILLS_WITH_BATCH_REDUCTION = (MBT_FILL_TRIANGULAR, MBT_FILL_POWER)
 
 MBT_IMP_NONE = 0
@@ -115,6 +116,8 @@ class mbt_config(C.Structure):
         ("fill_exponent", C.c_double),
         ("fill_max_depth", C.c_double),
         ("fill_multiplier", C.c_double),
+        ("fill_base", C.c_double),
+        ("fill_depth0", C.c_double * 2),
         ("imp_temp", C.c_double),
         ("imp_perm", C.c_double),
         ("imp_exponent", C.c_double),

@@ -26,6 +26,8 @@ static inline int mbt_dims(const mbt_config *c, int32_t *A, int32_t *D, int32_t 
     }
     if (c->midprice == MBT_MID_HESTON) d += 1; /* (price, variance)  midprice_models.py:346 */
     if (c->arrival == MBT_ARR_HAWKES) d += 2;
+    if (c->fill == MBT_FILL_EXOGENOUS_MM && (c->dynamics == MBT_DYN_LIMIT || c->dynamics == MBT_DYN_LIMIT_AND_MARKET))
+        d += 2; /* the two exogenous best-depth columns  fill_probability_models.py:144-152 */
     if (c->impact == MBT_IMP_TEMP_PERM || c->impact == MBT_IMP_TEMP_TRANSIENT || c->impact == MBT_IMP_TRANSIENT) d += 1;
     if (A) *A = a;
     if (D) *D = d;
@@ -86,9 +88,17 @@ static inline int mbt_validate_config(const mbt_config *c, std::string &err) {
     } else {
         /* ModelDynamics.py:123-125,163-165,234-236: arrival (+ fill) models required */
         if (c->arrival < MBT_ARR_POISSON || c->arrival > MBT_ARR_HAWKES) { err = "limit-order dynamics need an arrival model"; return MBT_E_UNSUPPORTED; }
-        if (c->dynamics != MBT_DYN_AT_TOUCH && (c->fill < MBT_FILL_EXPONENTIAL || c->fill > MBT_FILL_POWER)) {
-            err = "limit-order dynamics need a fill probability model (exponential, triangular or power)";
+        if (c->dynamics != MBT_DYN_AT_TOUCH && (c->fill < MBT_FILL_EXPONENTIAL || c->fill > MBT_FILL_EXOGENOUS_MM)) {
+            err = "limit-order dynamics need a fill probability model (exponential, triangular, power or exogenous-MM)";
             return MBT_E_UNSUPPORTED;
+        }
+        {
+            int32_t D = 0;
+            mbt_dims(c, nullptr, &D, nullptr);
+            if (D > MBT_MAX_OBS_DIM) {
+                err = "Heston midprice + Hawkes arrivals + exogenous-MM fills need 9 observation columns; at most 8 are supported";
+                return MBT_E_UNSUPPORTED;
+            }
         }
         if (c->impact != MBT_IMP_NONE) { err = "price impact models only combine with speed dynamics"; return MBT_E_UNSUPPORTED; }
         if (c->reward == MBT_REW_CJ_OE) { err = "CjOeCriterion needs a 1-d action (reference fails too, RewardFunctions.py:66)"; return MBT_E_UNSUPPORTED; }
@@ -151,6 +161,9 @@ static inline StepParams<T> mbt_make_params(const mbt_config &c, double t0, int 
     p.hawkes_speed = (T)c.hawkes_speed; p.hawkes_jump = (T)c.hawkes_jump;
     p.neg_kappa = -(T)c.fill_exponent;
     p.fill_max_depth = (T)c.fill_max_depth; p.fill_mult = (T)c.fill_multiplier; p.fill_pexp = (T)c.fill_exponent;
+    p.fill_base = (T)c.fill_base; p.fill_depth0[0] = (T)c.fill_depth0[0]; p.fill_depth0[1] = (T)c.fill_depth0[1];
+    /* exp() overflows to +inf above ln(max finite value) of the arithmetic type */
+    p.exp_overflow = sizeof(T) == 8 ? (T)709.782712893384 : (T)88.72284;
     p.drift_dt = (T)(c.mid_drift * c.mid_step);
     p.vol_sqdt = (T)(c.mid_vol * std::sqrt(c.mid_step));
     p.sqdt = (T)std::sqrt(c.mid_step);

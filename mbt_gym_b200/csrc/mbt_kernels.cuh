@@ -183,6 +183,17 @@ __device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T
         row[4] = norm_obs<T, V>(p, s.x0, 4);
         d = 5;
     }
+    if (V::dyn < 0 && p.fill == MBT_FILL_EXOGENOUS_MM) {
+        /* the fill model's two columns (constants, see include/mbt_b200.h) come after the arrival model's; `d` is a
+         * runtime value here, so each is placed by a compile-time-indexed select chain (no dynamic register indexing) */
+        const T c0 = norm_obs<T, V>(p, p.fill_depth0[0], d), c1 = norm_obs<T, V>(p, p.fill_depth0[1], d + 1);
+#pragma unroll
+        for (int k = 4; k < MBT_MAX_OBS_DIM; ++k) {
+            if (k == d) row[k] = c0;
+            if (k == d + 1) row[k] = c1;
+        }
+        d += 2;
+    }
     if (V::norm < 0 && p.obs_select) { /* keep the selected columns, in order (gym/wrappers.py:30-38) */
         /* compaction without dynamically indexed registers (a runtime `row[j++]` would push the whole row into local
          * memory for every launch of the runtime-flag variants, selecting or not): output slot j takes column k when k is

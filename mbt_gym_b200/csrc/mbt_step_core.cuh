@@ -30,6 +30,7 @@ struct Variant {
     static constexpr int dyn = DYN, mid = MID, arr = ARR, imp = IMP, rew = REW, norm = NORM;
     /* action / observation widths when the model kinds are fixed (0 = runtime) */
     static constexpr int A = DYN < 0 ? 0 : (DYN == MBT_DYN_SPEED ? 1 : (DYN == MBT_DYN_LIMIT_AND_MARKET ? 4 : 2));
+    /* (the specialised variants are only selected for the exponential fill function, which owns no state column) */
     static constexpr int D = (DYN < 0 || ARR < 0 || IMP < 0) ? 0
                                                              : 4 + (MID == MBT_MID_HESTON ? 1 : 0) + (ARR == MBT_ARR_HAWKES ? 2 : 0) +
                                                                    ((IMP == MBT_IMP_TEMP_PERM || IMP == MBT_IMP_TEMP_TRANSIENT || IMP == MBT_IMP_TRANSIENT) ? 1 : 0);
@@ -71,6 +72,8 @@ struct StepParams {
     T arr_step, arr_step_2p24 /* arr_step * 2^24 */, arr_rate[2], hawkes_speed, hawkes_jump;
     T neg_kappa; /* -fill_exponent */
     T fill_max_depth, fill_mult, fill_pexp; /* Triangular: max_fill_depth;  Power: fill_multiplier, fill_exponent */
+    T fill_base, fill_depth0[2];            /* ExogenousMm: base_fill_probability, exogenous best depth (bid, ask) */
+    T exp_overflow;                         /* smallest argument whose exp() is +inf in numpy's arithmetic type */
     T drift_dt, vol_sqdt, sqdt, mid_drift, mid_vol, mid_step, ou_neg_speed, ou_speed, ou_level, mid_jump;
     T heston_speed, heston_level, heston_rho, heston_rho_c /* sqrt(1 - rho^2) */, heston_xi;
     T imp_temp, imp_perm, imp_exp, imp_step, imp_transient, imp_resilience, imp_kernel, half_spread;
@@ -143,6 +146,22 @@ MBT_HD void fill_batch_thresholds(const StepParams<T> &p, T m_bid, T m_ask, T *t
     }
 }
 
+/*
+ * ExogenousMmFillProbabilityModel._get_fill_probabilities, one side, times 2^24            fill_probability_models.py:160-163
+ *   (depths > d) * base * np.exp(-kappa * (depths - d)) + (depths <= d)
+ * evaluated term by term like numpy does (so an overflowing exp gives 0 * inf = NaN = "never filled", and a NaN depth
+ * gives 0 * NaN + 0 = NaN as well).
+ */
+template <typename T>
+MBT_HD T fill_exogenous_threshold(const StepParams<T> &p, T depth, int side) {
+    const T d = p.fill_depth0[side];
+    const T gt = depth > d ? (T)1 : (T)0, le = depth <= d ? (T)1 : (T)0;
+    const T x = p.neg_kappa * (depth - d);
+    /* exp(x) * 2^24; numpy's exp overflows to +inf where the clamped kernel exp stays finite */
+    const T e = (x >= p.exp_overflow) ? (T)INFINITY : mbt_exp2k_t(x, 24);
+    return (gt * p.fill_base) * e + le * (T)16777216.0;
+}
+
 /* reward_function.calculate for one row; (c0, q_cur, S0) = current_state, s = next_state. */
 template <typename T, class V>
 MBT_HD T reward_one(const StepParams<T> &p, const StepClock<T> &ck, T c0, T q_cur, T S0, const Traj<T> &s, const T *a, T q_init) {
@@ -211,6 +230,9 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
             if (fill_is_batch(fill)) { /* unif < p, p one value per side for the whole batch   :82,113 */
                 fil_b = (vb < fill_thr[0]) ? (T)1 : (T)0;
                 fil_a = (va < fill_thr[1]) ? (T)1 : (T)0;
+            } else if (fill == MBT_FILL_EXOGENOUS_MM) { /* :160-163 */
+                fil_b = (vb < fill_exogenous_threshold<T>(p, a[0], 0)) ? (T)1 : (T)0;
+                fil_a = (va < fill_exogenous_threshold<T>(p, a[1], 1)) ? (T)1 : (T)0;
             } else {
                 fil_b = (vb < mbt_exp2k_t(p.neg_kappa * a[0], 24)) ? (T)1 : (T)0;
                 fil_a = (va < mbt_exp2k_t(p.neg_kappa * a[1], 24)) ? (T)1 : (T)0;

@@ -83,3 +83,44 @@ class PowerFillFunction(FillProbabilityModel):
         cfg.fill = self.KIND
         cfg.fill_exponent = float(self.fill_exponent)
         cfg.fill_multiplier = float(self.fill_multiplier)
+
+
+class ExogenousMmFillProbabilityModel(FillProbabilityModel):
+    """Reference :126-170: beyond the exogenous best depth d of the side the fill probability decays as
+    `base_fill_probability * exp(-fill_exponent * (depth - d))`, at or inside it the order is always filled.  The model owns
+    two state columns, (d_bid, d_ask), initialised from the two `exogenous_best_depth_processes`.  In the reference those
+    columns never change: `update()` advances the two processes but never copies their state back (:168-170), so the depths
+    stay at the processes' initial values -- which is what the kernel implements (two constant observation columns).
+    The processes are used as descriptors only: initial state and bounds."""
+    KIND = _abi.MBT_FILL_EXOGENOUS_MM
+
+    def __init__(self, exogenous_best_depth_processes, fill_exponent=1.5, base_fill_probability=1.0, step_size=0.1,
+                 num_trajectories=1, seed=None):
+        assert len(exogenous_best_depth_processes) == 2, "exogenous_best_depth_processes must be length 2 (bid and ask)"
+        assert all(p.initial_state.shape[1] > 0 for p in exogenous_best_depth_processes), \
+            "Exogenous best depth processes must have a state of at least size 1."
+        if any(p.initial_state.shape[1] != 1 for p in exogenous_best_depth_processes):
+            raise NotImplementedError("exogenous best-depth processes with more than one state column have no CUDA "
+                                      "implementation (the reference cannot compare their state with the depths either)")
+        self.exogenous_best_depth_processes = tuple(exogenous_best_depth_processes)
+        self.fill_exponent = fill_exponent
+        self.base_fill_probability = base_fill_probability
+        bid, ask = self.exogenous_best_depth_processes
+        super().__init__(np.concatenate([bid.min_value, ask.min_value], axis=1),
+                         np.concatenate([bid.max_value, ask.max_value], axis=1), step_size, 0.0,
+                         np.concatenate([bid.initial_state, ask.initial_state], axis=1), num_trajectories, seed)
+
+    def _get_fill_probabilities(self, depths):
+        """Host helper for analysis only; same expression as the reference with the (constant) exogenous depths."""
+        depths, best = np.asarray(depths), self.initial_state
+        return (depths > best) * self.base_fill_probability * np.exp(-self.fill_exponent * (depths - best)) + (depths <= best)
+
+    @property
+    def max_depth(self):
+        return -np.log(0.01) / self.fill_exponent + np.max(self.exogenous_best_depth_processes[0].max_value)
+
+    def _flatten(self, cfg):
+        cfg.fill = self.KIND
+        cfg.fill_exponent = float(self.fill_exponent)
+        cfg.fill_base = float(self.base_fill_probability)
+        cfg.fill_depth0[0], cfg.fill_depth0[1] = (float(x) for x in self.initial_state[0])

@@ -39,6 +39,8 @@ static int orc_dims(const mbt_config *c, int32_t *A, int32_t *D, int32_t *S) {
     }
     if (c->midprice == MBT_MID_HESTON) d += 1;   /* (price, variance)  midprice_models.py:346 */
     if (c->arrival == MBT_ARR_HAWKES) d += 2;    /* arrival_models.py:99-103 */
+    if (c->fill == MBT_FILL_EXOGENOUS_MM && (c->dynamics == MBT_DYN_LIMIT || c->dynamics == MBT_DYN_LIMIT_AND_MARKET))
+        d += 2; /* exogenous best depths (bid, ask)  fill_probability_models.py:144-152 */
     if (c->impact == MBT_IMP_TEMP_PERM || c->impact == MBT_IMP_TEMP_TRANSIENT || c->impact == MBT_IMP_TRANSIENT)
         d += 1; /* one state column: price_impact_models.py:79-83,119-127,162-170 */
     *A = a;

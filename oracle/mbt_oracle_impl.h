@@ -148,6 +148,12 @@ static void FN(orc_reset)(FN(orc_env) * e, const mbt_reset_args *args, REAL *obs
             s[col++] = (REAL)c->arr_rate[0];
             s[col++] = (REAL)c->arr_rate[1];
         }
+        if (c->fill == MBT_FILL_EXOGENOUS_MM && (c->dynamics == MBT_DYN_LIMIT || c->dynamics == MBT_DYN_LIMIT_AND_MARKET)) {
+            /* initial_state = the two depth processes' initial states; the reference never updates these columns
+             * (fill_probability_models.py:144-152,168-170) */
+            s[col++] = (REAL)c->fill_depth0[0];
+            s[col++] = (REAL)c->fill_depth0[1];
+        }
         if (c->impact == MBT_IMP_TEMP_PERM) s[col++] = (REAL)0; /* price_impact_models.py:83 */
         if (c->impact == MBT_IMP_TEMP_TRANSIENT || c->impact == MBT_IMP_TRANSIENT)
             s[col++] = (REAL)c->imp_initial; /* initial_transient_impact   price_impact_models.py:124,167 */
@@ -238,8 +244,19 @@ static void FN(orc_step_core)(FN(orc_env) * e, const REAL *actions_in, const REA
                 fil[1] = a[1];
             } else {
                 for (int j = 0; j < 2; ++j) { /* unif < exp(-kappa * depth)   fill_probability_models.py:33,58 */
-                    REAL p = (c->fill == MBT_FILL_EXPONENTIAL) ? FN(orc_exp)(-(REAL)c->fill_exponent * a[j])
-                                                               : p_fill_batch[j];
+                    REAL p;
+                    if (c->fill == MBT_FILL_EXPONENTIAL) {
+                        p = FN(orc_exp)(-(REAL)c->fill_exponent * a[j]);
+                    } else if (c->fill == MBT_FILL_EXOGENOUS_MM) {
+                        /* (depths > d) * base * exp(-kappa * (depths - d)) + (depths <= d), d = the model's (constant)
+                         * state column of the side                      fill_probability_models.py:160-163 */
+                        REAL d = cs[mc + (c->arrival == MBT_ARR_HAWKES ? 2 : 0) + j];
+                        REAL x = -(REAL)c->fill_exponent * (a[j] - d);
+                        REAL ex = (x >= (ORC_IS_F64 ? (REAL)709.782712893384 : (REAL)88.72284)) ? (REAL)INFINITY : FN(orc_exp)(x);
+                        p = ((REAL)(a[j] > d) * (REAL)c->fill_base) * ex + (REAL)(a[j] <= d);
+                    } else {
+                        p = p_fill_batch[j];
+                    }
                     fil[j] = (u[i * 4 + 2 + j] < p) ? (REAL)1 : (REAL)0;
                 }
             }

@@ -145,7 +145,13 @@ def build_reference_env(spec):
                                         num_trajectories=N)
     f = spec.get("fill")
     if f:
-        if f.get("kind", "exp") == "triangular":
+        if f.get("kind", "exp") == "exogenous":
+            depth_models = tuple(MM.OuMidpriceModel(mean_reversion_level=d0, mean_reversion_speed=0.1, volatility=0.05,
+                                                    initial_price=d0, terminal_time=T, step_size=dt, num_trajectories=N)
+                                 for d0 in f["best_depths"])
+            fill = FM.ExogenousMmFillProbabilityModel(depth_models, fill_exponent=f["fill_exponent"],
+                                                      base_fill_probability=f["base"], step_size=dt, num_trajectories=N)
+        elif f.get("kind", "exp") == "triangular":
             fill = FM.TriangularFillFunction(max_fill_depth=f["max_fill_depth"], step_size=dt, num_trajectories=N)
         elif f.get("kind", "exp") == "power":
             fill = FM.PowerFillFunction(fill_exponent=f["fill_exponent"], fill_multiplier=f["fill_multiplier"],
@@ -258,7 +264,10 @@ def config_from_reference_env(spec, env, precision=_abi.MBT_F64, traj_offset=0):
     fill = md.fill_probability_model
     if fill is not None:
         cfg.fill = {"exp": _abi.MBT_FILL_EXPONENTIAL, "triangular": _abi.MBT_FILL_TRIANGULAR,
-                    "power": _abi.MBT_FILL_POWER}[spec["fill"].get("kind", "exp")]
+                    "power": _abi.MBT_FILL_POWER, "exogenous": _abi.MBT_FILL_EXOGENOUS_MM}[spec["fill"].get("kind", "exp")]
+        if cfg.fill == _abi.MBT_FILL_EXOGENOUS_MM:
+            cfg.fill_base = float(fill.base_fill_probability)
+            cfg.fill_depth0[0], cfg.fill_depth0[1] = (float(x) for x in fill.initial_state[0])
         cfg.fill_exponent = float(getattr(fill, "fill_exponent", 0.0))
         cfg.fill_max_depth = float(getattr(fill, "max_fill_depth", 0.0))
         cfg.fill_multiplier = float(getattr(fill, "fill_multiplier", 0.0))

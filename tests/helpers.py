@@ -117,6 +117,12 @@ def build_facade_env(spec, **extra):
     f = spec.get("fill")
     if f and f.get("kind", "exp") == "triangular":
         fill = FM.TriangularFillFunction(max_fill_depth=f["max_fill_depth"], step_size=dt, num_trajectories=N)
+    elif f and f.get("kind", "exp") == "exogenous":
+        depth_models = tuple(MM.OuMidpriceModel(mean_reversion_level=d0, mean_reversion_speed=0.1, volatility=0.05,
+                                                initial_price=d0, terminal_time=T, step_size=dt, num_trajectories=N)
+                             for d0 in f["best_depths"])
+        fill = FM.ExogenousMmFillProbabilityModel(depth_models, fill_exponent=f["fill_exponent"],
+                                                  base_fill_probability=f["base"], step_size=dt, num_trajectories=N)
     elif f and f.get("kind", "exp") == "power":
         fill = FM.PowerFillFunction(fill_exponent=f["fill_exponent"], fill_multiplier=f["fill_multiplier"], step_size=dt,
                                     num_trajectories=N)

@@ -79,8 +79,12 @@ def random_spec(rng):
 def random_fill(spec, rng):
     """Swap the exponential fill function of some limit-order specs for a batch-reduced one (separate generator, so the
     sequence of specs drawn by `random_spec` stays what it was)."""
-    pick = rng.choice(["exp", "exp", "triangular", "power"])
+    pick = rng.choice(["exp", "exp", "triangular", "power", "exogenous"])
     if "fill" not in spec or pick == "exp":
+        return spec
+    if pick == "exogenous":
+        spec["fill"] = dict(kind="exogenous", fill_exponent=float(rng.uniform(0.5, 3.0)), base=float(rng.uniform(0.3, 1.0)),
+                            best_depths=[float(rng.uniform(0.0, 1.0)), float(rng.uniform(0.0, 1.0))])
         return spec
     if pick == "triangular":
         mfd = float(rng.uniform(0.5, 2.0))

@@ -132,6 +132,16 @@ SPECS = {
                                         midprice=AS["midprice"], arrival=AS["arrival"],
                                         fill=dict(kind="power", fill_exponent=2.0, fill_multiplier=0.8),
                                         depth_range=[0.0, 3.0]),
+    # exogenous-market-maker fill model: two (constant) best-depth columns in the observation
+    "exogenous_fill": dict(N=71, n_steps=40, terminal_time=1.0, seed=1257, dynamics="limit", reward=dict(kind="pnl"),
+                           max_inventory=8, midprice=AS["midprice"], arrival=AS["arrival"],
+                           fill=dict(kind="exogenous", fill_exponent=1.5, base=0.8, best_depths=[0.5, 0.4])),
+    "exogenous_fill_hawkes_normalised": dict(N=43, n_steps=30, terminal_time=1.0, seed=1258, dynamics="limit",
+                                             reward=dict(kind="rip", phi=0.01, alpha=0.1), max_inventory=6,
+                                             midprice=AS["midprice"],
+                                             arrival=dict(kind="hawkes", baseline=[30.0, 20.0], jump=20.0, speed=25.0),
+                                             fill=dict(kind="exogenous", fill_exponent=2.0, base=1.0, best_depths=[0.3, 0.6]),
+                                             normalise_action=True, normalise_obs=True),
     # two episodes back to back: RNG stream continues, reset redraws inventories
     "two_episodes": dict(N=59, n_steps=30, terminal_time=1.0, seed=1244, dynamics="limit",
                          reward=dict(kind="cjmm", phi=0.01, alpha=0.001), max_inventory=20,
