@@ -103,7 +103,8 @@ def random_heston(spec, rng):
     pars = dict(kind="heston", drift=float(rng.uniform(-0.2, 0.2)), speed=float(rng.uniform(0.5, 5.0)),
                 level=float(rng.uniform(0.01, 0.3)), corr=float(rng.choice([-0.8, -0.3, 0.0, 0.5, 1.0])),
                 volvol=float(rng.uniform(0.1, 1.5)), initial_variance=float(rng.uniform(0.0, 0.4)))
-    if heston and spec["midprice"]["kind"] in ("bm", "gbm"):
+    nine_columns = spec.get("fill", {}).get("kind") == "exogenous" and spec.get("arrival", {}).get("kind") == "hawkes"
+    if heston and spec["midprice"]["kind"] in ("bm", "gbm") and not nine_columns:  # at most 8 observation columns
         spec["midprice"] = dict(pars, initial_price=spec["midprice"]["initial_price"])
         spec["normalise_obs"] = False  # undefined for Heston in the reference (bounds for one of two columns)
     return spec
