@@ -433,6 +433,11 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_TRAFFIC_BYTES.get((args.workload, args.precision)) if N == N_PER_GPU else None,
                          "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/ (cold cache)",
+                         "frac_note": "achieved counts ALGORITHMIC bytes (SURVEY 8d); the state columns (2*S of the A+2S+O+1 "
+                                      "scalars per env-step) stay resident in the 126 MB L2 between steps, so DRAM moves only "
+                                      "`traffic` bytes per launch and frac can exceed 1; dram_frac = traffic / duration / peak",
+                         "dram_frac": (NCU_DRAM_TRAFFIC_BYTES[(args.workload, args.precision)] / (mean_kernel_ms * 1e-3) / 1e9 / peak
+                                       if (N == N_PER_GPU and (args.workload, args.precision) in NCU_DRAM_TRAFFIC_BYTES) else None),
                          "peak_source": peak_src, "kernel": "mbt_step_kernel",
                          "size_matched_copy_us": copy_b2b_us if not len(ktimes) else copy_us,
                          "frac_of_size_matched_copy": ((copy_b2b_us if not len(ktimes) else copy_us) * 1e-3 / mean_kernel_ms) if copy_us else None,
