@@ -81,3 +81,41 @@ def test_kernel_core_f32_matches_oracle_f32(hostsim, name):
         obs, rew, done, oobs, orew = run_hostsim(hostsim, g, _abi.MBT_F32, variant)
         assert_same(obs, oobs, exact=True, what=f"{name} f32 obs (variant {variant})")
         assert_same(rew, orew, exact=True, what=f"{name} f32 rew (variant {variant})")
+
+
+@pytest.mark.parametrize("precision", [_abi.MBT_F64, _abi.MBT_F32])
+def test_kernel_core_matches_oracle_on_random_configurations(hostsim, precision):
+    """The same randomly drawn configurations the GPU test steps (tests/test_random_configs.py), through the host compile of
+    the kernel core: every model kind, normalisation flag, start time and inventory mode against the oracle, bit-for-bit,
+    in both precisions and through both the selected variant and the generic one."""
+    from oracle import ref_shim as R  # make_actions only (no reference needed)
+    from tests.helpers import build_facade_env
+    from tests.test_random_configs import random_specs
+
+    dt = np.float64 if precision == _abi.MBT_F64 else np.float32
+    for spec in random_specs(60, 424242):
+        env = build_facade_env(spec, precision="float64" if precision == _abi.MBT_F64 else "float32")
+        cfg = env._build_config()
+        acts = np.ascontiguousarray(R.make_actions(spec, env, spec["n_steps"], 11), dtype=dt)
+        for variant in sorted({0, hostsim.hostsim_variant_of(C.byref(cfg))}):
+            orc = O.OracleEnv(cfg)
+            orc.seed(spec["seed"])
+            orc.reset()
+            state = orc.state.copy()
+            q0 = np.ascontiguousarray(state[:, 1].copy())
+            t0 = float(cfg.start_time)  # (the float32 state column holds a rounded copy; the clock itself is a double)
+            N, D, n = orc.N, orc.D, spec["n_steps"]
+            n_run = int(round((cfg.terminal_time - t0) / cfg.step_size))  # a late start shortens the episode
+            n_run = max(1, min(n, n_run))
+            obs = np.empty((n_run, N, D), dt)
+            rew = np.empty((n_run, N), dt)
+            dones = np.zeros(n_run, np.uint8)
+            rc = hostsim.hostsim_run(C.byref(cfg), variant, spec["seed"], 0, t0, t0, int(cfg.q0_mode == _abi.MBT_Q0_UNIFORM_INT),
+                                     cfg.q0_const, state.ctypes.data, q0.ctypes.data, n_run, acts.ctypes.data,
+                                     obs.ctypes.data, rew.ctypes.data, dones.ctypes.data)
+            assert rc == 0, spec
+            for k in range(n_run):
+                o, r, d = orc.step(acts[k])
+                assert_same(obs[k], o, what=f"{spec} variant {variant} obs step {k}")
+                assert_same(rew[k], r, what=f"{spec} variant {variant} rew step {k}")
+                assert bool(dones[k]) == d
