@@ -71,3 +71,33 @@ def test_numpy_port_reproduces_notebook_golden():
                 break
     got = [2 * np.mean(acts), R_.mean(), R_.std(), obs[:, 1].mean(), obs[:, 1].std()]
     np.testing.assert_allclose(got, [1.49177, 64.872139, 6.692567, 0.201, 2.893544], rtol=0, atol=6e-7)
+
+
+def _space_arrays(space):
+    return [np.asarray(getattr(space, k)) for k in ("low", "high") if hasattr(space, k)]
+
+
+def test_spaces_and_host_attributes_equal_the_reference_for_every_configuration():
+    """What an SB3 policy sees before the first step: observation / action spaces (and their un-normalised originals),
+    max_cash, step size, start time, `initial_state` -- equal to the reference's for every fixture specification and for
+    the randomly drawn configurations (all model kinds incl. Heston, Hawkes, the four fill models, the four dynamics)."""
+    from tests.test_random_configs import random_specs
+
+    specs = list(SPECS.items()) + [(f"random{i}", s) for i, s in enumerate(random_specs(40, 20260925))]
+    for name, spec in specs:
+        ref, mine = R.build_reference_env(spec), build_facade_env(spec)
+        for attr in ("observation_space", "action_space", "original_observation_space", "original_action_space"):
+            if not hasattr(ref, attr):
+                assert not hasattr(mine, attr) or attr.startswith("original"), (name, attr)
+                continue
+            a, b = _space_arrays(getattr(ref, attr)), _space_arrays(getattr(mine, attr))
+            assert len(a) == len(b), (name, attr)
+            for x, y in zip(a, b):
+                assert x.shape == y.shape and x.dtype == y.dtype, (name, attr, x.shape, y.shape, x.dtype, y.dtype)
+                np.testing.assert_array_equal(x, y, err_msg=f"{name} {attr}")
+        assert mine.max_cash == ref.max_cash and mine.max_inventory == ref.max_inventory, name
+        assert mine.step_size == ref.step_size and mine.n_steps == ref.n_steps and mine.terminal_time == ref.terminal_time
+        assert mine._get_start_time() == ref._get_start_time(), name
+        assert mine.num_trajectories == ref.num_trajectories
+        if not isinstance(spec.get("initial_inventory", 0), list):  # (random inventories come from different generators)
+            np.testing.assert_array_equal(mine.initial_state, ref.initial_state, err_msg=f"{name} initial_state")
