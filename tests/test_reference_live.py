@@ -101,3 +101,57 @@ def test_spaces_and_host_attributes_equal_the_reference_for_every_configuration(
         assert mine.num_trajectories == ref.num_trajectories
         if not isinstance(spec.get("initial_inventory", 0), list):  # (random inventories come from different generators)
             np.testing.assert_array_equal(mine.initial_state, ref.initial_state, err_msg=f"{name} initial_state")
+
+
+def test_wrappers_equal_the_reference_wrappers_on_the_same_env_outputs():
+    """gym/wrappers.py is host-side glue: fed the same environment outputs, the facade's wrappers must return exactly
+    what the reference's return (including NormaliseASObservation's asymmetric reset / step maps)."""
+    R.import_reference()
+    import gym  # the stub under oracle/gym_stub
+    from mbt_gym.gym import wrappers as RefW
+
+    from mbt_gym_b200 import spaces as my_spaces
+    from mbt_gym_b200.gym import wrappers as MyW
+
+    rng = np.random.default_rng(5)
+    low, high = np.float32([-2160.0, -20.0, 0.0, 92.0]), np.float32([2160.0, 20.0, 1.0, 108.0])
+    frames = [rng.uniform(low, high, size=(7, 4)) for _ in range(4)]
+    rewards = [rng.normal(size=7) for _ in range(4)]
+
+    class Reward:
+        per_step_inventory_aversion, terminal_inventory_aversion = 0.01, 0.5
+
+    def make_env(box_cls):
+        class DummyEnv:
+            observation_space = box_cls(low=low, high=high)
+            reward_function = Reward()
+            spec = None
+
+            def __init__(self):
+                self.k = 0
+
+            def reset(self):
+                self.k = 0
+                return frames[0].copy()
+
+            def step(self, action):
+                self.k += 1
+                done = self.k == 3
+                return frames[self.k].copy(), rewards[self.k].copy(), (done if box_cls is gym.spaces.box.Box else np.full(7, done)), {}
+
+        return DummyEnv()
+
+    for ref_cls, my_cls, kwargs in [(RefW.ReduceStateSizeWrapper, MyW.ReduceStateSizeWrapper, {}),
+                                    (RefW.ReduceStateSizeWrapper, MyW.ReduceStateSizeWrapper, {"list_of_state_indices": [3, 0]}),
+                                    (RefW.NormaliseASObservation, MyW.NormaliseASObservation, {}),
+                                    (RefW.RemoveTerminalRewards, MyW.RemoveTerminalRewards, {})]:
+        ref, mine = ref_cls(make_env(gym.spaces.box.Box), **kwargs), my_cls(make_env(my_spaces.Box), **kwargs)
+        if hasattr(ref, "observation_space") and ref_cls is not RefW.RemoveTerminalRewards:
+            np.testing.assert_array_equal(ref.observation_space.low, mine.observation_space.low)
+            np.testing.assert_array_equal(ref.observation_space.high, mine.observation_space.high)
+        np.testing.assert_array_equal(ref.reset(), mine.reset())
+        for _ in range(3):
+            (o1, r1, d1, _i1), (o2, r2, d2, _i2) = ref.step(None), mine.step(None)
+            np.testing.assert_array_equal(o1, o2, err_msg=ref_cls.__name__)
+            np.testing.assert_array_equal(r1, r2, err_msg=ref_cls.__name__)
+            assert bool(np.asarray(d1).reshape(-1)[0]) == bool(np.asarray(d2).reshape(-1)[0])
