@@ -64,6 +64,14 @@ class FixedSpreadAgent(Agent):
         return _fixed_policy(self._row())
 
 
+class HumanAgent(Agent):
+    """Asks for the two half-spreads on the terminal at every step (:45-49); single-trajectory play only."""
+
+    def get_action(self, state):
+        prompt = "Current state is {}. How large do you want to set {} half spread? "
+        return np.array([float(input(prompt.format(state, side))) for side in ("midprice-bid", "ask-midprice")])
+
+
 class AvellanedaStoikovAgent(Agent):
     """Avellaneda & Stoikov (2008) quotes: reservation-price shift q*gamma*sigma^2*(T-t) around a spread
     gamma*sigma^2*(T-t) + (2/gamma)*log(1+gamma/kappa)   (:52-83)."""

@@ -92,3 +92,33 @@ def test_unsupported_models_fail_loudly():
         MyProcess()._flatten(_abi.new_config())
     with pytest.raises(NotImplementedError):
         MyProcess().update(None, None, None)
+
+
+def test_sb_agent_adapter_duck_types_a_stable_baselines_model():
+    """SbAgent (reference agents/SbAgent.py:8-26) needs only predict / action_space / env / learn from the model."""
+    from mbt_gym_b200.agents.SbAgent import SbAgent
+
+    class Space:
+        shape = (2,)
+
+    class Env:
+        num_trajectories = 5
+
+    class Model:
+        action_space, env, learned = Space(), Env(), 0
+
+        def predict(self, obs, deterministic=False):
+            assert deterministic and obs.shape == (5, 2)
+            return np.stack([obs[:, 0] + 1, obs[:, 1] * 2], axis=1).reshape(-1), None  # flat, like some SB3 policies
+
+        def learn(self, total_timesteps):
+            self.learned += total_timesteps
+
+    model = Model()
+    agent = SbAgent(model, reduced_training_indices=[1, 2])
+    state = np.arange(20.0).reshape(5, 4)
+    act = agent.get_action(state)
+    assert act.shape == (5, 2)
+    np.testing.assert_array_equal(act, np.stack([state[:, 1] + 1, state[:, 2] * 2], axis=1))
+    agent.train(123)
+    assert model.learned == 123 and agent.num_trajectories == 5
