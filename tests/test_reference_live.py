@@ -155,3 +155,53 @@ def test_wrappers_equal_the_reference_wrappers_on_the_same_env_outputs():
             np.testing.assert_array_equal(o1, o2, err_msg=ref_cls.__name__)
             np.testing.assert_array_equal(r1, r2, err_msg=ref_cls.__name__)
             assert bool(np.asarray(d1).reshape(-1)[0]) == bool(np.asarray(d2).reshape(-1)[0])
+
+
+def test_generate_trajectory_helper_equals_the_reference_helper_on_the_same_env():
+    """gym/helpers/generate_trajectory.py (the canonical rollout loop every notebook uses) is host-side glue: on the same
+    environment outputs and the same agent it must record exactly what the reference's helper records -- with and
+    without log-probabilities, for several trajectories and for one."""
+    import torch
+
+    R.import_reference()
+    from mbt_gym.gym.helpers.generate_trajectory import generate_trajectory as ref_generate
+
+    from mbt_gym_b200.gym.helpers.generate_trajectory import generate_trajectory as my_generate
+
+    class Space:
+        def __init__(self, d):
+            self.shape = (d,)
+
+    class DummyEnv:
+        n_steps = 6
+
+        def __init__(self, n):
+            self.num_trajectories, self.observation_space, self.action_space = n, Space(4), Space(2)
+            self.rng = np.random.default_rng(11)
+
+        def seed(self, seed=None):
+            self.rng = np.random.default_rng(seed)
+
+        def reset(self):
+            self.k = 0
+            return self.rng.normal(size=(self.num_trajectories, 4))
+
+        def step(self, action):
+            self.k += 1
+            obs = self.rng.normal(size=(self.num_trajectories, 4)) + action.sum()
+            rew = self.rng.normal(size=(self.num_trajectories,))
+            done = self.k == self.n_steps
+            return obs, rew, (np.full(self.num_trajectories, done) if self.num_trajectories > 1 else done), {}
+
+    class DummyAgent:
+        def get_action(self, obs, include_log_probs=False):
+            a = np.stack([obs[:, 0] * 0.5, obs[:, 1] - 1.0], axis=1)
+            return (a, torch.from_numpy(a * 0.1)) if include_log_probs else a
+
+    for n in (5, 1):
+        for with_lp in (False, True):
+            ref = ref_generate(DummyEnv(n), DummyAgent(), seed=3, include_log_probs=with_lp)
+            mine = my_generate(DummyEnv(n), DummyAgent(), seed=3, include_log_probs=with_lp)
+            assert len(ref) == len(mine) == (4 if with_lp else 3)
+            for a, b in zip(ref, mine):
+                np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
