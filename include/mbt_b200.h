@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MBT_ABI_VERSION 2
+#define MBT_ABI_VERSION 3
 
 /* error codes */
 #define MBT_OK 0
@@ -52,6 +52,7 @@ extern "C" {
 #define MBT_E_STATE (-3)
 #define MBT_E_UNSUPPORTED (-4)
 #define MBT_E_NOMEM (-5)
+#define MBT_E_NCCL (-6)
 
 /* where a caller buffer lives */
 #define MBT_MEM_HOST 0   /* pageable or pinned host memory; copies are inside the call      */
@@ -119,6 +120,8 @@ extern "C" {
 /* initial inventory (TradingEnvironment.py:270-281) */
 #define MBT_Q0_CONST 0       /* int, or the value a callable returned on the host            */
 #define MBT_Q0_UNIFORM_INT 1 /* tuple (lo, hi): rng.integers(lo, hi) per trajectory          */
+#define MBT_Q0_PER_TRAJ 2    /* a callable that returned one value per trajectory (:275-279 assigns whatever the
+                                callable returns to the inventory column); only through mbt_reset_args          */
 
 #define MBT_MAX_ACTION_DIM 4
 #define MBT_MAX_OBS_DIM 8
@@ -220,6 +223,7 @@ typedef struct mbt_reset_args {
     int32_t _pad;
     double q0_const;
     int64_t q0_lo, q0_hi;
+    const double *q0_values; /* MBT_Q0_PER_TRAJ: HOST pointer to num_trajectories float64 values (else ignored) */
 } mbt_reset_args;
 
 /* On-device policies for the fused rollout (mbt_gym/agents/BaselineAgents.py).  The host facade computes
@@ -282,6 +286,19 @@ int mbt_sync(mbt_env *env);
  * that policy lives in the Python facade, here 0 is just a key.) */
 int mbt_seed(mbt_env *env, uint64_t seed);
 
+/* The key and the counters of the Philox draw contract (include/mbt_philox.h): env-steps and resets since mbt_seed.
+ * mbt_set_counters lets a caller that re-creates a handle (a model attribute was edited between episodes) continue the
+ * random streams where the old handle stopped, like the reference's generators do. */
+int mbt_get_seed(mbt_env *env, uint64_t *seed);
+int mbt_set_counters(mbt_env *env, int64_t steps_since_seed, int64_t episodes_since_seed);
+
+/* Replace the handle's configuration IN PLACE, keeping device state, clock and counters: the reference reads its Python
+ * attributes at every step, so `env.max_inventory = 5` or `env.reward_function.per_step_inventory_aversion = 0.1` take
+ * effect at the next step (TradingEnvironment.py:283-297, RewardFunctions.py:60).  Allowed: everything that keeps
+ * num_trajectories, traj_offset, precision, io_precision, the action / observation widths and the set of state columns;
+ * anything else returns MBT_E_STATE (destroy and create a new handle between episodes instead). */
+int mbt_reconfigure(mbt_env *env, const mbt_config *cfg);
+
 /* Start an episode.  args may be NULL (config defaults).  obs_out may be NULL. */
 int mbt_reset(mbt_env *env, const mbt_reset_args *args, void *obs_out, int mem);
 
@@ -318,8 +335,14 @@ int mbt_checkpoint_load(mbt_env *env, const void *host_buf, size_t bytes);
  * after the replays continue the same streams.  Requirements inside the captured region: MBT_MEM_DEVICE buffers only
  * (host-buffer calls synchronise), the handle already on the capturing stream (mbt_set_stream before capture), a
  * constant start time / initial-inventory mode, and the region must span whole episodes (the clock values are baked).
+ * If the handle was used before the capture (warm-up resets / steps), call mbt_prepare_capture first, OUTSIDE the capture:
+ * it moves the counters consumed so far into the device base eagerly, so the launches baked into the graph count from
+ * zero; from then on eager calls also advance the device base (one extra one-thread kernel per call), which keeps eager
+ * steps and graph replays interleavable in any order without reusing a draw index.  A first captured launch on a handle
+ * with non-zero host counters and no mbt_prepare_capture fails with MBT_E_STATE instead of silently skipping indices.
  * (No reference counterpart: the reference has no device path.)
  */
+int mbt_prepare_capture(mbt_env *env);
 int mbt_fold_counters(mbt_env *env);
 
 /* Trajectories whose inventory or cash was clipped since mbt_create (the reference prints the arrays
@@ -347,6 +370,37 @@ typedef struct mbt_record {
     int64_t steps_capacity;
 } mbt_record;
 int mbt_rollout_record(mbt_env *env, const mbt_policy *policy, mbt_summary *summary_out, const mbt_record *record, int mem);
+
+/*
+ * Multi-GPU: one process per GPU, every process owns a contiguous shard of the trajectories
+ * (mbt_config.traj_offset = global id of its first one).  A GROUP joins the handles of all ranks through NCCL
+ * (libnccl.so.2 is loaded with dlopen at mbt_group_create; no NCCL = MBT_E_UNSUPPORTED, single-GPU use never needs it).
+ * Replaces mbt_gym/gym/MultiprocessTradingEnv.py:72-116 (process fan-out over pipes, results concatenated by
+ * flatten_multi :112-116).  All collectives run on device buffers, on the handle's stream (summary, batch-reduced fills)
+ * or on the group's own stream behind an event (the optional gather), never through host memory.
+ *
+ *   mbt_group_unique_id   rank 0 creates the 128-byte NCCL id; the caller ships it to the other ranks (any transport)
+ *   mbt_group_create      ncclCommInitRank; exchanges the shard sizes (all-gather of one int64 per rank)
+ *   mbt_group_rollout     mbt_rollout on the local shard, then ncclAllReduce(sum) of the device-resident summary on the
+ *                         handle's stream: summary_out is the summary of ALL trajectories of the group.  returns_local
+ *                         (N_local,) and returns_all (sum of all shard sizes, global-id order) are DEVICE buffers or NULL;
+ *                         the all-gather of returns is enqueued on the group's stream after the rollout, so it overlaps
+ *                         whatever the caller enqueues next on the handle's stream (the next episode); mbt_group_wait
+ *                         makes the handle's stream (and the host, if `host_sync`) wait for it.
+ *   mbt_group_summary     all-reduce of a summary the caller already holds (e.g. from mbt_rollout_record)
+ * With a group attached, mbt_step of the batch-reduced fill models (MBT_FILL_TRIANGULAR / MBT_FILL_POWER) all-reduces
+ * (max) the deepest quotes of the shards before the step, so `np.max(depths, 0)` runs over the WHOLE batch and results
+ * do not depend on the shard layout.
+ */
+#define MBT_GROUP_ID_BYTES 128
+int mbt_group_unique_id(void *id_out);
+int mbt_group_create(mbt_env *env, const void *id, int rank, int world);
+int mbt_group_destroy(mbt_env *env);
+int mbt_group_info(mbt_env *env, int32_t *rank, int32_t *world, int64_t *total_trajectories);
+int mbt_group_rollout(mbt_env *env, const mbt_policy *policy, mbt_summary *summary_out, void *returns_local_out,
+                      void *returns_all_out);
+int mbt_group_summary(mbt_env *env, const mbt_summary *local, mbt_summary *global_out);
+int mbt_group_wait(mbt_env *env, int host_sync);
 
 /* Per-call statistics for bench.py: number of kernel launches issued by this handle so far, and the
  * device time (ms, CUDA events on the handle's stream) of the most recent step kernel when enabled. */

@@ -5,7 +5,7 @@ Kept in one place so the product binding (`_lib.py`) and the test oracle's loade
 """
 import ctypes as C
 
-MBT_ABI_VERSION = 2
+MBT_ABI_VERSION = 3
 
 MBT_OK = 0
 MBT_E_INVALID_ARG = -1
@@ -13,6 +13,7 @@ MBT_E_CUDA = -2
 MBT_E_STATE = -3
 MBT_E_UNSUPPORTED = -4
 MBT_E_NOMEM = -5
+MBT_E_NCCL = -6
 
 MBT_MEM_HOST = 0
 MBT_MEM_DEVICE = 1
@@ -63,6 +64,7 @@ MBT_REW_EXP_UTILITY = 4
 
 MBT_Q0_CONST = 0
 MBT_Q0_UNIFORM_INT = 1
+MBT_Q0_PER_TRAJ = 2
 
 MBT_POL_FIXED = 0
 MBT_POL_AVELLANEDA_STOIKOV = 1
@@ -154,7 +156,11 @@ class mbt_reset_args(C.Structure):
         ("q0_const", C.c_double),
         ("q0_lo", C.c_int64),
         ("q0_hi", C.c_int64),
+        ("q0_values", C.c_void_p),
     ]
+
+
+MBT_GROUP_ID_BYTES = 128
 
 
 class mbt_policy(C.Structure):

@@ -4,6 +4,7 @@ The product has NO CPU fallback: if the library is missing or no CUDA device is 
 """
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -18,7 +19,9 @@ ABI_SYMBOLS = [
     "mbt_seed", "mbt_reset", "mbt_step", "mbt_get_state", "mbt_set_state", "mbt_get_clock", "mbt_get_clip_count",
     "mbt_reward_eval", "mbt_rollout", "mbt_rollout_record", "mbt_get_launch_count", "mbt_enable_timing", "mbt_get_kernel_times",
     "mbt_host_alloc", "mbt_host_alloc_near", "mbt_host_free", "mbt_checkpoint_size", "mbt_checkpoint_save",
-    "mbt_checkpoint_load", "mbt_fold_counters",
+    "mbt_checkpoint_load", "mbt_fold_counters", "mbt_prepare_capture", "mbt_get_seed", "mbt_set_counters", "mbt_reconfigure",
+    "mbt_group_unique_id", "mbt_group_create", "mbt_group_destroy", "mbt_group_info", "mbt_group_rollout", "mbt_group_summary",
+    "mbt_group_wait",
 ]
 
 _lib = None
@@ -71,6 +74,17 @@ def load():
     L.mbt_checkpoint_save.argtypes = [vp, vp, C.c_size_t]
     L.mbt_checkpoint_load.argtypes = [vp, vp, C.c_size_t]
     L.mbt_fold_counters.argtypes = [vp]
+    L.mbt_prepare_capture.argtypes = [vp]
+    L.mbt_get_seed.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.mbt_set_counters.argtypes = [vp, C.c_int64, C.c_int64]
+    L.mbt_reconfigure.argtypes = [vp, cfgp]
+    L.mbt_group_unique_id.argtypes = [vp]
+    L.mbt_group_create.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.mbt_group_destroy.argtypes = [vp]
+    L.mbt_group_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i64p]
+    L.mbt_group_rollout.argtypes = [vp, C.POINTER(_abi.mbt_policy), C.POINTER(_abi.mbt_summary), vp, vp]
+    L.mbt_group_summary.argtypes = [vp, C.POINTER(_abi.mbt_summary), C.POINTER(_abi.mbt_summary)]
+    L.mbt_group_wait.argtypes = [vp, C.c_int]
     if L.mbt_abi_version() != _abi.MBT_ABI_VERSION:
         raise ImportError(f"libmbt_b200.so ABI {L.mbt_abi_version()} != binding ABI {_abi.MBT_ABI_VERSION}")
     _lib = L
@@ -88,18 +102,26 @@ def config_dims(cfg):
     return a.value, d.value, s.value
 
 
-class PinnedArray:
-    """A numpy array backed by page-locked memory from mbt_host_alloc (freed with the object)."""
+class _PinnedBlock:
+    """Page-locked host memory (mbt_host_alloc_near) whose lifetime is tied to the arrays that view it: numpy arrays made
+    by `array()` -- and every view, slice or `torch.from_numpy` of them -- keep a reference to the block, and the memory
+    is returned to CUDA only when the last of them is gone.  Nothing a caller still holds is ever freed or reused."""
 
-    def __init__(self, shape, dtype, device=0):
-        self.shape = tuple(int(x) for x in np.atleast_1d(shape))
-        self.dtype = np.dtype(dtype)
-        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+    def __init__(self, nbytes, device=0):
+        self.nbytes = max(int(nbytes), 1)
         p = C.c_void_p()
-        _check(load().mbt_host_alloc_near(max(nbytes, 1), int(device), C.byref(p)))
+        _check(load().mbt_host_alloc_near(self.nbytes, int(device), C.byref(p)))
         self._ptr = p
-        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
-        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def array(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        shape = tuple(int(x) for x in np.atleast_1d(shape))
+        assert int(np.prod(shape)) * dtype.itemsize <= self.nbytes
+        self.__array_interface__ = {"shape": shape, "typestr": dtype.str, "data": (self._ptr.value, False), "version": 3}
+        try:
+            return np.asarray(self)
+        finally:
+            del self.__array_interface__
 
     def __del__(self):
         p = getattr(self, "_ptr", None)
@@ -109,6 +131,53 @@ class PinnedArray:
             except Exception:
                 pass
             self._ptr = None
+
+
+def _refcount(obj):
+    return sys.getrefcount(obj)
+
+
+class PinnedPool:
+    """Output buffers for the host path: pinned blocks that are handed out again only when NO array viewing them is alive
+    (CPython reference counts), so `step()` / `reset()` results behave like the reference's fresh `.copy()` arrays -- never
+    overwritten behind the caller's back -- while the steady state (a caller that consumes each step's arrays before the
+    next few steps, as SB3's rollout buffer and `generate_trajectory` do) reuses the same few page-locked buffers and the
+    device-to-host copy stays a direct DMA.  A caller that keeps everything makes the pool grow up to `max_bytes`; beyond
+    that `get` returns None and the caller allocates ordinary (pageable) arrays."""
+
+    def __init__(self, device=0, max_bytes=1 << 31):
+        self.device, self.max_bytes, self.total = int(device), int(max_bytes), 0
+        self._blocks = []
+        holder = [object()]
+        self._idle_refs = _refcount(holder[0])  # list slot + call arguments: what an unused block shows in `get`
+
+    def get(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        blocks = self._blocks
+        for i in range(len(blocks)):
+            if blocks[i].nbytes == max(nbytes, 1) and _refcount(blocks[i]) <= self._idle_refs:
+                return blocks[i].array(shape, dtype)
+        if self.total + nbytes > self.max_bytes:
+            return None
+        blocks.append(_PinnedBlock(nbytes, self.device))
+        self.total += nbytes
+        return blocks[-1].array(shape, dtype)
+
+    def clear(self):
+        """Forget the blocks (those still viewed by caller arrays stay alive until the arrays go)."""
+        self._blocks = []
+        self.total = 0
+
+
+class PinnedArray:
+    """A numpy array backed by page-locked memory from mbt_host_alloc (freed when the last view of it is gone)."""
+
+    def __init__(self, shape, dtype, device=0):
+        self.shape = tuple(int(x) for x in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.array = _PinnedBlock(nbytes, device).array(self.shape, self.dtype)
 
 
 def _addr(x):
@@ -170,6 +239,62 @@ class NativeEnv:
         """Last call inside a CUDA-graph captured episode: moves the step / episode counters to the device so every
         replay draws fresh random numbers (include/mbt_b200.h, mbt_fold_counters)."""
         _check(load().mbt_fold_counters(self._h))
+
+    def prepare_capture(self):
+        """Before a CUDA-graph capture on a handle that was already used: counters consumed so far move to the device."""
+        _check(load().mbt_prepare_capture(self._h))
+
+    def get_seed(self):
+        v = C.c_uint64()
+        _check(load().mbt_get_seed(self._h, C.byref(v)))
+        return v.value
+
+    def set_counters(self, n_step, n_episode):
+        _check(load().mbt_set_counters(self._h, int(n_step), int(n_episode)))
+
+    def reconfigure(self, cfg):
+        """Swap the configuration in place (state, clock and counters kept); MbtError(MBT_E_STATE) if the new config
+        changes the shape of the device state."""
+        _check(load().mbt_reconfigure(self._h, C.byref(cfg)))
+        self.cfg = cfg
+        dout = C.c_int32()
+        _check(load().mbt_config_obs_out_dim(C.byref(cfg), C.byref(dout)))
+        self.Dout = dout.value
+
+    # -- group of handles over NCCL (one process per GPU)
+    @staticmethod
+    def group_unique_id():
+        buf = (C.c_char * _abi.MBT_GROUP_ID_BYTES)()
+        _check(load().mbt_group_unique_id(buf))
+        return bytes(buf)
+
+    def group_create(self, unique_id, rank, world):
+        assert len(unique_id) == _abi.MBT_GROUP_ID_BYTES
+        buf = (C.c_char * _abi.MBT_GROUP_ID_BYTES).from_buffer_copy(unique_id)
+        _check(load().mbt_group_create(self._h, buf, int(rank), int(world)))
+
+    def group_destroy(self):
+        _check(load().mbt_group_destroy(self._h))
+
+    def group_info(self):
+        r, w, t = C.c_int32(), C.c_int32(), C.c_int64()
+        _check(load().mbt_group_info(self._h, C.byref(r), C.byref(w), C.byref(t)))
+        return dict(rank=r.value, world=w.value, total_trajectories=t.value)
+
+    def group_rollout(self, policy, returns_local=None, returns_all=None):
+        """Fused rollout of the local shard + NCCL all-reduce of the summary (+ all-gather of returns, overlapped);
+        returns the summary of ALL trajectories of the group.  Buffers are device tensors / pointers."""
+        summary = _abi.mbt_summary()
+        _check(load().mbt_group_rollout(self._h, C.byref(policy), C.byref(summary), _addr(returns_local), _addr(returns_all)))
+        return summary
+
+    def group_summary(self, local):
+        out = _abi.mbt_summary()
+        _check(load().mbt_group_summary(self._h, C.byref(local), C.byref(out)))
+        return out
+
+    def group_wait(self, host_sync=True):
+        _check(load().mbt_group_wait(self._h, int(bool(host_sync))))
 
     # -- hot path
     def reset(self, obs_out=None, args=None, mem=_abi.MBT_MEM_HOST):

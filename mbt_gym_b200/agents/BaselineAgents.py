@@ -4,7 +4,8 @@ Agents are CALLERS of the hot path: `get_action(obs)` runs on the host exactly a
 rollout loops (`generate_trajectory`, SB3-style loops) work unchanged.  Each agent additionally offers
 `to_policy(env)`: the same rule as an `mbt_policy` for the fused on-device rollout (`env.rollout_summary`), where the
 per-step host round trip disappears.  Policy constants are formed with the same Python expressions in both places, so
-the device reproduces the host agent bit-for-bit.
+the device reproduces the host agent bit-for-bit -- for environments with raw observations
+(`normalise_observation_space=False`); the state-dependent policies refuse normalised ones (`_require_raw_observations`).
 """
 import warnings
 from copy import deepcopy
@@ -17,6 +18,16 @@ from ..gym.ModelDynamics import LimitOrderModelDynamics, TradinghWithSpeedModelD
 from ..gym.TradingEnvironment import TradingEnvironment
 from ..rewards.RewardFunctions import CjMmCriterion, PnL
 from .Agent import Agent
+
+
+def _require_raw_observations(env, agent):
+    """The closed-form agents read inventory and time straight from the observation (`state[:, INVENTORY_INDEX]`,
+    `state[:, TIME_INDEX]`, reference :64-65,117-119,205), i.e. they are written for
+    `normalise_observation_space=False` (what the reference's notebooks construct).  The on-device policy reads the raw
+    state, so with normalised observations it would NOT reproduce `get_action(env.step(...)[0])`: refuse instead."""
+    if getattr(env, "normalise_observation_space_", False):
+        raise ValueError(f"{type(agent).__name__}.to_policy needs an environment built with "
+                         "normalise_observation_space=False: the agent's formula reads raw inventory and time")
 
 
 def _fixed_policy(row):
@@ -104,6 +115,7 @@ class AvellanedaStoikovAgent(Agent):
         return action
 
     def to_policy(self, env=None):
+        _require_raw_observations(env or self.env, self)
         pol = _abi.mbt_policy()
         pol.kind = _abi.MBT_POL_AVELLANEDA_STOIKOV
         pol.as_gamma = float(self.risk_aversion)
@@ -203,6 +215,7 @@ class CarteaJaimungalMmAgent(Agent):
         env = env or self.env
         if self.inventory_neutral:
             return _fixed_policy(self.risk_neutral_action[0])
+        _require_raw_observations(env, self)
         times = self.decision_times(env)
         cols = 2 * self.max_inventory + 1
         table = np.empty((len(times), cols, 2))
@@ -248,6 +261,7 @@ class CarteaJaimungalOeAgent(Agent):
 
     def to_policy(self, env=None):
         env = env or self.env
+        _require_raw_observations(env, self)
         times = CarteaJaimungalMmAgent.decision_times(self, env)
         self._table = np.ascontiguousarray([[self._speed(t)] for t in times], dtype=float)
         pol = _abi.mbt_policy()

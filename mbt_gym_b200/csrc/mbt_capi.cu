@@ -5,6 +5,7 @@
  * kernels of mbt_kernels.cuh on the handle's stream.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <sched.h>
 
 #include <algorithm>
@@ -84,8 +85,18 @@ struct mbt_env {
     size_t clocks_cap = 0;    /* bytes */
     void *d_table = nullptr;
     size_t table_cap = 0;
-    double *d_block_sums = nullptr, *h_block_sums = nullptr;
+    double *d_block_sums = nullptr;
     int block_sums_cap = 0;
+    double *d_summary = nullptr, *h_summary = nullptr; /* MBT_SUMMARY_DOUBLES each: device-resident fold, pinned mirror */
+    unsigned int *d_roll_ticket = nullptr;
+
+    /* group of handles (one per rank / GPU) joined through NCCL: mbt_group_* */
+    void *comm = nullptr; /* ncclComm_t */
+    int g_rank = 0, g_world = 1;
+    std::vector<long long> g_counts; /* shard sizes of all ranks */
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_rollout = nullptr, ev_gather = nullptr;
+    bool gather_pending = false;
 
     /* clock (uniform over trajectories) */
     double t = 0, t0 = 0;
@@ -258,12 +269,38 @@ static bool stream_is_capturing(mbt_env *e) {
     return st == cudaStreamCaptureStatusActive;
 }
 
-/* kernels read the device-resident counter base once the handle has been used under stream capture (or folded) */
-static const unsigned long long *counter_base_for_launch(mbt_env *e) {
-    if (!e->device_counters && stream_is_capturing(e)) e->device_counters = true;
-    return e->device_counters ? e->d_counter_base : nullptr;
+/*
+ * Counters of the draw contract.  Effective counter of a launch = host counter baked into its arguments + device-resident
+ * base (read by the kernel).  Plain eager use: base unused (NULL), host counters advance.  Once the handle has been used
+ * under stream capture (or mbt_prepare_capture / mbt_fold_counters was called) it is in DEVICE-COUNTER mode: captured
+ * launches bake host counters that count from the start of the captured region; mbt_fold_counters (captured last) adds the
+ * region's totals to the base at every replay; and every EAGER call folds its own advance into the base right after its
+ * launch (fold_eager), keeping the host counters at zero outside a capture -- so graph replays and eager calls can be
+ * interleaved in any order without reusing or skipping a draw index.
+ */
+static int counter_base_for_launch(mbt_env *e, const unsigned long long **out) {
+    if (!e->device_counters && stream_is_capturing(e)) {
+        if (e->n_step != 0 || e->n_episode != 0)
+            return fail(MBT_E_STATE,
+                        "the handle was used before this stream capture began: call mbt_prepare_capture() (env.prepare_capture()) "
+                        "before capturing, so the graph's baked draw counters start from zero");
+        e->device_counters = true;
+    }
+    *out = e->device_counters ? e->d_counter_base : nullptr;
+    return MBT_OK;
 }
 
+/* device-counter mode, eager call: move what the call just consumed into the device base (one-thread kernel) */
+static int fold_eager(mbt_env *e) {
+    if (!e->device_counters || stream_is_capturing(e)) return MBT_OK;
+    if (e->n_step == 0 && e->n_episode == 0) return MBT_OK;
+    mbt_fold_counters_kernel<<<1, 1, 0, e->stream>>>(e->d_counter_base, (unsigned long long)e->n_step, (unsigned long long)e->n_episode);
+    CU(cudaGetLastError());
+    e->launches += 1;
+    e->n_step = 0;
+    e->n_episode = 0;
+    return MBT_OK;
+}
 
 /* MBT_PDL=0 disables programmatic dependent launch of consecutive step kernels (default: on) */
 static bool use_pdl() {
@@ -331,7 +368,10 @@ static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<
     g.n_step = (unsigned long long)e->n_step;
     g.clipped = e->d_clipped;
     g.fill_thr = (const T *)e->d_fill_thr;
-    g.counter_base = counter_base_for_launch(e);
+    {
+        int rcb = counter_base_for_launch(e, &g.counter_base);
+        if (rcb) return rcb;
+    }
     if (g.counter_base) allow_pdl = false; /* the base is written by a kernel: order behind it */
     const bool vec = rows_vector_aligned<E>(e, g.actions, g.obs);
     switch (variant_of(c)) {
@@ -343,6 +383,8 @@ static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<
     e->launches += 1;
     return MBT_OK;
 }
+
+static int group_allreduce_max_u64(mbt_env *e, unsigned long long *dev, int count);
 
 /* the batch reduction of the quoted depths (mbt_fill_batch_kernel) over ALL rows of the action matrix */
 template <typename T, typename E>
@@ -357,10 +399,25 @@ static int launch_fill_batch(mbt_env *e, const StepParams<T> &p, const void *act
     const unsigned blocks = std::min<unsigned>(grid_for(e->N), (unsigned)e->fill_blocks);
     /* rows of 2 or 4 elements whose base is aligned to a 2-element vector: one vector load per row */
     const bool vec = (e->A == 2 || e->A == 4) && ((uintptr_t)actions % (2 * sizeof(E))) == 0;
+    if (e->comm) {
+        /* group of handles: np.max(depths, 0) runs over the trajectories of ALL ranks -- shard maxima (keys), NCCL
+         * all-reduce (max) on the handle's stream, thresholds from the global maxima */
+        if (vec)
+            mbt_fill_batch_kernel<T, E, true, false><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
+        else
+            mbt_fill_batch_kernel<T, E, false, false><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
+        CU(cudaGetLastError());
+        int rc = group_allreduce_max_u64(e, g.cells, 2);
+        if (rc) return rc;
+        mbt_fill_finalize_kernel<T><<<1, 1, 0, e->stream>>>(p, g.cells, g.thr);
+        CU(cudaGetLastError());
+        e->launches += 2;
+        return MBT_OK;
+    }
     if (vec)
-        mbt_fill_batch_kernel<T, E, true><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
+        mbt_fill_batch_kernel<T, E, true, true><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
     else
-        mbt_fill_batch_kernel<T, E, false><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
+        mbt_fill_batch_kernel<T, E, false, true><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
     CU(cudaGetLastError());
     e->launches += 1;
     return MBT_OK;
@@ -391,7 +448,7 @@ static int do_step_device(mbt_env *e, const void *actions, void *obs, void *rew,
     if (rc) return rc;
     advance_clock(e, t_next);
     if (done_out) *done_out = (uint8_t)ck.done;
-    return MBT_OK;
+    return fold_eager(e);
 }
 
 /* host-buffer path: MBT_HOST_PATH=zerocopy lets the kernel access pinned host memory directly; default = DMA pipeline */
@@ -458,7 +515,7 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
     CU(cudaStreamSynchronize(e->stream));
     advance_clock(e, t_next);
     if (done_out) *done_out = (uint8_t)ck.done;
-    return MBT_OK;
+    return fold_eager(e);
 }
 
 template <typename T, typename E>
@@ -469,17 +526,32 @@ static int do_reset_device(mbt_env *e, const mbt_reset_args *args, void *obs) {
     const double q0_const = args ? args->q0_const : c.q0_const;
     const int64_t lo = args ? args->q0_lo : c.q0_lo, hi = args ? args->q0_hi : c.q0_hi;
     if (q0_mode == MBT_Q0_UNIFORM_INT && !(hi > lo)) return fail(MBT_E_INVALID_ARG, "initial inventory range needs hi > lo");
+    if (q0_mode != MBT_Q0_CONST && q0_mode != MBT_Q0_UNIFORM_INT && q0_mode != MBT_Q0_PER_TRAJ)
+        return fail(MBT_E_INVALID_ARG, "unknown q0_mode");
     if (!(t0 >= 0.0) || !(t0 < c.terminal_time))
         return fail(MBT_E_INVALID_ARG, "Start time is not within (0, env.terminal_time)."); /* TradingEnvironment.py:267 */
+    if (q0_mode == MBT_Q0_PER_TRAJ) {
+        /* one initial inventory per trajectory (a callable returned an array): converted once to the state type and
+         * uploaded into the q0 column, where the rewards read it (RewardFunctions.py:72,111) and reset takes it from */
+        if (!args || !args->q0_values) return fail(MBT_E_INVALID_ARG, "MBT_Q0_PER_TRAJ needs mbt_reset_args.q0_values");
+        if (stream_is_capturing(e)) return fail(MBT_E_STATE, "per-trajectory initial inventories are uploaded from the host: not capturable");
+        std::vector<T> q0((size_t)e->N);
+        for (long long i = 0; i < e->N; ++i) q0[(size_t)i] = (T)args->q0_values[i];
+        CU(cudaMemcpyAsync(e->col[5], q0.data(), (size_t)e->N * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream)); /* `q0` is a pageable temporary */
+    }
     ResetArgs<T, E> g;
-    g.p = mbt_make_params<T>(c, t0, q0_mode == MBT_Q0_UNIFORM_INT, q0_const);
+    g.p = mbt_make_params<T>(c, t0, q0_mode != MBT_Q0_CONST, q0_const);
     g.st = dev_state<T>(e);
     g.obs = (E *)obs;
     g.n = e->N;
     g.seed = e->seed;
     g.traj_offset = (unsigned long long)c.traj_offset;
     g.n_episode = (unsigned long long)e->n_episode;
-    g.counter_base = counter_base_for_launch(e);
+    {
+        int rcb = counter_base_for_launch(e, &g.counter_base);
+        if (rcb) return rcb;
+    }
     g.cash0 = (T)c.initial_cash;
     g.t0 = (T)t0;
     g.mid0 = (T)c.mid_initial;
@@ -499,9 +571,9 @@ static int do_reset_device(mbt_env *e, const mbt_reset_args *args, void *obs) {
     e->k = 0;
     e->n_episode += 1;
     e->started = true;
-    e->q0_per_traj = (q0_mode == MBT_Q0_UNIFORM_INT);
+    e->q0_per_traj = (q0_mode != MBT_Q0_CONST);
     e->q0_uniform = q0_const;
-    return MBT_OK;
+    return fold_eager(e);
 }
 
 /* (arithmetic type, caller-buffer element type) dispatch: (double,double), (double,float) or (float,float) */
@@ -561,6 +633,8 @@ int mbt_host_free(void *ptr) {
     return MBT_OK;
 }
 
+static void group_teardown(mbt_env *e);
+
 int mbt_destroy(mbt_env *e) {
     if (!e) return MBT_OK;
     cudaSetDevice(e->device);
@@ -580,7 +654,10 @@ int mbt_destroy(mbt_env *e) {
     cudaFree(e->d_clocks);
     cudaFree(e->d_table);
     cudaFree(e->d_block_sums);
-    cudaFreeHost(e->h_block_sums);
+    cudaFree(e->d_summary);
+    cudaFreeHost(e->h_summary);
+    cudaFree(e->d_roll_ticket);
+    group_teardown(e);
     for (auto ev : e->ev0) cudaEventDestroy(ev);
     for (auto ev : e->ev1) cudaEventDestroy(ev);
     for (int i = 0; i < MBT_PIPE_CHUNKS; ++i) {
@@ -652,15 +729,20 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     CUB(cudaMemsetAsync(e->d_clipped, 0, sizeof(unsigned long long), e->stream));
     CUB(cudaMalloc((void **)&e->d_counter_base, 2 * sizeof(unsigned long long)));
     CUB(cudaMemsetAsync(e->d_counter_base, 0, 2 * sizeof(unsigned long long), e->stream));
-    if (needs_fill_batch(*cfg)) {
-        e->fill_blocks = std::max(1, e->sm_count * fill_blocks_per_sm()); /* every block ends in 3 same-address atomics */
-        CUB(cudaMalloc(&e->d_fill_partial, 2 * sizeof(unsigned long long)));
-        CUB(cudaMemsetAsync(e->d_fill_partial, 0, 2 * sizeof(unsigned long long), e->stream));
-        CUB(cudaMalloc(&e->d_fill_thr, 2 * sizeof(double)));
-        CUB(cudaMalloc((void **)&e->d_fill_ticket, sizeof(unsigned int)));
-        CUB(cudaMemsetAsync(e->d_fill_thr, 0, 2 * sizeof(double), e->stream));
-        CUB(cudaMemsetAsync(e->d_fill_ticket, 0, sizeof(unsigned int), e->stream));
-    }
+    /* batch-reduction cells (a few bytes; allocated for every handle: mbt_reconfigure may switch the fill function) */
+    e->fill_blocks = std::max(1, e->sm_count * fill_blocks_per_sm()); /* every block ends in 3 same-address atomics */
+    CUB(cudaMalloc(&e->d_fill_partial, 2 * sizeof(unsigned long long)));
+    CUB(cudaMemsetAsync(e->d_fill_partial, 0, 2 * sizeof(unsigned long long), e->stream));
+    CUB(cudaMalloc(&e->d_fill_thr, 2 * sizeof(double)));
+    CUB(cudaMalloc((void **)&e->d_fill_ticket, sizeof(unsigned int)));
+    CUB(cudaMemsetAsync(e->d_fill_thr, 0, 2 * sizeof(double), e->stream));
+    CUB(cudaMemsetAsync(e->d_fill_ticket, 0, sizeof(unsigned int), e->stream));
+    /* episode summary: folded on the device by the rollout kernel, mirrored to pinned host memory on demand */
+    CUB(cudaMalloc((void **)&e->d_summary, MBT_SUMMARY_DOUBLES * sizeof(double)));
+    CUB(cudaMemsetAsync(e->d_summary, 0, MBT_SUMMARY_DOUBLES * sizeof(double), e->stream));
+    CUB(cudaHostAlloc((void **)&e->h_summary, MBT_SUMMARY_DOUBLES * sizeof(double), cudaHostAllocDefault));
+    CUB(cudaMalloc((void **)&e->d_roll_ticket, sizeof(unsigned int)));
+    CUB(cudaMemsetAsync(e->d_roll_ticket, 0, sizeof(unsigned int), e->stream));
     CUB(cudaStreamSynchronize(e->stream));
 #undef CUB
     *out = e;
@@ -693,6 +775,54 @@ int mbt_seed(mbt_env *e, uint64_t seed) {
         CU(cudaSetDevice(e->device));
         CU(cudaMemsetAsync(e->d_counter_base, 0, 2 * sizeof(unsigned long long), e->stream));
     }
+    return MBT_OK;
+}
+
+int mbt_get_seed(mbt_env *e, uint64_t *seed) {
+    if (!e || !seed) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    *seed = e->seed;
+    return MBT_OK;
+}
+
+int mbt_set_counters(mbt_env *e, int64_t steps_since_seed, int64_t episodes_since_seed) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    if (steps_since_seed < 0 || episodes_since_seed < 0) return fail(MBT_E_INVALID_ARG, "counters must be >= 0");
+    if (stream_is_capturing(e)) return fail(MBT_E_STATE, "mbt_set_counters is not capturable");
+    CU(cudaSetDevice(e->device));
+    if (e->device_counters) { /* the device base is the truth in this mode */
+        const unsigned long long base[2] = {(unsigned long long)steps_since_seed, (unsigned long long)episodes_since_seed};
+        CU(cudaMemcpyAsync(e->d_counter_base, base, sizeof base, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        e->n_step = 0;
+        e->n_episode = 0;
+    } else {
+        e->n_step = steps_since_seed;
+        e->n_episode = episodes_since_seed;
+    }
+    return MBT_OK;
+}
+
+/* which state columns a configuration keeps alive (the part of the layout mbt_reconfigure must not change) */
+static unsigned state_layout_key(const mbt_config &c) {
+    return (c.midprice == MBT_MID_HESTON ? 1u : 0u) | (c.arrival == MBT_ARR_HAWKES ? 2u : 0u) | (imp_has_state(c.impact) ? 4u : 0u) |
+           ((c.midprice == MBT_MID_CONSTANT ? 1u : 0u) << 3);
+}
+
+int mbt_reconfigure(mbt_env *e, const mbt_config *cfg) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    std::string err;
+    int rc = mbt_validate_config(cfg, err);
+    if (rc) return fail(rc, err);
+    const mbt_config &o = e->cfg;
+    int32_t A = 0, D = 0, S = 0;
+    mbt_dims(cfg, &A, &D, &S);
+    if (cfg->num_trajectories != o.num_trajectories || cfg->traj_offset != o.traj_offset || cfg->precision != o.precision ||
+        cfg->io_precision != o.io_precision || A != e->A || D != e->D || state_layout_key(*cfg) != state_layout_key(o))
+        return fail(MBT_E_STATE, "mbt_reconfigure: the new configuration changes the shape of the device state (num_trajectories, "
+                                 "precision, action / observation widths or the set of model state columns)");
+    if (stream_is_capturing(e)) return fail(MBT_E_STATE, "mbt_reconfigure is not capturable");
+    e->cfg = *cfg;
+    e->Dout = mbt_obs_out_dim(cfg, e->D);
     return MBT_OK;
 }
 
@@ -973,9 +1103,9 @@ int mbt_reward_eval(mbt_env *e, int64_t n, const void *current_state, const void
 
 } /* extern "C" */
 
+/* enqueue the fused rollout of the rest of the episode on the handle's stream; the summary stays on the device */
 template <typename T>
-static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, void *returns, void *term_q,
-                      const mbt_record *rec = nullptr) {
+static int enqueue_rollout(mbt_env *e, const mbt_policy *pol, void *returns, void *term_q, const mbt_record *rec, int *steps_out) {
     const mbt_config &c = e->cfg;
     /* the clock exactly as repeated `state[:, TIME] += step_size` produces it   TradingEnvironment.py:216 */
     std::vector<double> times;
@@ -1017,7 +1147,10 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
     g.keys = mbt_philox_expand(e->seed);
     g.traj_offset = (unsigned long long)c.traj_offset;
     g.n_step0 = (unsigned long long)e->n_step;
-    g.counter_base = e->device_counters ? e->d_counter_base : nullptr;
+    {
+        int rcb = counter_base_for_launch(e, &g.counter_base);
+        if (rcb) return rcb;
+    }
     g.steps = steps;
     g.clocks = (const RolloutClock<T> *)e->d_clocks;
     g.pol_kind = pol->kind;
@@ -1065,16 +1198,14 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
     const int blocks = (int)grid_for(g.n);
     if (blocks > e->block_sums_cap) {
         cudaFree(e->d_block_sums);
-        cudaFreeHost(e->h_block_sums);
-        e->d_block_sums = e->h_block_sums = nullptr;
+        e->d_block_sums = nullptr;
         CU(cudaMalloc(&e->d_block_sums, (size_t)blocks * MBT_SUMMARY_DOUBLES * sizeof(double)));
-        CU(cudaHostAlloc(&e->h_block_sums, (size_t)blocks * MBT_SUMMARY_DOUBLES * sizeof(double), cudaHostAllocDefault));
         e->block_sums_cap = blocks;
     }
     g.block_sums = e->d_block_sums;
+    g.summary = e->d_summary;
+    g.ticket = e->d_roll_ticket;
     g.clipped = e->d_clipped;
-    unsigned long long clip_before = 0, clip_after = 0;
-    CU(cudaMemcpyAsync(&clip_before, e->d_clipped, sizeof clip_before, cudaMemcpyDeviceToHost, e->stream));
     int rc = timing_begin(e);
     if (rc) return rc;
     /* the fast path (no recording) has the policy kind compiled in; the recording kernels (store-bound) switch at run time */
@@ -1098,27 +1229,39 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
     rc = timing_end(e);
     if (rc) return rc;
     e->launches += 1;
-    CU(cudaMemcpyAsync(e->h_block_sums, e->d_block_sums, (size_t)blocks * MBT_SUMMARY_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(&clip_after, e->d_clipped, sizeof clip_after, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    double tot[MBT_SUMMARY_DOUBLES] = {0, 0, 0, 0, 0, 0};
-    for (int b = 0; b < blocks; ++b)
-        for (int m = 0; m < MBT_SUMMARY_DOUBLES; ++m) tot[m] += e->h_block_sums[(size_t)b * MBT_SUMMARY_DOUBLES + m];
-    if (summary) {
-        summary->count = e->N;
-        summary->steps = steps;
-        summary->sum_return = tot[0];
-        summary->sum_return_sq = tot[1];
-        summary->sum_q = tot[2];
-        summary->sum_q_sq = tot[3];
-        summary->sum_action = tot[4];
-        summary->sum_reward_sq = tot[5];
-        summary->clipped = (int64_t)(clip_after - clip_before);
-    }
     e->t = times.back();
     e->k += steps;
     e->n_step += steps;
+    *steps_out = steps;
+    return fold_eager(e);
+}
+
+/* the device-resident summary of the last rollout (local, or all-reduced over the group) -> host struct.  One small D2H
+ * into pinned memory on the handle's stream + one synchronize: the only host round trip of an episode. */
+static int fetch_summary(mbt_env *e, int steps, long long count, mbt_summary *summary) {
+    CU(cudaMemcpyAsync(e->h_summary, e->d_summary, MBT_SUMMARY_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (summary) {
+        summary->count = count;
+        summary->steps = steps;
+        summary->sum_return = e->h_summary[0];
+        summary->sum_return_sq = e->h_summary[1];
+        summary->sum_q = e->h_summary[2];
+        summary->sum_q_sq = e->h_summary[3];
+        summary->sum_action = e->h_summary[4];
+        summary->sum_reward_sq = e->h_summary[5];
+        summary->clipped = (int64_t)e->h_summary[6];
+    }
     return MBT_OK;
+}
+
+template <typename T>
+static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, void *returns, void *term_q,
+                      const mbt_record *rec = nullptr) {
+    int steps = 0;
+    int rc = enqueue_rollout<T>(e, pol, returns, term_q, rec, &steps);
+    if (rc) return rc;
+    return fetch_summary(e, steps, e->N, summary);
 }
 
 extern "C" {
@@ -1184,6 +1327,14 @@ int mbt_rollout_record(mbt_env *e, const mbt_policy *policy, mbt_summary *summar
     return rc;
 }
 
+int mbt_prepare_capture(mbt_env *e) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    CU(cudaSetDevice(e->device));
+    if (stream_is_capturing(e)) return fail(MBT_E_STATE, "mbt_prepare_capture must be called before the capture begins");
+    e->device_counters = true;
+    return fold_eager(e); /* base += counters consumed so far; host counters = 0 */
+}
+
 int mbt_fold_counters(mbt_env *e) {
     if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
     CU(cudaSetDevice(e->device));
@@ -1227,6 +1378,247 @@ int mbt_get_kernel_times(mbt_env *e, float *ms_out, int64_t capacity, int64_t *c
             CU(cudaEventElapsedTime(&ms_out[i], e->ev0[i], e->ev1[i]));
     }
     *count = e->timed;
+    return MBT_OK;
+}
+
+} /* extern "C" */
+
+/* ------------------------------------------------------------------ group of handles over NCCL */
+/* NCCL is loaded at run time (dlopen): single-GPU users need no NCCL, and inside a torch process the already loaded
+ * libnccl.so.2 (torch's own) is the one that answers.  Only the handful of entry points below are used. */
+namespace {
+typedef struct { char internal[MBT_GROUP_ID_BYTES]; } nccl_unique_id;
+typedef void *nccl_comm_t;
+enum { NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8 }; /* ncclDataType_t (nccl.h) */
+enum { NCCL_SUM = 0, NCCL_MAX = 2 };                                           /* ncclRedOp_t                */
+struct NcclApi {
+    void *so = nullptr;
+    int (*GetUniqueId)(nccl_unique_id *) = nullptr;
+    int (*CommInitRank)(nccl_comm_t *, int, nccl_unique_id, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string error;
+};
+NcclApi *nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names)
+            if ((a.so = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (!a.so) {
+            a.error = std::string("NCCL not found (dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "?") + ")";
+            return a;
+        }
+#define SYM(field, name)                                                      \
+    *(void **)(&a.field) = dlsym(a.so, name);                                 \
+    if (!a.field && a.error.empty()) a.error = std::string("libnccl lacks ") + name;
+        SYM(GetUniqueId, "ncclGetUniqueId")
+        SYM(CommInitRank, "ncclCommInitRank")
+        SYM(CommDestroy, "ncclCommDestroy")
+        SYM(AllReduce, "ncclAllReduce")
+        SYM(AllGather, "ncclAllGather")
+        SYM(Broadcast, "ncclBroadcast")
+        SYM(GroupStart, "ncclGroupStart")
+        SYM(GroupEnd, "ncclGroupEnd")
+        SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+        return a;
+    }();
+    return &api;
+}
+} /* namespace */
+
+#define NC(expr)                                                                                                   \
+    do {                                                                                                           \
+        int _r = (expr);                                                                                           \
+        if (_r != 0) {                                                                                             \
+            char _b[512];                                                                                          \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, nccl_api()->GetErrorString(_r), __FILE__, __LINE__); \
+            return fail(MBT_E_NCCL, _b);                                                                           \
+        }                                                                                                          \
+    } while (0)
+
+static void group_teardown(mbt_env *e) {
+    if (e->comm && nccl_api()->CommDestroy) {
+        if (e->comm_stream) cudaStreamSynchronize(e->comm_stream);
+        nccl_api()->CommDestroy((nccl_comm_t)e->comm);
+    }
+    e->comm = nullptr;
+    if (e->ev_rollout) cudaEventDestroy(e->ev_rollout);
+    if (e->ev_gather) cudaEventDestroy(e->ev_gather);
+    if (e->comm_stream) cudaStreamDestroy(e->comm_stream);
+    e->ev_rollout = e->ev_gather = nullptr;
+    e->comm_stream = nullptr;
+    e->g_rank = 0;
+    e->g_world = 1;
+    e->g_counts.clear();
+    e->gather_pending = false;
+}
+
+static int group_allreduce_max_u64(mbt_env *e, unsigned long long *dev, int count) {
+    NC(nccl_api()->AllReduce(dev, dev, (size_t)count, NCCL_UINT64, NCCL_MAX, (nccl_comm_t)e->comm, e->stream));
+    return MBT_OK;
+}
+
+extern "C" {
+
+int mbt_group_unique_id(void *id_out) {
+    if (!id_out) return fail(MBT_E_INVALID_ARG, "id_out is NULL");
+    NcclApi *api = nccl_api();
+    if (!api->error.empty()) return fail(MBT_E_UNSUPPORTED, api->error);
+    nccl_unique_id id;
+    NC(api->GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return MBT_OK;
+}
+
+int mbt_group_create(mbt_env *e, const void *id, int rank, int world) {
+    if (!e || !id) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(MBT_E_INVALID_ARG, "need 0 <= rank < world");
+    if (e->comm) return fail(MBT_E_STATE, "the handle already belongs to a group");
+    NcclApi *api = nccl_api();
+    if (!api->error.empty()) return fail(MBT_E_UNSUPPORTED, api->error);
+    CU(cudaSetDevice(e->device));
+    nccl_unique_id uid;
+    memcpy(&uid, id, sizeof uid);
+    nccl_comm_t comm = nullptr;
+    NC(api->CommInitRank(&comm, world, uid, rank));
+    e->comm = comm;
+    e->g_rank = rank;
+    e->g_world = world;
+    CU(cudaStreamCreateWithFlags(&e->comm_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e->ev_rollout, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->ev_gather, cudaEventDisableTiming));
+    /* shard sizes of all ranks (the gather of returns places shard r at the sum of the sizes before it) */
+    long long *d_counts = nullptr;
+    CU(cudaMalloc((void **)&d_counts, (size_t)world * sizeof(long long)));
+    const long long mine = e->N;
+    CU(cudaMemcpyAsync(d_counts + rank, &mine, sizeof mine, cudaMemcpyHostToDevice, e->stream));
+    int r = api->AllGather(d_counts + rank, d_counts, 1, NCCL_INT64, comm, e->stream);
+    e->g_counts.assign((size_t)world, 0);
+    cudaError_t ce = cudaMemcpyAsync(e->g_counts.data(), d_counts, (size_t)world * sizeof(long long), cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t se = cudaStreamSynchronize(e->stream);
+    cudaFree(d_counts);
+    if (r != 0 || ce != cudaSuccess || se != cudaSuccess) {
+        group_teardown(e);
+        return fail(MBT_E_NCCL, std::string("mbt_group_create: exchanging shard sizes failed: ") +
+                                    (r != 0 ? api->GetErrorString(r) : cudaGetErrorString(ce != cudaSuccess ? ce : se)));
+    }
+    return MBT_OK;
+}
+
+int mbt_group_destroy(mbt_env *e) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    group_teardown(e);
+    return MBT_OK;
+}
+
+int mbt_group_info(mbt_env *e, int32_t *rank, int32_t *world, int64_t *total) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    if (rank) *rank = e->g_rank;
+    if (world) *world = e->g_world;
+    if (total) {
+        long long t = 0;
+        if (e->comm) for (long long c : e->g_counts) t += c;
+        else t = e->N;
+        *total = t;
+    }
+    return MBT_OK;
+}
+
+/* all-reduce (sum) of the device-resident summary on the handle's stream */
+static int group_allreduce_summary(mbt_env *e) {
+    NC(nccl_api()->AllReduce(e->d_summary, e->d_summary, MBT_SUMMARY_DOUBLES, NCCL_FLOAT64, NCCL_SUM, (nccl_comm_t)e->comm, e->stream));
+    return MBT_OK;
+}
+
+int mbt_group_rollout(mbt_env *e, const mbt_policy *policy, mbt_summary *summary_out, void *returns_local, void *returns_all) {
+    if (!e || !policy) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    if (!e->comm) return fail(MBT_E_STATE, "the handle belongs to no group (mbt_group_create)");
+    if (!e->started) return fail(MBT_E_STATE, "mbt_group_rollout called before mbt_reset");
+    if (e->t >= e->cfg.terminal_time - e->cfg.step_size / 2) return fail(MBT_E_STATE, "episode already finished; call mbt_reset");
+    if (returns_all && !returns_local) return fail(MBT_E_INVALID_ARG, "returns_all needs returns_local (the shard's own returns)");
+    CU(cudaSetDevice(e->device));
+    if (e->gather_pending) { /* the previous episode's gather reads that episode's returns: order this rollout's writes behind it
+                                only if the caller reuses the same buffer -- it may not know, so always order */
+        CU(cudaStreamWaitEvent(e->stream, e->ev_gather, 0));
+        e->gather_pending = false;
+    }
+    int steps = 0;
+    int rc = e->cfg.precision == MBT_F64 ? enqueue_rollout<double>(e, policy, returns_local, nullptr, nullptr, &steps)
+                                         : enqueue_rollout<float>(e, policy, returns_local, nullptr, nullptr, &steps);
+    if (rc) return rc;
+    if (returns_all) {
+        /* the gather runs on the group's own stream behind the rollout: it overlaps the summary's host round trip and
+         * whatever the caller enqueues next on the handle's stream */
+        CU(cudaEventRecord(e->ev_rollout, e->stream));
+        CU(cudaStreamWaitEvent(e->comm_stream, e->ev_rollout, 0));
+    }
+    rc = group_allreduce_summary(e);
+    if (rc) return rc;
+    if (returns_all) {
+        const int dt = e->cfg.precision == MBT_F64 ? NCCL_FLOAT64 : NCCL_FLOAT32;
+        bool equal = true;
+        for (long long c : e->g_counts) equal = equal && c == e->g_counts[0];
+        NcclApi *api = nccl_api();
+        if (equal) {
+            NC(api->AllGather(returns_local, returns_all, (size_t)e->N, dt, (nccl_comm_t)e->comm, e->comm_stream));
+        } else { /* ragged shards (N % world != 0): one broadcast per rank, grouped */
+            NC(api->GroupStart());
+            long long off = 0;
+            for (int r = 0; r < e->g_world; ++r) {
+                char *dst = (char *)returns_all + (size_t)off * e->esz;
+                int br = api->Broadcast(r == e->g_rank ? returns_local : dst, dst, (size_t)e->g_counts[(size_t)r], dt, r, (nccl_comm_t)e->comm, e->comm_stream);
+                if (br != 0) {
+                    api->GroupEnd();
+                    return fail(MBT_E_NCCL, std::string("ncclBroadcast failed: ") + api->GetErrorString(br));
+                }
+                off += e->g_counts[(size_t)r];
+            }
+            NC(api->GroupEnd());
+        }
+        CU(cudaEventRecord(e->ev_gather, e->comm_stream));
+        e->gather_pending = true;
+    }
+    long long total = 0;
+    for (long long c : e->g_counts) total += c;
+    return fetch_summary(e, steps, total, summary_out);
+}
+
+int mbt_group_summary(mbt_env *e, const mbt_summary *local, mbt_summary *global_out) {
+    if (!e || !local || !global_out) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    if (!e->comm) return fail(MBT_E_STATE, "the handle belongs to no group (mbt_group_create)");
+    CU(cudaSetDevice(e->device));
+    e->h_summary[0] = local->sum_return; e->h_summary[1] = local->sum_return_sq; e->h_summary[2] = local->sum_q;
+    e->h_summary[3] = local->sum_q_sq; e->h_summary[4] = local->sum_action; e->h_summary[5] = local->sum_reward_sq;
+    e->h_summary[6] = (double)local->clipped;
+    CU(cudaMemcpyAsync(e->d_summary, e->h_summary, MBT_SUMMARY_DOUBLES * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    int rc = group_allreduce_summary(e);
+    if (rc) return rc;
+    long long total = 0;
+    for (long long c : e->g_counts) total += c;
+    return fetch_summary(e, (int)local->steps, total, global_out);
+}
+
+int mbt_group_wait(mbt_env *e, int host_sync) {
+    if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
+    if (!e->comm) return fail(MBT_E_STATE, "the handle belongs to no group (mbt_group_create)");
+    CU(cudaSetDevice(e->device));
+    if (e->gather_pending) {
+        CU(cudaStreamWaitEvent(e->stream, e->ev_gather, 0));
+        e->gather_pending = false;
+    }
+    if (host_sync) {
+        CU(cudaStreamSynchronize(e->comm_stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
     return MBT_OK;
 }
 

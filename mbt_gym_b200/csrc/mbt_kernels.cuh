@@ -388,7 +388,9 @@ __device__ __forceinline__ void load_depths(const E *__restrict__ actions, long 
     }
 }
 
-template <typename T, typename E, bool VEC>
+/* FINAL: the last block turns the maxima into thresholds (one handle = the whole batch).  !FINAL: the maxima stay in
+ * `cells` as keys -- a group of handles all-reduces (max) them over NCCL first, then mbt_fill_finalize_kernel runs. */
+template <typename T, typename E, bool VEC, bool FINAL>
 __global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_constant__ FillBatchArgs<T, E> g) {
     const StepParams<T> &p = g.p;
     const int A = p.action_dim;
@@ -422,6 +424,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_
     for (int w = 1; w < MBT_BLOCK / 32; ++w) { b0 = nanmax<T>(b0, sm[w][0]); b1 = nanmax<T>(b1, sm[w][1]); }
     atomicMax(g.cells + 0, real_to_key((double)b0));
     atomicMax(g.cells + 1, real_to_key((double)b1));
+    if (!FINAL) return;
     __threadfence(); /* this block's maxima are visible before its ticket is taken */
     if (atomicAdd(g.ticket, 1u) != gridDim.x - 1) return;
     /* last block: every other block's atomicMax happened before its ticket; read and clear for the next step */
@@ -433,6 +436,19 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_
     g.thr[0] = thr[0];
     g.thr[1] = thr[1];
     *g.ticket = 0u;
+}
+
+/* group of handles: thresholds from the all-reduced maxima (one thread); clears the cells for the next step */
+template <typename T>
+__global__ void mbt_fill_finalize_kernel(StepParams<T> p, unsigned long long *cells, T *thr_out) {
+    const T a0 = (T)key_to_real(cells[0]);
+    const T a1 = (T)key_to_real(cells[1]);
+    cells[0] = 0ull;
+    cells[1] = 0ull;
+    T thr[2];
+    fill_batch_thresholds<T>(p, a0, a1, thr);
+    thr_out[0] = thr[0];
+    thr_out[1] = thr[1];
 }
 
 /* ------------------------------------------------------------------ reset */
@@ -462,6 +478,8 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_reset_kernel(const __grid_const
         const unsigned long long n_episode = g.n_episode + (g.counter_base ? g.counter_base[1] : 0ull);
         const mbt_u32x4 r = mbt_draw(g.seed, g.traj_offset + (unsigned long long)i, n_episode, MBT_STREAM_RESET);
         s.inv = (T)(g.q0_lo + (long long)(((unsigned long long)r.x * g.q0_span) >> 32));
+    } else if (g.q0_mode == MBT_Q0_PER_TRAJ) { /* a callable's array, uploaded into the q0 column   TradingEnvironment.py:275-279 */
+        s.inv = g.st.q0[i];
     } else {
         s.inv = g.q0_const;
     }
@@ -545,7 +563,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_reward_kernel(StepParams<T> p, 
 }
 
 /* ------------------------------------------------------------------ fused rollout */
-constexpr int MBT_SUMMARY_DOUBLES = 6; /* sum R, sum R^2, sum q, sum q^2, sum action, sum r^2 */
+constexpr int MBT_SUMMARY_DOUBLES = 7; /* sum R, sum R^2, sum q, sum q^2, sum action, sum r^2, clip events */
 
 template <typename T>
 struct RolloutClock {
@@ -578,6 +596,8 @@ struct RolloutArgs {
      * returned them, rec_rew (steps, N).  The host exposes them transposed, in the shapes of generate_trajectory. */
     T *rec_obs, *rec_act, *rec_rew;
     double *block_sums; /* (gridDim.x, MBT_SUMMARY_DOUBLES) */
+    double *summary;    /* (MBT_SUMMARY_DOUBLES,): the block rows folded in a fixed order by the last block to finish */
+    unsigned int *ticket; /* zero on entry, zero again on exit */
     unsigned long long *clipped;
 };
 
@@ -618,7 +638,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
     const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
     const bool live = i < g.n;
     const StepParams<T> &p = g.p;
-    double acc[MBT_SUMMARY_DOUBLES] = {0, 0, 0, 0, 0, 0};
+    double acc[MBT_SUMMARY_DOUBLES] = {0, 0, 0, 0, 0, 0, 0};
     if (live) {
         Traj<T> s;
         load_traj<T, V>(p, g.st, i, s);
@@ -627,7 +647,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
         if ((rew_kind == MBT_REW_CJ_MM || rew_kind == MBT_REW_CJ_OE) && p.q0_per_traj) q_init = g.st.q0[i];
         const int A = action_width<T, V>(p);
         T ret = (T)0;
-        int clipped = 0;
+        int n_clipped = 0; /* clip EVENTS (steps in which inventory or cash hit a bound), like a loop of mbt_step counts them */
         const int D = obs_width<T, V>(p);
         const unsigned long long n_step0 = g.n_step0 + (g.counter_base ? g.counter_base[0] : 0ull);
         if (REC && g.rec_obs) {
@@ -652,7 +672,9 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
             T fill_thr[2] = {(T)0, (T)0};
             if (V::dyn < 0 && fill_is_batch(p.fill)) fill_batch_thresholds<T>(p, a[0], a[1], fill_thr);
             const uint32_t nbits2 = second_normal_bits<T, V>(p, g.keys, g.traj_offset + (unsigned long long)i, n_step0 + (unsigned long long)k);
+            int clipped = 0;
             const T rwd = step_one<T, V>(p, ck, s, a, r, q_init, &clipped, fill_thr, nbits2);
+            n_clipped += clipped;
             ret = ret + rwd;
             acc[5] += (double)rwd * (double)rwd;
             if (REC && g.rec_rew) g.rec_rew[(long long)k * g.n + i] = rwd;
@@ -669,10 +691,11 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
         acc[1] = (double)ret * (double)ret;
         acc[2] = (double)s.inv;
         acc[3] = (double)s.inv * (double)s.inv;
-        if (clipped) atomicAdd(g.clipped, 1ull);
+        acc[6] = (double)n_clipped;
     }
-    /* episode-return summaries: warp shuffle -> shared -> one row per block (summed on the host in
-     * block order, so the result is deterministic).  This is the only cross-thread step of the path. */
+    /* episode-return summaries: warp shuffle -> shared -> one row per block; the LAST block to finish (ticket) folds the
+     * rows in a fixed order into g.summary, so the result is deterministic and stays on the device (a group all-reduces
+     * it over NCCL from there).  This is the only cross-thread step of the path. */
     __shared__ double sm[MBT_BLOCK / 32][MBT_SUMMARY_DOUBLES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -687,7 +710,35 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
         double v = 0;
         for (int w = 0; w < MBT_BLOCK / 32; ++w) v += sm[w][threadIdx.x];
         g.block_sums[(long long)blockIdx.x * MBT_SUMMARY_DOUBLES + threadIdx.x] = v;
+        if (threadIdx.x == 6 && v != 0.0) atomicAdd(g.clipped, (unsigned long long)v); /* cumulative counter of the handle */
+        __threadfence(); /* this block's row is visible before its ticket is taken */
     }
+    __shared__ bool is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(g.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    /* thread t folds rows t, t + 256, ... in increasing order; then the same shuffle -> shared tree as above */
+    double part[MBT_SUMMARY_DOUBLES] = {0, 0, 0, 0, 0, 0, 0};
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += MBT_BLOCK) {
+#pragma unroll
+        for (int m = 0; m < MBT_SUMMARY_DOUBLES; ++m) part[m] += __ldcg(g.block_sums + (long long)b * MBT_SUMMARY_DOUBLES + m);
+    }
+#pragma unroll
+    for (int m = 0; m < MBT_SUMMARY_DOUBLES; ++m) {
+        double v = part[m];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) sm[warp][m] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < MBT_SUMMARY_DOUBLES) {
+        double v = 0;
+        for (int w = 0; w < MBT_BLOCK / 32; ++w) v += sm[w][threadIdx.x];
+        g.summary[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) *g.ticket = 0u;
 }
 
 #endif /* MBT_KERNELS_CUH */

@@ -4,10 +4,11 @@ bodies of the fused CUDA step kernel (mbt_gym_b200/csrc/mbt_step_core.cuh)."""
 import numpy as np
 
 from .. import _abi
+from .._track import Tracked
 from ..spaces import Box, MultiBinary
 
 
-class ModelDynamics:
+class ModelDynamics(Tracked):
     KIND = None
     REQUIRED = ()
     round_initial_inventory = False

@@ -11,9 +11,11 @@ Extra keyword-only arguments (all optional, defaults keep the reference behaviou
                   `np.float32` with float64 arithmetic keeps the dynamics reference-exact and halves the host traffic
     device        CUDA device index
     traj_offset   global id of trajectory 0 (multi-GPU sharding: RNG counters use global ids)
-    copy_outputs  False: `step()`/`reset()` return views of a ring of 4 pinned host buffers (valid until 4 more
-                  calls; what SB3 / generate_trajectory need, and what makes the host path PCIe-bound instead of
-                  page-fault-bound); True: fresh arrays every call, exactly like the reference's `.copy()`.
+    copy_outputs  False (default): `step()`/`reset()` return arrays backed by a POOL of page-locked buffers that are
+                  handed out again only when nothing references them any more (`_lib.PinnedPool`) -- like the
+                  reference's fresh `.copy()` arrays they are never overwritten while the caller holds them (or any
+                  view / `torch.from_numpy` of them), and their memory outlives `close()`; the device-to-host copy is
+                  a direct DMA.  True: ordinary `np.empty` arrays every call (staged through pinned memory).
 Actions may also be a CUDA torch tensor: then observations and rewards come back as CUDA tensors on the same device
 and nothing crosses PCIe (the zero-copy path for on-device policies).
 """
@@ -23,7 +25,7 @@ from copy import copy
 
 import numpy as np
 
-from .. import _abi, _lib
+from .. import _abi, _lib, _track
 from ..rewards.RewardFunctions import PnL, RewardFunction
 from ..spaces import Box
 from ..stochastic_processes.arrival_models import PoissonArrivalModel
@@ -41,14 +43,13 @@ except Exception:  # noqa: BLE001
         _EnvBase = object
 
 _PROCESS_ORDER = ("midprice_model", "arrival_model", "fill_probability_model", "price_impact_model")
-_RING = 4
 
 
 class _EmptyInfos(list):
     """The reference returns one pre-built list of N empty dicts every step (TradingEnvironment.py:320-321)."""
 
 
-class TradingEnvironment(_EnvBase):
+class TradingEnvironment(_track.Tracked, _EnvBase):
     metadata = {"render.modes": ["human"]}
 
     def __init__(self, terminal_time=1.0, n_steps=20 * 10, reward_function=None, model_dynamics=None, initial_cash=0.0,
@@ -60,10 +61,10 @@ class TradingEnvironment(_EnvBase):
         self._native = None
         self._native_cfg_bytes = None
         self._started = False
-        self._ring = None
-        self._ring_pos = 0
+        self._episode_open = False  # between reset() and the step that returned done
+        self._seen_version = -1     # _track.version the device handle was last validated against
+        self._pool = None
         self._infos = None
-        self._dones_cache = None
         self.precision = {"float64": _abi.MBT_F64, "f64": _abi.MBT_F64, "float32": _abi.MBT_F32, "f32": _abi.MBT_F32}[str(precision)]
         self.dtype = np.dtype(np.float64 if self.precision == _abi.MBT_F64 else np.float32)
         # dtype of the arrays step()/reset() exchange with the caller: the arithmetic dtype, or float32 over float64
@@ -138,23 +139,29 @@ class TradingEnvironment(_EnvBase):
         full = self._full_observation_space
         idx = self._obs_columns if self._obs_columns is not None else list(range(full.shape[0]))
         self.observation_space = Box(low=full.low[idx], high=full.high[idx], dtype=full.low.dtype)
-        self._ring = None
 
     # ------------------------------------------------------------------ reference surface: hot path
     def reset(self):
         """Start an episode; returns the (N, D) observation  (TradingEnvironment.py:96-101)."""
-        native = self._ensure_native()
+        native = self._ensure_native(at_reset=True)
         args = _abi.mbt_reset_args()
         args.start_time = float(self._get_start_time())
         self._fill_initial_inventory(args)
-        out = self._out_buffers()[0]
+        out = self._out_buffers(rewards=False)[0]
         native.reset(out, args)
+        self._after_reset(args)
+        return out
+
+    def _after_reset(self, args):
         self._started = True
+        self._episode_open = True
         if getattr(self.reward_function, "terminal_time", None) is not None:
             # what reward_function.reset(initial_state) records (RewardFunctions.py:72-74,111-113), without a D2H copy
             self.reward_function.episode_length = self.reward_function.terminal_time - args.start_time
-            self.reward_function.initial_inventory = None if args.q0_mode == _abi.MBT_Q0_UNIFORM_INT else args.q0_const
-        return out
+            self.reward_function.initial_inventory = (
+                None if args.q0_mode == _abi.MBT_Q0_UNIFORM_INT else
+                self._q0_values if args.q0_mode == _abi.MBT_Q0_PER_TRAJ else args.q0_const)
+        self._seen_version = _track.version[0]  # the two assignments above are ours, not the caller's
 
     def reset_device(self, out=None):
         """`reset()` that stays on the device: the first observation as a CUDA torch tensor (written into `out` when
@@ -162,7 +169,7 @@ class TradingEnvironment(_EnvBase):
         together with `step(cuda_tensor)` calls (see `fold_counters`)."""
         import torch
 
-        native = self._ensure_native()
+        native = self._ensure_native(at_reset=True)
         args = _abi.mbt_reset_args()
         args.start_time = float(self._get_start_time())
         self._fill_initial_inventory(args)
@@ -174,26 +181,34 @@ class TradingEnvironment(_EnvBase):
             raise ValueError(f"out must be a contiguous {tdt} tensor of shape ({self.num_trajectories}, {native.Dout})")
         native.set_stream(torch.cuda.current_stream(dev).cuda_stream)
         native.reset(out, args, mem=_abi.MBT_MEM_DEVICE)
-        self._started = True
-        if getattr(self.reward_function, "terminal_time", None) is not None:
-            self.reward_function.episode_length = self.reward_function.terminal_time - args.start_time
-            self.reward_function.initial_inventory = None if args.q0_mode == _abi.MBT_Q0_UNIFORM_INT else args.q0_const
+        self._after_reset(args)
         return out
+
+    def prepare_capture(self):
+        """Call BEFORE `torch.cuda.graph(...)` when the environment was already used (warm-up `reset_device()` / steps):
+        the random-number counters consumed so far move to the device, so the launches baked into the graph count from
+        zero and later eager calls and graph replays interleave without reusing or skipping a draw.
+        C ABI: `mbt_prepare_capture` (include/mbt_b200.h)."""
+        self._ensure_native(at_reset=True).prepare_capture()
 
     def fold_counters(self):
         """Call LAST inside a `torch.cuda.graph` capture that spans whole episodes (`reset_device`, then policy and
         `step(cuda_tensor)` until done): the random-number counters move to the device, so every `graph.replay()` is a
         NEW episode -- bit-identical to stepping the same episodes eagerly -- instead of a repeat of the captured one.
-        Bind the environment to the capture stream first (a warm-up `reset_device()` under `torch.cuda.stream(s)`) and
-        capture with `torch.cuda.graph(g, stream=s)`.  C ABI: `mbt_fold_counters` (include/mbt_b200.h)."""
-        self._ensure_native().fold_counters()
+        Bind the environment to the capture stream first (a warm-up `reset_device()` under `torch.cuda.stream(s)`), call
+        `prepare_capture()`, then capture with `torch.cuda.graph(g, stream=s)`.  C ABI: `mbt_fold_counters`."""
+        self._native.fold_counters()
 
     def step(self, action):
         """One env-step for all trajectories  (TradingEnvironment.py:103-110).
         action (N, A) -> observations (N, D), rewards (N,), dones (N,) bool, infos."""
-        native = self._native  # the handle is (re)validated against the Python attributes at reset(), not per step
+        native = self._native
         if native is None or not self._started:
             raise RuntimeError("step() called before reset()")
+        if _track.version[0] != self._seen_version:
+            # some attribute of an environment / model object was assigned since the handle was validated: re-flatten; an
+            # edit of THIS environment is applied in place, like the reference applies it at its next step
+            native = self._ensure_native()
         if hasattr(action, "is_cuda") and action.is_cuda:
             return self._step_device(native, action)
         a = action if (type(action) is np.ndarray and action.dtype == self.io_dtype and action.flags.c_contiguous) \
@@ -205,6 +220,8 @@ class TradingEnvironment(_EnvBase):
                 raise ValueError(f"action must have shape ({self.num_trajectories}, {native.A}); got {np.shape(action)}")
         obs, rew = self._out_buffers()
         done = native.step(a, obs, rew)
+        if done:
+            self._episode_open = False
         infos = self._calculate_infos()
         return obs, rew, self._dones(done), infos
 
@@ -222,6 +239,8 @@ class TradingEnvironment(_EnvBase):
         obs = torch.empty((self.num_trajectories, native.Dout), dtype=tdt, device=action.device)
         rew = torch.empty((self.num_trajectories,), dtype=tdt, device=action.device)
         done = native.step(action, obs, rew, mem=_abi.MBT_MEM_DEVICE)
+        if done:
+            self._episode_open = False
         return obs, rew, self._dones(done), self._calculate_infos()
 
     # ------------------------------------------------------------------ reference surface: helpers
@@ -300,8 +319,6 @@ class TradingEnvironment(_EnvBase):
                 process.num_trajectories = num_trajectories
         self.model_dynamics.num_trajectories = num_trajectories
         self._infos = None
-        self._dones_cache = None
-        self._ring = None
 
     def save_checkpoint(self):
         """The whole environment (device state + clock + RNG counters) as a uint8 array; see `load_checkpoint`."""
@@ -311,23 +328,24 @@ class TradingEnvironment(_EnvBase):
 
     def load_checkpoint(self, blob):
         """Resume exactly where `save_checkpoint` was taken (same trajectories, same future random draws)."""
-        native = self._ensure_native()
+        native = self._ensure_native(at_reset=True)
         native.restore(blob)
-        self._key = None  # the key now lives in the handle; a later seed() replaces it
+        self._key = native.get_seed()  # the checkpoint carries its own key; a later seed() replaces it
         self._started = True
+        clk = native.clock()
+        self._episode_open = clk["time"] < self.terminal_time - self.step_size / 2
 
     def pinned_actions(self):
         """A page-locked (N, A) array in the environment's dtype: fill it and pass it to `step()` and the action copy
         is one direct DMA (any other host array is first staged through the handle's own pinned buffer)."""
         native = self._ensure_native()
-        self._pinned_actions = _lib.PinnedArray((self.num_trajectories, native.A), self.io_dtype, self.device)
-        return self._pinned_actions.array
+        return _lib.PinnedArray((self.num_trajectories, native.A), self.io_dtype, self.device).array
 
     def close(self):
         if self._native is not None:
             self._native.close()
             self._native = None
-        self._ring = None
+        self._pool = None  # arrays the caller still holds keep their own page-locked blocks alive
 
     # ------------------------------------------------------------------ fused rollout (agents on the device)
     def rollout_summary(self, policy, return_trajectory_stats=False):
@@ -419,8 +437,16 @@ class TradingEnvironment(_EnvBase):
             args.q0_mode, args.q0_const = _abi.MBT_Q0_CONST, float(q0)
         elif callable(q0):
             v = q0()
-            args.q0_mode = _abi.MBT_Q0_CONST
-            args.q0_const = float(int(np.round(v)) if self.model_dynamics.round_initial_inventory else v)
+            if self.model_dynamics.round_initial_inventory:
+                v = int(np.round(v))  # (fails for arrays of more than one element, like the reference's :277-278)
+            if np.ndim(v) == 0 or np.size(v) == 1:
+                args.q0_mode, args.q0_const = _abi.MBT_Q0_CONST, float(np.asarray(v, float).reshape(-1)[0])
+            else:
+                # the reference assigns whatever the callable returns to the inventory column (:137,275-279): an
+                # (N,) array gives every trajectory its own initial inventory
+                vals = np.ascontiguousarray(np.broadcast_to(np.asarray(v, np.float64), (self.num_trajectories,)))
+                self._q0_values = vals  # kept alive for the call (host pointer in the struct) and for reward_function
+                args.q0_mode, args.q0_values = _abi.MBT_Q0_PER_TRAJ, vals.ctypes.data
         else:
             raise Exception("Initial inventory must be a tuple of length 2 or an int.")
 
@@ -457,37 +483,57 @@ class TradingEnvironment(_EnvBase):
                 cfg.obs_low[i], cfg.obs_grad[i] = float(lo[i]), float(gr[i])
         return cfg
 
-    def _ensure_native(self):
-        """(Re)create the device handle when the flattened configuration changed (setters, edited model attributes)."""
+    def _ensure_native(self, at_reset=False):
+        """The device handle for the CURRENT Python attributes.  An edited attribute (setters, model parameters) is
+        applied to the live handle in place (`mbt_reconfigure`: state, clock and random streams continue, as they do in
+        the reference); an edit that changes the shape of the device state (num_trajectories, dtype, another set of model
+        state columns) needs a new handle, which is only possible between episodes -- it inherits the key and the draw
+        counters of the old one, so the random streams continue instead of restarting."""
         cfg = self._build_config()
         raw = bytes(cfg)
-        if self._native is None or raw != self._native_cfg_bytes:
-            if self._native is not None:
-                self._native.close()
+        if self._native is None:
             self._native = _lib.NativeEnv(cfg, device=self.device)
             if self._key is not None:
                 self._native.seed(self._key)
-            self._native_cfg_bytes = raw
-            self._started = False
-            self._ring = None
+            self._started = self._episode_open = False
+        elif raw != self._native_cfg_bytes:
+            try:
+                self._native.reconfigure(cfg)
+            except _lib.MbtError as err:
+                if err.code != _abi.MBT_E_STATE:
+                    raise
+                if self._episode_open and not at_reset:
+                    raise RuntimeError(
+                        "an attribute that changes the shape of the device state (num_trajectories, precision, the set of "
+                        "model state columns) was edited in the middle of an episode; finish the episode or call reset()"
+                    ) from err
+                old = self._native
+                clk, key = old.clock(), old.get_seed()
+                old.close()
+                self._native = _lib.NativeEnv(cfg, device=self.device)
+                self._native.seed(key)
+                self._native.set_counters(clk["n_step"], clk["n_episode"])  # the Philox streams go on, they do not restart
+                self._started = self._episode_open = False
+        self._native_cfg_bytes = raw
+        self._seen_version = _track.version[0]
         return self._native
 
-    def _out_buffers(self):
+    def _out_buffers(self, rewards=True):
         n, d = self.num_trajectories, self._native.Dout
-        if self.copy_outputs:
-            return np.empty((n, d), self.io_dtype), np.empty((n,), self.io_dtype)
-        if self._ring is None:
-            self._ring = [(_lib.PinnedArray((n, d), self.io_dtype, self.device), _lib.PinnedArray((n,), self.io_dtype, self.device))
-                          for _ in range(_RING)]
-            self._ring_pos = 0
-        o, r = self._ring[self._ring_pos]
-        self._ring_pos = (self._ring_pos + 1) % _RING
-        return o.array, r.array
+        obs = rew = None
+        if not self.copy_outputs:
+            if self._pool is None:
+                self._pool = _lib.PinnedPool(self.device)
+            obs = self._pool.get((n, d), self.io_dtype)
+            rew = self._pool.get((n,), self.io_dtype) if rewards else None
+        if obs is None:
+            obs = np.empty((n, d), self.io_dtype)
+        if rew is None and rewards:
+            rew = np.empty((n,), self.io_dtype)
+        return obs, rew
 
     def _dones(self, done):
-        if self._dones_cache is None:
-            self._dones_cache = (np.zeros((self.num_trajectories,), bool), np.ones((self.num_trajectories,), bool))
-        return self._dones_cache[1 if done else 0]
+        return np.full((self.num_trajectories,), bool(done))  # a fresh array every step, like the reference's (:218-220)
 
     def _calculate_infos(self):
         if self.info_calculator is not None:

@@ -7,10 +7,11 @@ code through `mbt_reward_eval` of the C ABI on a small private handle -- there i
 import numpy as np
 
 from .. import _abi
+from .._track import Tracked
 from ..gym.index_names import INVENTORY_INDEX, TIME_INDEX
 
 
-class RewardFunction:
+class RewardFunction(Tracked):
     KIND = None
 
     def __init__(self):

@@ -11,13 +11,15 @@ types with NotImplementedError instead of silently running them on the CPU.
 """
 import numpy as np
 
+from .._track import Tracked
+
 
 def _row(values):
     """(1, d) float array; d may be 0 for stateless processes."""
     return np.asarray(values, dtype=float).reshape(1, -1)
 
 
-class StochasticProcessModel:
+class StochasticProcessModel(Tracked):
     #: MBT_* enum value written to mbt_config by the environment (set by concrete classes)
     KIND = None
 

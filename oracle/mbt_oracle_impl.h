@@ -137,6 +137,8 @@ static void FN(orc_reset)(FN(orc_env) * e, const mbt_reset_args *args, REAL *obs
             mbt_u32x4 r = mbt_draw(e->seed, (uint64_t)(c->traj_offset + i), (uint64_t)e->n_episode, MBT_STREAM_RESET);
             uint64_t span = (uint64_t)(hi - lo);
             s[1] = (REAL)(lo + (int64_t)(((uint64_t)r.x * span) >> 32));
+        } else if (q0_mode == MBT_Q0_PER_TRAJ) {
+            s[1] = (REAL)args->q0_values[i]; /* a callable that returned an array: assigned as is  TradingEnvironment.py:275-279,137 */
         } else {
             s[1] = (REAL)q0_const; /* TradingEnvironment.py:273-279 */
         }

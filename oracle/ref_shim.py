@@ -211,6 +211,12 @@ def build_reference_env(spec):
                              normalise_action_space=spec.get("normalise_action", False),
                              normalise_observation_space=spec.get("normalise_obs", False),
                              normalise_rewards=False)
+    if spec.get("normalise_rewards"):
+        # the constructor's own bootstrap (TradingEnvironment.py:90-94,329-343: a 100 000-trajectory rollout from the
+        # env's generators) cannot be driven by injected draws; the reward-scaling leg of step() (:128-129) is pinned with
+        # the scale set after construction -- exactly the two attributes the constructor would have set
+        env.normalise_rewards_ = True
+        env.reward_scaling = float(spec["reward_scaling"])
     return env
 
 
@@ -296,6 +302,9 @@ def config_from_reference_env(spec, env, precision=_abi.MBT_F64, traj_offset=0):
     cfg.rew_risk_aversion = float(getattr(rf, "risk_aversion", 0.0))
     cfg.normalise_action = int(env.normalise_action_space_)
     cfg.normalise_obs = int(env.normalise_observation_space_)
+    cfg.normalise_rewards = int(bool(env.normalise_rewards_))
+    if env.normalise_rewards_:
+        cfg.reward_scaling = float(env.reward_scaling)
     if env.normalise_action_space_:
         lo, hi = env.original_action_space.low, env.original_action_space.high
         for i in range(lo.shape[0]):

@@ -163,10 +163,15 @@ def build_facade_env(spec, **extra):
     q0 = spec.get("initial_inventory", 0)
     if isinstance(q0, list):
         q0 = tuple(q0)
-    return TradingEnvironment(terminal_time=T, n_steps=n_steps, reward_function=rew, model_dynamics=dyn,
-                              initial_cash=spec.get("initial_cash", 0.0), initial_inventory=q0,
-                              max_inventory=spec.get("max_inventory", 10_000), max_cash=spec.get("max_cash"),
-                              start_time=spec.get("start_time", 0.0), seed=spec["seed"], num_trajectories=N,
-                              normalise_action_space=spec.get("normalise_action", False),
-                              normalise_observation_space=spec.get("normalise_obs", False), normalise_rewards=False,
-                              **extra)
+    env = TradingEnvironment(terminal_time=T, n_steps=n_steps, reward_function=rew, model_dynamics=dyn,
+                             initial_cash=spec.get("initial_cash", 0.0), initial_inventory=q0,
+                             max_inventory=spec.get("max_inventory", 10_000), max_cash=spec.get("max_cash"),
+                             start_time=spec.get("start_time", 0.0), seed=spec["seed"], num_trajectories=N,
+                             normalise_action_space=spec.get("normalise_action", False),
+                             normalise_observation_space=spec.get("normalise_obs", False), normalise_rewards=False,
+                             **extra)
+    if spec.get("normalise_rewards"):
+        # like oracle/ref_shim.build_reference_env: the scale the constructor's bootstrap would have set, given by the spec
+        env.normalise_rewards_ = True
+        env.reward_scaling = float(spec["reward_scaling"])
+    return env

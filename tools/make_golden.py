@@ -142,6 +142,16 @@ SPECS = {
                                              arrival=dict(kind="hawkes", baseline=[30.0, 20.0], jump=20.0, speed=25.0),
                                              fill=dict(kind="exogenous", fill_exponent=2.0, base=1.0, best_depths=[0.3, 0.6]),
                                              normalise_action=True, normalise_obs=True),
+    # reward normalisation (TradingEnvironment.py:128-129): rewards * reward_scaling, the scale set like the constructor's
+    # bootstrap would (ref_shim.build_reference_env); alone, with the other two normalisations, and with a random q0
+    "as_pnl_reward_scaled": dict(N=69, n_steps=40, terminal_time=1.0, seed=1259, dynamics="limit", reward=dict(kind="pnl"),
+                                 max_inventory=40, normalise_rewards=True, reward_scaling=0.03713528, **AS),
+    "rip_all_normalised": dict(N=75, n_steps=40, terminal_time=1.0, seed=1260, dynamics="limit",
+                               reward=dict(kind="rip", phi=0.02, alpha=0.3), max_inventory=9, normalise_action=True,
+                               normalise_obs=True, normalise_rewards=True, reward_scaling=1.0 / 27.31, **AS),
+    "cjmm_reward_scaled": dict(N=63, n_steps=30, terminal_time=1.0, seed=1261, dynamics="limit",
+                               reward=dict(kind="cjmm", phi=0.01, alpha=0.001), max_inventory=30, initial_inventory=[-4, 5],
+                               normalise_obs=True, normalise_rewards=True, reward_scaling=3.25, n_episodes=2, **AS),
     # two episodes back to back: RNG stream continues, reset redraws inventories
     "two_episodes": dict(N=59, n_steps=30, terminal_time=1.0, seed=1244, dynamics="limit",
                          reward=dict(kind="cjmm", phi=0.01, alpha=0.001), max_inventory=20,
