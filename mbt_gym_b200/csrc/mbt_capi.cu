@@ -97,6 +97,7 @@ struct mbt_env {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_rollout = nullptr, ev_gather = nullptr;
     bool gather_pending = false;
+    const void *gather_src = nullptr; /* returns buffer the pending gather reads */
 
     /* clock (uniform over trajectories) */
     double t = 0, t0 = 0;
@@ -460,6 +461,16 @@ static bool host_path_zero_copy() {
     return zc;
 }
 
+/* MBT_PIPE_CHUNKS set = equal chunks; unset (or MBT_PIPE_SCHEDULE=geo) = the geometric schedule of do_step_host_pipelined */
+static bool pipe_schedule_geometric() {
+    static const bool geo = [] {
+        const char *sch = getenv("MBT_PIPE_SCHEDULE");
+        if (sch) return strcmp(sch, "geo") == 0;
+        return getenv("MBT_PIPE_CHUNKS") == nullptr;
+    }();
+    return geo;
+}
+
 /* number of pipeline chunks of the host-buffer path (env MBT_PIPE_CHUNKS overrides for tuning; 1..16, default 4) */
 static int pipe_chunks() {
     static const int n = [] {
@@ -484,13 +495,32 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
     const StepClock<T> ck = mbt_make_clock<T>(c, e->t, t_next, e->t0);
     const long long N = e->N;
     const bool batch = needs_fill_batch(c); /* the reduction needs every action row on the device first */
-    int chunks = (N >= (1 << 17) && !batch) ? pipe_chunks() : 1;
-    long long rows = ((N + chunks - 1) / chunks + 255) & ~255ll;
+    /* chunk boundaries: equal chunks (MBT_PIPE_CHUNKS=k), or by default a GEOMETRIC schedule 1/16, 1/16, 1/8, 1/4, 1/2 of the
+     * rows -- the device-to-host copies (the longer direction: D+1 against A elements per row) start after 1/16 of the
+     * action upload instead of 1/4, and every later chunk's upload + kernel finish before the D2H engine drains the one
+     * before, so the D2H engine stays busy from ~25 us after the call to its end */
+    long long bounds[MBT_PIPE_CHUNKS + 1];
+    int chunks = 1;
+    bounds[0] = 0;
+    if (N >= (1 << 17) && !batch) {
+        if (pipe_schedule_geometric()) {
+            const int shifts[5] = {4, 3, 2, 1, 0}; /* cumulative end of chunk i = N >> shift */
+            chunks = 5;
+            for (int i = 0; i < 5; ++i) bounds[i + 1] = i == 4 ? N : ((N >> shifts[i]) + 255) & ~255ll;
+        } else {
+            chunks = pipe_chunks();
+            const long long rows = ((N + chunks - 1) / chunks + 255) & ~255ll;
+            for (int i = 1; i <= chunks; ++i) bounds[i] = std::min(N, rows * i);
+        }
+    } else {
+        bounds[1] = N;
+    }
     const size_t arow = (size_t)e->A * sizeof(E), orow = (size_t)e->Dout * sizeof(E);
     for (int k = 0; k < chunks; ++k) {
-        const long long r0 = (long long)k * rows;
+        const long long r0 = bounds[k];
         if (r0 >= N) break;
-        const long long n = std::min(rows, N - r0);
+        const long long n = std::min(bounds[k + 1], N) - r0;
+        if (n <= 0) continue;
         CU(cudaMemcpyAsync((char *)e->d_actions + r0 * arow, (const char *)act_src + r0 * arow, n * arow,
                            cudaMemcpyHostToDevice, e->copy_in));
         CU(cudaEventRecord(e->ev_in[k], e->copy_in));
@@ -1546,8 +1576,9 @@ int mbt_group_rollout(mbt_env *e, const mbt_policy *policy, mbt_summary *summary
     if (e->t >= e->cfg.terminal_time - e->cfg.step_size / 2) return fail(MBT_E_STATE, "episode already finished; call mbt_reset");
     if (returns_all && !returns_local) return fail(MBT_E_INVALID_ARG, "returns_all needs returns_local (the shard's own returns)");
     CU(cudaSetDevice(e->device));
-    if (e->gather_pending) { /* the previous episode's gather reads that episode's returns: order this rollout's writes behind it
-                                only if the caller reuses the same buffer -- it may not know, so always order */
+    if (e->gather_pending && returns_local == e->gather_src) {
+        /* the previous episode's gather is still reading this buffer: order the rollout's writes behind it.  A caller
+         * that alternates two returns buffers gets the gather overlapped with the next episode's rollout. */
         CU(cudaStreamWaitEvent(e->stream, e->ev_gather, 0));
         e->gather_pending = false;
     }
@@ -1586,6 +1617,7 @@ int mbt_group_rollout(mbt_env *e, const mbt_policy *policy, mbt_summary *summary
         }
         CU(cudaEventRecord(e->ev_gather, e->comm_stream));
         e->gather_pending = true;
+        e->gather_src = returns_local;
     }
     long long total = 0;
     for (long long c : e->g_counts) total += c;

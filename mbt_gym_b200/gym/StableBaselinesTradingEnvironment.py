@@ -17,20 +17,23 @@ except Exception:  # noqa: BLE001
     _VecEnvBase = object
 
 
-class _TerminalInfos:
-    """Sequence of N dicts built on demand: {"terminal_observation": terminal_obs[i]} and, with `monitor=True`,
-    {"episode": {"r": return, "l": length, "t": seconds}} -- the entries SB3's VecMonitor would add."""
+class _TerminalInfos(list):
+    """The `infos` of an episode-ending step: a real `list` of N dicts -- {"terminal_observation": terminal_obs[i]} and,
+    with `monitor=True`, {"episode": {"r": return, "l": length, "t": seconds}} (what SB3's VecMonitor would add) -- whose
+    items are built on first use instead of by an O(N) Python loop at every episode end (reference :31-35).
+    `len()` and single-item reads cost O(1); a built item is kept, so `infos[i]["key"] = v` and `infos[i] = d` stick;
+    anything that looks at the whole list (iteration, slices, `list(infos)`, `==`, pickling ...) materialises all items
+    once and from then on it IS an ordinary list."""
 
     def __init__(self, terminal_obs, episode=None):
+        super().__init__()
         self._obs = terminal_obs
         self._episode = episode  # (returns (N,), length, elapsed seconds) or None
+        self._n = int(terminal_obs.shape[0] if terminal_obs is not None else episode[0].shape[0])
+        self._made = {}
+        self._filled = False
 
-    def __len__(self):
-        return self._obs.shape[0] if self._obs is not None else self._episode[0].shape[0]
-
-    def __getitem__(self, i):
-        if isinstance(i, slice):
-            return [self[j] for j in range(*i.indices(len(self)))]
+    def _make(self, i):
         info = {}
         if self._obs is not None:
             info["terminal_observation"] = self._obs[i, :]
@@ -39,11 +42,72 @@ class _TerminalInfos:
             info["episode"] = {"r": float(ret[i]), "l": int(length), "t": elapsed}
         return info
 
+    def _fill(self):
+        if not self._filled:
+            made = self._made
+            list.extend(self, (made[i] if i in made else self._make(i) for i in range(self._n)))
+            self._filled, self._made = True, {}
+        return self
+
+    def __len__(self):
+        return list.__len__(self) if self._filled else self._n
+
+    def __bool__(self):
+        return len(self) > 0
+
+    def __getitem__(self, i):
+        if self._filled or isinstance(i, slice):
+            return list.__getitem__(self._fill(), i)
+        j = i + self._n if i < 0 else i
+        if not 0 <= j < self._n:
+            raise IndexError("list index out of range")
+        if j not in self._made:
+            self._made[j] = self._make(j)
+        return self._made[j]
+
+    def __setitem__(self, i, value):
+        if self._filled or isinstance(i, slice):
+            return list.__setitem__(self._fill(), i, value)
+        j = i + self._n if i < 0 else i
+        if not 0 <= j < self._n:
+            raise IndexError("list assignment index out of range")
+        self._made[j] = value
+
     def __iter__(self):
-        return (self[i] for i in range(len(self)))
+        return list.__iter__(self._fill())
+
+    def __reversed__(self):
+        return list.__reversed__(self._fill())
+
+    def __contains__(self, x):
+        return list.__contains__(self._fill(), x)
+
+    def __eq__(self, other):
+        return list.__eq__(self._fill(), other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        return list.__repr__(self) if self._filled else f"<{self._n} lazy episode-end infos>"
+
+    def __reduce__(self):
+        return (list, (list(self),))
 
     def copy(self):
         return list(self)
+
+
+def _mutator(name):
+    def method(self, *args, **kwargs):
+        return getattr(list, name)(self._fill(), *args, **kwargs)
+
+    method.__name__ = name
+    return method
+
+
+for _name in ("append", "extend", "insert", "pop", "remove", "clear", "sort", "reverse", "index", "count", "__delitem__",
+              "__add__", "__iadd__", "__mul__", "__imul__", "__rmul__"):
+    setattr(_TerminalInfos, _name, _mutator(_name))
 
 
 class StableBaselinesTradingEnvironment(_VecEnvBase):

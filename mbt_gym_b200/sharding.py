@@ -6,6 +6,17 @@ trajectory ids, so the simulated trajectories are identical for 1, 2, 4 or 8 GPU
 communication; the only exchange is per episode: an all-reduce (sum) of the `mbt_summary` moments and, optionally, an
 all-gather of per-trajectory episode returns (BASELINE configs[4] "NCCL gather of returns").
 
+One exception, inherited from the reference: the Triangular and Power fill functions reduce the quoted depths over the
+WHOLE batch (`np.max(depths, 0)`, fill_probability_models.py:82,113), which couples the trajectories of a step.  With a
+library group attached (`create_group`) `step()` all-reduces (max) the shard maxima over NCCL before the step, so results
+are again independent of the shard layout; WITHOUT a group every shard reduces over its own trajectories only, i.e. it
+behaves like one worker of the reference's MultiprocessTradingEnv.
+
+On GPUs the collectives run INSIDE the library (`mbt_group_*`, include/mbt_b200.h): NCCL on device buffers, on the
+handle's stream, the summary never leaving the device before it is reduced.  `create_group` only ships the NCCL unique id
+over `torch.distributed`.  The `allreduce_summary` / `allgather_returns` helpers below do the same exchange through
+`torch.distributed` itself; they are what the CPU (gloo) tests exercise and a cross-check for the library path.
+
 Replaces the reference's process fan-out (mbt_gym/gym/MultiprocessTradingEnv.py:72-116: SubprocVecEnv over pipes,
 results concatenated by `flatten_multi`).
 """
@@ -65,6 +76,24 @@ def results_table(summary, action_dim):
     }
 
 
+def create_group(native_env, group=None):
+    """Join this rank's device handle (`env._ensure_native()` / `_lib.NativeEnv`) to a library-level NCCL group spanning
+    the ranks of the `torch.distributed` group: rank 0 creates the NCCL unique id, `broadcast_object_list` ships it."""
+    import torch.distributed as dist
+
+    from . import _lib
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [_lib.NativeEnv.group_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    native_env.group_create(box[0], rank, world)
+    return native_env.group_info()
+
+
+def summary_struct_to_dict(summary):
+    return array_to_summary(summary_to_array(summary))
+
+
 def allreduce_summary(summary, group=None, device=None):
     """All-reduce (sum) of the summary moments over `torch.distributed` (NCCL on GPUs, gloo in the CPU tests)."""
     import torch
@@ -87,11 +116,24 @@ def allreduce_summary(summary, group=None, device=None):
 
 
 def allgather_returns(returns, group=None):
-    """All-gather per-trajectory episode returns (torch tensor, same length on every rank) in global-id order."""
+    """All-gather per-trajectory episode returns (torch tensor) in global-id order; shard lengths may differ by one
+    (`shard_bounds` when N % world != 0), so the lengths are exchanged first and the short shards padded."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    out = torch.empty((world * returns.numel(),), dtype=returns.dtype, device=returns.device)
-    dist.all_gather_into_tensor(out, returns.contiguous(), group=group)
-    return out
+    returns = returns.contiguous().reshape(-1)
+    n = torch.tensor([returns.numel()], dtype=torch.int64, device=returns.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x) for x in sizes]
+    width = max(sizes)
+    if min(sizes) == width:
+        out = torch.empty((world * width,), dtype=returns.dtype, device=returns.device)
+        dist.all_gather_into_tensor(out, returns, group=group)
+        return out
+    padded = torch.zeros((width,), dtype=returns.dtype, device=returns.device)
+    padded[: returns.numel()] = returns
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:k] for p, k in zip(parts, sizes)])

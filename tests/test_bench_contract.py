@@ -22,6 +22,11 @@ def test_reference_arm_prints_one_json_line_with_contract_keys():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 1e5
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
+    # both arms print the SAME config object for the same command line (the driver compares them key by key)
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.config_dict("as", bench.N_PER_GPU, bench.N_PER_GPU)
 
 
 def test_reference_arm_non_zero_rank_is_silent():
