@@ -36,8 +36,7 @@
 #ifndef MBT_B200_H
 #define MBT_B200_H
 
-#include <stddef.h>
-#include <stdint.h>
+#include "mbt_rtc.h" /* <stddef.h>, <stdint.h> (or their NVRTC stand-ins) */
 
 #ifdef __cplusplus
 extern "C" {
@@ -401,6 +400,32 @@ int mbt_group_rollout(mbt_env *env, const mbt_policy *policy, mbt_summary *summa
                       void *returns_all_out);
 int mbt_group_summary(mbt_env *env, const mbt_summary *local, mbt_summary *global_out);
 int mbt_group_wait(mbt_env *env, int host_sync);
+
+/*
+ * Run-time specialisation (csrc/mbt_jit.h).  mbt_create / mbt_reconfigure compile -- once per configuration KIND, cached
+ * per process and on disk -- a step kernel with every model kind, reward kind, normalisation flag and column mask of the
+ * handle's configuration fixed at compile time (NVRTC; the same kernel bodies and floating-point flags as the
+ * ahead-of-time build, so results are bit-identical), unless one of the fully specialised ahead-of-time variants already
+ * serves the configuration.  Without libnvrtc the ahead-of-time kernels run (`message` says why); MBT_JIT=0 switches the
+ * specialiser off, MBT_JIT=require turns its failure into an error of mbt_create.
+ */
+typedef struct mbt_kernel_info {
+    int32_t aot_variant;          /* index into the ahead-of-time table (0 = generic kernel with run-time switches) */
+    int32_t jit_mode;             /* 0 off, 1 on (fallback allowed), 2 required */
+    int32_t step_is_jit;          /* the step kernel this handle launches was specialised at run time */
+    int32_t step_registers;       /* registers per thread / local-memory bytes of that kernel (0 when not JIT) */
+    int32_t step_local_bytes;
+    int32_t jit_from_disk_cache;  /* the cubin came from the on-disk cache (no compile in this process) */
+    double jit_compile_ms;        /* time spent compiling or reading it */
+    uint64_t jit_hash;            /* cache key: <library dir>/_jit_cache/<hash>.cubin */
+    int32_t rollout_is_jit[5];    /* per policy kind (MBT_POL_*), [4] = the recording kernel: specialised kernels loaded so far */
+    int32_t _pad;
+    char message[256];            /* why the specialiser is not in use, if it should be */
+} mbt_kernel_info;
+int mbt_get_kernel_info(mbt_env *env, mbt_kernel_info *out);
+/* Compile the specialised kernel of `cfg` into the on-disk cache WITHOUT a CUDA device (build machines): kind 0 = step,
+ * 1 = rollout with `policy_kind` compiled in (or the recording kernel when `record`). */
+int mbt_jit_precompile(const mbt_config *cfg, int32_t kind, int32_t policy_kind, int32_t record);
 
 /* Per-call statistics for bench.py: number of kernel launches issued by this handle so far, and the
  * device time (ms, CUDA events on the handle's stream) of the most recent step kernel when enabled. */

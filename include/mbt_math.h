@@ -20,9 +20,7 @@
 #ifndef MBT_MATH_H
 #define MBT_MATH_H
 
-#include <math.h>
-#include <stdint.h>
-#include <string.h>
+#include "mbt_rtc.h" /* <math.h>, <stdint.h>, <string.h> -- or their NVRTC stand-ins */
 
 #include "mbt_philox.h" /* MBT_HD */
 

@@ -22,7 +22,7 @@
 #ifndef MBT_PHILOX_H
 #define MBT_PHILOX_H
 
-#include <stdint.h>
+#include "mbt_rtc.h" /* <stdint.h> or its NVRTC stand-in */
 
 #if defined(__CUDACC__)
 #define MBT_HD __host__ __device__ __forceinline__

@@ -196,6 +196,22 @@ class mbt_summary(C.Structure):
     ]
 
 
+class mbt_kernel_info(C.Structure):
+    _fields_ = [
+        ("aot_variant", C.c_int32),
+        ("jit_mode", C.c_int32),
+        ("step_is_jit", C.c_int32),
+        ("step_registers", C.c_int32),
+        ("step_local_bytes", C.c_int32),
+        ("jit_from_disk_cache", C.c_int32),
+        ("jit_compile_ms", C.c_double),
+        ("jit_hash", C.c_uint64),
+        ("rollout_is_jit", C.c_int32 * 5),
+        ("_pad", C.c_int32),
+        ("message", C.c_char * 256),
+    ]
+
+
 def new_config(**kw):
     """Zero-initialised mbt_config with struct_size set and the given fields assigned."""
     cfg = mbt_config()

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "mbt_host_alloc", "mbt_host_alloc_near", "mbt_host_free", "mbt_checkpoint_size", "mbt_checkpoint_save",
     "mbt_checkpoint_load", "mbt_fold_counters", "mbt_prepare_capture", "mbt_get_seed", "mbt_set_counters", "mbt_reconfigure",
     "mbt_group_unique_id", "mbt_group_create", "mbt_group_destroy", "mbt_group_info", "mbt_group_rollout", "mbt_group_summary",
-    "mbt_group_wait",
+    "mbt_group_wait", "mbt_get_kernel_info", "mbt_jit_precompile",
 ]
 
 _lib = None
@@ -85,6 +85,8 @@ def load():
     L.mbt_group_rollout.argtypes = [vp, C.POINTER(_abi.mbt_policy), C.POINTER(_abi.mbt_summary), vp, vp]
     L.mbt_group_summary.argtypes = [vp, C.POINTER(_abi.mbt_summary), C.POINTER(_abi.mbt_summary)]
     L.mbt_group_wait.argtypes = [vp, C.c_int]
+    L.mbt_get_kernel_info.argtypes = [vp, C.POINTER(_abi.mbt_kernel_info)]
+    L.mbt_jit_precompile.argtypes = [cfgp, C.c_int32, C.c_int32, C.c_int32]
     if L.mbt_abi_version() != _abi.MBT_ABI_VERSION:
         raise ImportError(f"libmbt_b200.so ABI {L.mbt_abi_version()} != binding ABI {_abi.MBT_ABI_VERSION}")
     _lib = L
@@ -94,6 +96,11 @@ def load():
 def _check(rc):
     if rc != 0:
         raise MbtError(rc, load().mbt_last_error().decode("utf-8", "replace"))
+
+
+def jit_precompile(cfg, kind=0, policy_kind=0, record=False):
+    """Compile the run-time specialised kernel of `cfg` into the on-disk cache (no CUDA device needed)."""
+    _check(load().mbt_jit_precompile(C.byref(cfg), int(kind), int(policy_kind), int(bool(record))))
 
 
 def config_dims(cfg):
@@ -367,6 +374,16 @@ class NativeEnv:
         _check(load().mbt_checkpoint_load(self._h, buf.ctypes.data, buf.size))
 
     # -- statistics
+    def kernel_info(self):
+        """Which step / rollout kernels this handle launches (run-time specialised or ahead-of-time), registers, cache."""
+        info = _abi.mbt_kernel_info()
+        _check(load().mbt_get_kernel_info(self._h, C.byref(info)))
+        return dict(aot_variant=info.aot_variant, jit_mode=info.jit_mode, step_is_jit=bool(info.step_is_jit),
+                    step_registers=info.step_registers, step_local_bytes=info.step_local_bytes,
+                    jit_from_disk_cache=bool(info.jit_from_disk_cache), jit_compile_ms=info.jit_compile_ms,
+                    jit_hash=f"{info.jit_hash:016x}", rollout_is_jit=list(info.rollout_is_jit),
+                    message=info.message.decode("utf-8", "replace"))
+
     def launch_count(self):
         c = C.c_int64()
         _check(load().mbt_get_launch_count(self._h, C.byref(c)))

@@ -19,10 +19,11 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/mbt_b200.h"
+#include "mbt_b200.h"
 #include "mbt_host_params.h"
 #include "mbt_variants.h"
 #include "mbt_kernels.cuh"
+#include "mbt_jit.h"
 
 /* ------------------------------------------------------------------ errors */
 static thread_local std::string g_err;
@@ -71,7 +72,7 @@ struct mbt_env {
     cudaEvent_t ev_in[MBT_PIPE_CHUNKS] = {}, ev_k[MBT_PIPE_CHUNKS] = {};
 
     /* batch reduction in front of the step (Triangular / Power fill functions): running maxima (keys), ticket, thresholds */
-    void *d_fill_partial = nullptr, *d_fill_thr = nullptr;
+    void *d_fill_partial = nullptr;
     unsigned int *d_fill_ticket = nullptr;
     int fill_blocks = 1;
 
@@ -107,6 +108,12 @@ struct mbt_env {
     int q0_per_traj = 0;
     double q0_uniform = 0;
 
+    /* run-time specialised kernels of this configuration (mbt_jit.h); NULL = the ahead-of-time table is used */
+    const mbt_jit::Module *jit_step = nullptr;
+    const mbt_jit::Module *jit_roll[5] = {}; /* MBT_POL_FIXED .. MBT_POL_SCHEDULE, [4] = recording */
+    int jit_roll_state[5] = {};              /* 0 untried, 1 ready, -1 failed */
+    std::string jit_error;                   /* why the specialiser is not in use (empty = in use or switched off) */
+
     /* statistics */
     int64_t launches = 0;
     int timing = 0; /* 0 off, 1 two events around every kernel, 2 one event before every kernel (interval timing) */
@@ -114,6 +121,8 @@ struct mbt_env {
     int64_t timed = 0;
     bool interval_closed = false;
 };
+
+static bool stream_is_capturing_fwd(mbt_env *e);
 
 template <typename T>
 static DevState<T> dev_state(mbt_env *e) {
@@ -140,6 +149,40 @@ static int fill_blocks_per_sm() {
 /* does a step of this config start with the batch reduction of the quoted depths? */
 static inline bool needs_fill_batch(const mbt_config &c) {
     return fill_is_batch(c.fill) && (c.dynamics == MBT_DYN_LIMIT || c.dynamics == MBT_DYN_LIMIT_AND_MARKET);
+}
+
+/*
+ * MBT_L2_PERSIST=1 (opt-in, measured in profiles/r2_session_notes.md): keep the structure-of-arrays state block -- read and
+ * rewritten by EVERY step, 25 MB for the BASELINE market at 2^20 trajectories -- resident in the 126 MB L2 with an
+ * access-policy window on the handle's stream, while the caller's action / observation / reward buffers stream through.
+ */
+static bool l2_persist_enabled() {
+    static const bool on = [] {
+        const char *v = getenv("MBT_L2_PERSIST");
+        return v && v[0] == '1';
+    }();
+    return on;
+}
+
+static void apply_l2_window(mbt_env *e, cudaStream_t stream) {
+    if (!l2_persist_enabled() || !stream) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
+    const size_t col_bytes = (((size_t)e->N * e->esz) + 255) & ~(size_t)255;
+    size_t bytes = col_bytes * 5; /* cash, inventory, midprice, x0, x1 (contiguous; q0 / variance follow) */
+    bytes = std::min(bytes, (size_t)std::max(0, max_window));
+    if (max_persist <= 0 || bytes == 0) return;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)max_persist, bytes));
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
+    v.accessPolicyWindow.base_ptr = e->state_block;
+    v.accessPolicyWindow.num_bytes = bytes;
+    v.accessPolicyWindow.hitRatio = bytes <= (size_t)max_persist ? 1.0f : (float)max_persist / (float)bytes;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaGetLastError();
 }
 
 static int timing_begin(mbt_env *e) {
@@ -259,6 +302,50 @@ static void par_memcpy(void *dst, const void *src, size_t bytes) {
     for (auto &t : th) t.join();
 }
 
+/* ------------------------------------------------------------------ run-time specialisation (mbt_jit.h) */
+/* configurations whose ahead-of-time variant still reads model kinds or normalisation flags at run time */
+static bool wants_jit(const mbt_config &c) {
+    const int v = variant_of(c);
+    return v == 0 || v == 4 || v == 6 || v == 9;
+}
+
+/* (re)select the step kernel of the handle's configuration: called by mbt_create and mbt_reconfigure, never inside a
+ * stream capture.  Returns an error only when MBT_JIT=require. */
+static int jit_select_step(mbt_env *e) {
+    e->jit_step = nullptr;
+    for (int i = 0; i < 5; ++i) { e->jit_roll[i] = nullptr; e->jit_roll_state[i] = 0; }
+    e->jit_error.clear();
+    if (mbt_jit::mode() == 0 || !wants_jit(e->cfg)) return MBT_OK;
+    const mbt_jit::Key key = mbt_jit::key_of(e->cfg, e->io_esz == 8, mbt_jit::STEP, 0, 0);
+    std::string err;
+    int rc = mbt_jit::module_of(key, &e->jit_step, err);
+    if (rc) {
+        e->jit_step = nullptr;
+        e->jit_error = err;
+        if (mbt_jit::mode() == 2) return fail(rc, "MBT_JIT=require: " + err);
+    }
+    return MBT_OK;
+}
+
+/* the specialised rollout kernel for policy slot `slot` (lazily; not while capturing); *out = NULL -> ahead-of-time table */
+static int jit_rollout_module(mbt_env *e, int slot, const mbt_jit::Module **out) {
+    *out = nullptr;
+    if (slot < 0 || slot > 4 || mbt_jit::mode() == 0 || !wants_jit(e->cfg)) return MBT_OK;
+    if (e->jit_roll_state[slot] == 0 && !stream_is_capturing_fwd(e)) {
+        const mbt_jit::Key key = mbt_jit::key_of(e->cfg, e->esz == 8, mbt_jit::ROLLOUT, slot == 4 ? -1 : slot, slot == 4);
+        std::string err;
+        int rc = mbt_jit::module_of(key, &e->jit_roll[slot], err);
+        e->jit_roll_state[slot] = rc ? -1 : 1;
+        if (rc) {
+            e->jit_roll[slot] = nullptr;
+            e->jit_error = err;
+            if (mbt_jit::mode() == 2) return fail(rc, "MBT_JIT=require: " + err);
+        }
+    }
+    if (e->jit_roll_state[slot] == 1) *out = e->jit_roll[slot];
+    return MBT_OK;
+}
+
 /* ------------------------------------------------------------------ launchers */
 /* is the handle's stream being captured into a CUDA graph right now? */
 static bool stream_is_capturing(mbt_env *e) {
@@ -269,6 +356,8 @@ static bool stream_is_capturing(mbt_env *e) {
     }
     return st == cudaStreamCaptureStatusActive;
 }
+
+static bool stream_is_capturing_fwd(mbt_env *e) { return stream_is_capturing(e); }
 
 /*
  * Counters of the draw contract.  Effective counter of a launch = host counter baked into its arguments + device-resident
@@ -333,6 +422,24 @@ static void launch_step_k(mbt_env *e, const StepArgs<T, E> &g, bool allow_pdl) {
     cudaLaunchKernelEx(&cfg, mbt_step_kernel<T, E, V, VEC>, g);
 }
 
+/* the run-time specialised step kernel of the handle's configuration (same argument block, same launch attributes) */
+template <typename T, typename E>
+static void launch_step_jit(mbt_env *e, const StepArgs<T, E> &g, bool vec, bool allow_pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid_for(g.n));
+    cfg.blockDim = dim3(MBT_BLOCK);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    const bool pdl = allow_pdl && use_pdl();
+    cfg.attrs = pdl ? attr : nullptr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    void *args[1] = {const_cast<StepArgs<T, E> *>(&g)};
+    cudaLaunchKernelExC(&cfg, (const void *)(vec ? e->jit_step->k0 : e->jit_step->k1), args);
+}
+
 template <typename T, typename E, class V>
 static void launch_step_v(mbt_env *e, const StepArgs<T, E> &g, bool vec, bool allow_pdl) {
     if (vec)
@@ -368,17 +475,22 @@ static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<
     g.traj_offset = (unsigned long long)c.traj_offset + (unsigned long long)r0;
     g.n_step = (unsigned long long)e->n_step;
     g.clipped = e->d_clipped;
-    g.fill_thr = (const T *)e->d_fill_thr;
+    g.fill_cells = (unsigned long long *)e->d_fill_partial;
+    g.fill_ticket = e->d_fill_ticket;
     {
         int rcb = counter_base_for_launch(e, &g.counter_base);
         if (rcb) return rcb;
     }
     if (g.counter_base) allow_pdl = false; /* the base is written by a kernel: order behind it */
     const bool vec = rows_vector_aligned<E>(e, g.actions, g.obs);
-    switch (variant_of(c)) {
+    if (e->jit_step) {
+        launch_step_jit<T, E>(e, g, vec, allow_pdl);
+    } else {
+        switch (variant_of(c)) {
 #define X(id, ...) case id: launch_step_v<T, E, __VA_ARGS__>(e, g, vec, allow_pdl); break;
-        MBT_FOR_EACH_VARIANT(X)
+            MBT_FOR_EACH_VARIANT(X)
 #undef X
+        }
     }
     CU(cudaGetLastError());
     e->launches += 1;
@@ -387,40 +499,40 @@ static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<
 
 static int group_allreduce_max_u64(mbt_env *e, unsigned long long *dev, int count);
 
-/* the batch reduction of the quoted depths (mbt_fill_batch_kernel) over ALL rows of the action matrix */
+/* the batch reduction of the quoted depths (mbt_fill_batch_kernel) over ALL rows of the action matrix; the maxima stay
+ * in e->d_fill_partial (keys) for the step kernel that follows */
 template <typename T, typename E>
-static int launch_fill_batch(mbt_env *e, const StepParams<T> &p, const void *actions) {
+static int launch_fill_batch(mbt_env *e, const StepParams<T> &p, const void *actions, bool allow_pdl) {
     FillBatchArgs<T, E> g;
     g.p = p;
     g.actions = (const E *)actions;
     g.n = e->N;
     g.cells = (unsigned long long *)e->d_fill_partial;
-    g.ticket = e->d_fill_ticket;
-    g.thr = (T *)e->d_fill_thr;
     const unsigned blocks = std::min<unsigned>(grid_for(e->N), (unsigned)e->fill_blocks);
     /* rows of 2 or 4 elements whose base is aligned to a 2-element vector: one vector load per row */
     const bool vec = (e->A == 2 || e->A == 4) && ((uintptr_t)actions % (2 * sizeof(E))) == 0;
-    if (e->comm) {
-        /* group of handles: np.max(depths, 0) runs over the trajectories of ALL ranks -- shard maxima (keys), NCCL
-         * all-reduce (max) on the handle's stream, thresholds from the global maxima */
-        if (vec)
-            mbt_fill_batch_kernel<T, E, true, false><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
-        else
-            mbt_fill_batch_kernel<T, E, false, false><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
-        CU(cudaGetLastError());
-        int rc = group_allreduce_max_u64(e, g.cells, 2);
-        if (rc) return rc;
-        mbt_fill_finalize_kernel<T><<<1, 1, 0, e->stream>>>(p, g.cells, g.thr);
-        CU(cudaGetLastError());
-        e->launches += 2;
-        return MBT_OK;
-    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(MBT_BLOCK);
+    cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    const bool pdl = allow_pdl && use_pdl();
+    cfg.attrs = pdl ? attr : nullptr;
+    cfg.numAttrs = pdl ? 1 : 0;
     if (vec)
-        mbt_fill_batch_kernel<T, E, true, true><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
+        cudaLaunchKernelEx(&cfg, mbt_fill_batch_kernel<T, E, true>, g);
     else
-        mbt_fill_batch_kernel<T, E, false, true><<<blocks, MBT_BLOCK, 0, e->stream>>>(g);
+        cudaLaunchKernelEx(&cfg, mbt_fill_batch_kernel<T, E, false>, g);
     CU(cudaGetLastError());
     e->launches += 1;
+    if (e->comm) {
+        /* group of handles: np.max(depths, 0) runs over the trajectories of ALL ranks -- NCCL all-reduce (max) of the two
+         * keys on the handle's stream, between the reduction and the step */
+        int rc = group_allreduce_max_u64(e, g.cells, 2);
+        if (rc) return rc;
+    }
     return MBT_OK;
 }
 
@@ -440,10 +552,12 @@ static int do_step_device(mbt_env *e, const void *actions, void *obs, void *rew,
     if (rc) return rc;
     const bool batch = needs_fill_batch(c);
     if (batch) {
-        rc = launch_fill_batch<T, E>(e, p, actions);
+        /* (device-counter mode: the previous launch may be the one-thread fold kernel, which is not PDL-aware) */
+        rc = launch_fill_batch<T, E>(e, p, actions, /*allow_pdl=*/!e->device_counters);
         if (rc) return rc;
     }
-    rc = launch_step_rows<T, E>(e, p, ck, actions, obs, rew, 0, e->N, /*allow_pdl=*/!batch);
+    /* behind an NCCL all-reduce (group of handles) the step is launched plainly */
+    rc = launch_step_rows<T, E>(e, p, ck, actions, obs, rew, 0, e->N, /*allow_pdl=*/!(batch && e->comm));
     if (rc) return rc;
     rc = timing_end(e);
     if (rc) return rc;
@@ -526,7 +640,7 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
         CU(cudaEventRecord(e->ev_in[k], e->copy_in));
         CU(cudaStreamWaitEvent(e->stream, e->ev_in[k], 0));
         if (batch) {
-            int rcb = launch_fill_batch<T, E>(e, p, e->d_actions);
+            int rcb = launch_fill_batch<T, E>(e, p, e->d_actions, /*allow_pdl=*/false);
             if (rcb) return rcb;
         }
         int rc = launch_step_rows<T, E>(e, p, ck, e->d_actions, obs_dst ? e->d_obs : nullptr, rew_dst ? e->d_rew : nullptr, r0, n,
@@ -673,7 +787,6 @@ int mbt_destroy(mbt_env *e) {
     cudaFree(e->d_clipped);
     cudaFree(e->d_counter_base);
     cudaFree(e->d_fill_partial);
-    cudaFree(e->d_fill_thr);
     cudaFree(e->d_fill_ticket);
     cudaFree(e->d_actions);
     cudaFree(e->d_obs);
@@ -763,9 +876,7 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     e->fill_blocks = std::max(1, e->sm_count * fill_blocks_per_sm()); /* every block ends in 3 same-address atomics */
     CUB(cudaMalloc(&e->d_fill_partial, 2 * sizeof(unsigned long long)));
     CUB(cudaMemsetAsync(e->d_fill_partial, 0, 2 * sizeof(unsigned long long), e->stream));
-    CUB(cudaMalloc(&e->d_fill_thr, 2 * sizeof(double)));
     CUB(cudaMalloc((void **)&e->d_fill_ticket, sizeof(unsigned int)));
-    CUB(cudaMemsetAsync(e->d_fill_thr, 0, 2 * sizeof(double), e->stream));
     CUB(cudaMemsetAsync(e->d_fill_ticket, 0, sizeof(unsigned int), e->stream));
     /* episode summary: folded on the device by the rollout kernel, mirrored to pinned host memory on demand */
     CUB(cudaMalloc((void **)&e->d_summary, MBT_SUMMARY_DOUBLES * sizeof(double)));
@@ -775,6 +886,8 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     CUB(cudaMemsetAsync(e->d_roll_ticket, 0, sizeof(unsigned int), e->stream));
     CUB(cudaStreamSynchronize(e->stream));
 #undef CUB
+    if ((rc = jit_select_step(e)) != MBT_OK) return bail(rc);
+    apply_l2_window(e, e->own_stream);
     *out = e;
     return MBT_OK;
 }
@@ -786,6 +899,7 @@ int mbt_set_stream(mbt_env *e, void *cuda_stream) {
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream)); /* work queued on the old stream must finish before the new one is used */
     e->stream = next;
+    apply_l2_window(e, next);
     return MBT_OK;
 }
 
@@ -853,7 +967,8 @@ int mbt_reconfigure(mbt_env *e, const mbt_config *cfg) {
     if (stream_is_capturing(e)) return fail(MBT_E_STATE, "mbt_reconfigure is not capturable");
     e->cfg = *cfg;
     e->Dout = mbt_obs_out_dim(cfg, e->D);
-    return MBT_OK;
+    CU(cudaSetDevice(e->device));
+    return jit_select_step(e);
 }
 
 /* lazily allocate the device + pinned staging used by MBT_MEM_HOST calls */
@@ -1239,6 +1354,17 @@ static int enqueue_rollout(mbt_env *e, const mbt_policy *pol, void *returns, voi
     int rc = timing_begin(e);
     if (rc) return rc;
     /* the fast path (no recording) has the policy kind compiled in; the recording kernels (store-bound) switch at run time */
+    const mbt_jit::Module *jm = nullptr;
+    rc = jit_rollout_module(e, rec ? 4 : pol->kind, &jm);
+    if (rc) return rc;
+    if (jm) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)blocks);
+        lc.blockDim = dim3(MBT_BLOCK);
+        lc.stream = e->stream;
+        void *args[1] = {&g};
+        cudaLaunchKernelExC(&lc, (const void *)jm->k0, args);
+    } else
     switch (variant_of(c)) {
 #define X(id, ...)                                                                                                        \
     case id:                                                                                                              \
@@ -1651,6 +1777,44 @@ int mbt_group_wait(mbt_env *e, int host_sync) {
         CU(cudaStreamSynchronize(e->comm_stream));
         CU(cudaStreamSynchronize(e->stream));
     }
+    return MBT_OK;
+}
+
+} /* extern "C" */
+
+extern "C" {
+
+int mbt_get_kernel_info(mbt_env *e, mbt_kernel_info *out) {
+    if (!e || !out) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    memset(out, 0, sizeof *out);
+    out->aot_variant = variant_of(e->cfg);
+    out->jit_mode = mbt_jit::mode();
+    if (e->jit_step) {
+        out->step_is_jit = 1;
+        out->step_registers = e->jit_step->regs;
+        out->step_local_bytes = e->jit_step->local_bytes;
+        out->jit_compile_ms = e->jit_step->compile_ms;
+        out->jit_from_disk_cache = e->jit_step->from_disk ? 1 : 0;
+        out->jit_hash = e->jit_step->hash;
+    }
+    for (int i = 0; i < 5; ++i) out->rollout_is_jit[i] = e->jit_roll_state[i] == 1;
+    snprintf(out->message, sizeof out->message, "%s", e->jit_error.c_str());
+    return MBT_OK;
+}
+
+int mbt_jit_precompile(const mbt_config *cfg, int32_t kind, int32_t policy_kind, int32_t record) {
+    std::string err;
+    int rc = mbt_validate_config(cfg, err);
+    if (rc) return fail(rc, err);
+    if (!wants_jit(*cfg)) return MBT_OK; /* served by a fully specialised ahead-of-time variant */
+    const int io64 = cfg->precision == MBT_F64 && (kind != 0 || cfg->io_precision == MBT_IO_SAME);
+    const mbt_jit::Key key = mbt_jit::key_of(*cfg, io64, kind == 0 ? mbt_jit::STEP : mbt_jit::ROLLOUT, record ? -1 : policy_kind, record ? 1 : 0);
+    std::vector<char> cubin;
+    unsigned long long h = 0;
+    bool from_disk = false;
+    double ms = 0;
+    rc = mbt_jit::cubin_of(key, cubin, &h, &from_disk, &ms, err);
+    if (rc) return fail(rc, err);
     return MBT_OK;
 }
 

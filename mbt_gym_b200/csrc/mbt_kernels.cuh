@@ -21,7 +21,9 @@
 #ifndef MBT_KERNELS_CUH
 #define MBT_KERNELS_CUH
 
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 
 #include "mbt_step_core.cuh"
 
@@ -49,7 +51,10 @@ struct StepArgs {
     mbt_philox_keys keys; /* the ten Philox round keys of the seed, expanded on the host */
     unsigned long long traj_offset, n_step;
     unsigned long long *clipped;
-    const T *fill_thr; /* batch-reduced fill models: the step's two thresholds, written by mbt_fill_batch_kernel */
+    /* batch-reduced fill models: the two running maxima of the quoted depths (order-preserving keys) that
+     * mbt_fill_batch_kernel left in front of this launch, and the ticket by which the last block clears them */
+    unsigned long long *fill_cells;
+    unsigned int *fill_ticket;
     /* CUDA-graph replay (mbt_fold_counters): NULL, or the device-resident base {steps, episodes} that is added to the
      * counters baked into this launch -- a captured episode replays with fresh random numbers every time */
     const unsigned long long *counter_base;
@@ -59,12 +64,10 @@ struct StepArgs {
 template <typename T, class V>
 __device__ __forceinline__ int action_width(const StepParams<T> &p) { return V::A ? V::A : p.action_dim; }
 template <typename T, class V>
-__device__ __forceinline__ int obs_width(const StepParams<T> &p) {
-    /* the fully specialised variants (V::norm >= 0) never select columns: variant_of() routes obs_select to the others */
-    return (V::D && V::norm >= 0) ? V::D : p.obs_out_dim;
-}
+__device__ __forceinline__ int obs_width(const StepParams<T> &p) { return V::Dout ? V::Dout : p.obs_out_dim; }
 
 /* ------------------------------------------------------------------ row access helpers */
+#ifndef MBT_NO_256BIT
 __device__ __forceinline__ void st_v4_f64(double *ptr, double a, double b, double c, double d) {
     /* sm_100: 256-bit global store (SASS STG.E.ENL2.256), 32-byte aligned */
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(ptr), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
@@ -72,6 +75,16 @@ __device__ __forceinline__ void st_v4_f64(double *ptr, double a, double b, doubl
 __device__ __forceinline__ void ld_v4_f64(const double *ptr, double &a, double &b, double &c, double &d) {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(ptr));
 }
+#else /* an NVRTC older than CUDA 12.9 (PTX ISA < 8.8) has no 256-bit vector accesses: two 128-bit ones */
+__device__ __forceinline__ void st_v4_f64(double *ptr, double a, double b, double c, double d) {
+    reinterpret_cast<double2 *>(ptr)[0] = make_double2(a, b);
+    reinterpret_cast<double2 *>(ptr)[1] = make_double2(c, d);
+}
+__device__ __forceinline__ void ld_v4_f64(const double *ptr, double &a, double &b, double &c, double &d) {
+    const double2 lo = __ldg(reinterpret_cast<const double2 *>(ptr)), hi = __ldg(reinterpret_cast<const double2 *>(ptr) + 1);
+    a = lo.x; b = lo.y; c = hi.x; d = hi.y;
+}
+#endif
 
 template <typename T>
 __device__ __forceinline__ void load_row(const T *__restrict__ base, long long i, int w, T *out, bool vec_ok) {
@@ -183,7 +196,7 @@ __device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T
         row[4] = norm_obs<T, V>(p, s.x0, 4);
         d = 5;
     }
-    if (V::dyn < 0 && p.fill == MBT_FILL_EXOGENOUS_MM) {
+    if (pick<V::fill>(p.fill) == MBT_FILL_EXOGENOUS_MM) { /* (p.fill is MBT_FILL_NONE for dynamics that draw no fills) */
         /* the fill model's two columns (constants, see include/mbt_b200.h) come after the arrival model's; `d` is a
          * runtime value here, so each is placed by a compile-time-indexed select chain (no dynamic register indexing) */
         const T c0 = norm_obs<T, V>(p, p.fill_depth0[0], d), c1 = norm_obs<T, V>(p, p.fill_depth0[1], d + 1);
@@ -194,7 +207,8 @@ __device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T
         }
         d += 2;
     }
-    if (V::norm < 0 && p.obs_select) { /* keep the selected columns, in order (gym/wrappers.py:30-38) */
+    const int sel = pick<V::sel>(p.obs_select);
+    if (sel) { /* keep the selected columns, in order (gym/wrappers.py:30-38) */
         /* compaction without dynamically indexed registers (a runtime `row[j++]` would push the whole row into local
          * memory for every launch of the runtime-flag variants, selecting or not): output slot j takes column k when k is
          * the j-th set bit of the mask -- all indices below are compile-time after unrolling, the tests are warp-uniform */
@@ -202,7 +216,7 @@ __device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T
         int j = 0;
 #pragma unroll
         for (int k = 0; k < MBT_MAX_OBS_DIM; ++k) {
-            const bool take = k < d && ((p.obs_select >> k) & 1);
+            const bool take = k < d && ((sel >> k) & 1);
 #pragma unroll
             for (int slot = 0; slot < MBT_MAX_OBS_DIM; ++slot)
                 if (slot <= k && take && slot == j) out[slot] = row[k];
@@ -245,8 +259,19 @@ __device__ __forceinline__ void store_traj(const StepParams<T> &p, const DevStat
 template <typename T, class V>
 __device__ __forceinline__ uint32_t second_normal_bits(const StepParams<T> &p, const mbt_philox_keys &keys,
                                                        unsigned long long traj, unsigned long long n_step) {
-    if (V::mid >= 0 || p.mid != MBT_MID_HESTON) return 0u; /* the specialised variants fix other midprice models */
+    if (pick<V::mid>(p.mid) != MBT_MID_HESTON) return 0u;
     return mbt_normal_bits(mbt_draw_keyed(keys, traj, n_step, MBT_STREAM_STEP2));
+}
+
+/* order-preserving key of a real (float widens exactly): key(a) < key(b) <=> a < b; every NaN -> the largest key */
+__device__ __forceinline__ unsigned long long real_to_key(double x) {
+    if (x != x) return ~0ull;
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_to_real(unsigned long long k) {
+    if (k == ~0ull) return __longlong_as_double(0x7ff8000000000000ll); /* NaN */
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
 }
 
 /* ------------------------------------------------------------------ step */
@@ -260,6 +285,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 template <typename T, typename E, class V, bool VEC>
 __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, bool full_warp, E *warp_smem) {
     const StepParams<T> &p = g.p;
+    const bool live = i < g.n; /* (the threads past the end still take part in the block-level stage below) */
     /* state-independent prologue: the step's 128 random bits depend only on (seed, trajectory id, step index) */
     unsigned long long n_step = g.n_step;
     if (g.counter_base) { /* warp-uniform; such launches are never programmatic (the base is written by a kernel) */
@@ -268,7 +294,30 @@ __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, b
     }
     const mbt_u32x4 r = mbt_draw_keyed(g.keys, g.traj_offset + (unsigned long long)i, n_step, MBT_STREAM_STEP);
     const uint32_t nbits2 = second_normal_bits<T, V>(p, g.keys, g.traj_offset + (unsigned long long)i, n_step);
-    pdl_wait(); /* everything below reads what the previous kernel (previous step, or the caller's policy) wrote */
+    pdl_wait(); /* everything below reads what the previous kernel (previous step, the batch reduction, or the caller's policy) wrote */
+
+    T fill_thr[2] = {(T)0, (T)0};
+    if (fill_is_batch(pick<V::fill>(p.fill))) {
+        /* one thread per block turns the batch maxima into the step's two fill thresholds (2 pow at most) and shares them */
+        __shared__ T s_thr[2];
+        if (threadIdx.x == 0) {
+            T thr[2];
+            fill_batch_thresholds<T>(p, (T)key_to_real(__ldcg(g.fill_cells + 0)), (T)key_to_real(__ldcg(g.fill_cells + 1)), thr);
+            s_thr[0] = thr[0];
+            s_thr[1] = thr[1];
+        }
+        __syncthreads();
+        fill_thr[0] = s_thr[0];
+        fill_thr[1] = s_thr[1];
+        /* the last block to get here has seen every other block read the cells: clear them for the next step's reduction */
+        if (threadIdx.x == 0 && atomicAdd(g.fill_ticket, 1u) == gridDim.x - 1) {
+            g.fill_cells[0] = 0ull;
+            g.fill_cells[1] = 0ull;
+            *g.fill_ticket = 0u;
+        }
+    }
+    if (!live) return;
+
     const int A = action_width<T, V>(p);
     E a_io[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
     load_row<E>(g.actions, i, A, a_io, VEC);
@@ -282,12 +331,6 @@ __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, b
     const int rew_kind = pick<V::rew>(p.rew);
     T q_init = p.q0_uniform;
     if ((rew_kind == MBT_REW_CJ_MM || rew_kind == MBT_REW_CJ_OE) && p.q0_per_traj) q_init = g.st.q0[i];
-
-    T fill_thr[2] = {(T)0, (T)0};
-    if (V::dyn < 0 && fill_is_batch(p.fill)) { /* two uniform scalars, L2-resident broadcast loads */
-        fill_thr[0] = g.fill_thr[0];
-        fill_thr[1] = g.fill_thr[1];
-    }
 
     int clipped = 0;
     const T rwd = step_one<T, V>(p, g.ck, s, a, r, q_init, &clipped, fill_thr, nbits2);
@@ -318,18 +361,24 @@ __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, b
  * VEC: the caller's action/obs pointers are aligned for whole-row vector access.
  */
 template <typename T, typename E, class V, bool VEC>
-__global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_constant__ StepArgs<T, E> g) {
+__device__ __forceinline__ void mbt_step_body(const StepArgs<T, E> &g) {
     /* staging for non-power-of-two observation rows: one 32 x MBT_MAX_OBS_DIM tile per warp (unused when D == 4) */
-    constexpr bool FIXED_W = V::D && V::norm >= 0;          /* emitted row width known at compile time */
-    constexpr int SW = FIXED_W ? V::D : MBT_MAX_OBS_DIM;     /* staged row width */
-    __shared__ E smem[(FIXED_W && V::D == 4) ? 1 : (MBT_BLOCK / 32) * 32 * SW];
+    constexpr bool FIXED_W = V::Dout > 0;                    /* emitted row width known at compile time */
+    constexpr int SW = FIXED_W ? V::Dout : MBT_MAX_OBS_DIM;  /* staged row width */
+    constexpr bool NO_STAGE = FIXED_W && (V::Dout == 4 || V::Dout == 2 || V::Dout == 1); /* one aligned vector per row */
+    __shared__ E smem[NO_STAGE ? 1 : (MBT_BLOCK / 32) * 32 * SW];
     const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
     const long long warp_row0 = i - (long long)(threadIdx.x & 31u);
-    const bool full_warp = !(FIXED_W && V::D == 4) && (warp_row0 + 32 <= g.n); /* warp-uniform */
-    E *warp_smem = (FIXED_W && V::D == 4) ? smem : smem + (threadIdx.x >> 5) * 32 * SW;
+    const bool full_warp = !NO_STAGE && (warp_row0 + 32 <= g.n); /* warp-uniform */
+    E *warp_smem = NO_STAGE ? smem : smem + (threadIdx.x >> 5) * 32 * SW;
     pdl_launch_dependents();
-    if (i < g.n) step_row<T, E, V, VEC>(g, i, full_warp, warp_smem);
-    else pdl_wait();
+    step_row<T, E, V, VEC>(g, i, full_warp, warp_smem);
+}
+
+/* ahead-of-time instantiations (mbt_variants.h); the run-time specialiser wraps mbt_step_body in extern "C" kernels */
+template <typename T, typename E, class V, bool VEC>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_constant__ StepArgs<T, E> g) {
+    mbt_step_body<T, E, V, VEC>(g);
 }
 
 /* ------------------------------------------------------------------ batch reduction in front of the step */
@@ -338,30 +387,19 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_consta
  * over the trajectory axis, so a step's fill probability depends on the deepest quote of the whole batch.  This kernel
  * is that reduction: NaN-propagating max of the (de-normalised) depth columns, eight independent row loads in flight per
  * thread, warp shuffle -> shared -> ONE 64-bit atomicMax per block and side on an order-preserving integer key of the
- * value (NaN = the largest key, like np.max), and the LAST block to finish (ticket counter) decodes the two maxima and
- * writes the thresholds the step kernel compares its fill uniforms with.  max is order-independent, so the result is
- * deterministic and equal to numpy's.  One launch; the step kernel that follows is ordered after it by the stream.
+ * value (NaN = the largest key, like np.max).  max is order-independent, so the result is deterministic and equal to
+ * numpy's.  The maxima stay in `cells` as keys: the step kernel that follows decodes them (one thread per block) and its
+ * last block clears them; a group of handles all-reduces (max) the cells over NCCL in between.  Both kernels are launched
+ * programmatically dependent: this one starts while the previous step drains and waits before it reads the actions; the
+ * step's Philox prologue overlaps this kernel's tail.
  */
 template <typename T, typename E>
 struct FillBatchArgs {
     StepParams<T> p;
     const E *actions; /* (N, A) */
     long long n;
-    unsigned long long *cells; /* [2] running maxima as keys; zero on entry, zero again on exit */
-    unsigned int *ticket;      /* zero on entry, zero again on exit */
-    T *thr;                    /* out: p_bid * 2^24, p_ask * 2^24 */
+    unsigned long long *cells; /* [2] running maxima as keys; zero on entry (cleared by the step kernel) */
 };
-
-/* order-preserving key of a real (float widens exactly): key(a) < key(b) <=> a < b; every NaN -> the largest key */
-__device__ __forceinline__ unsigned long long real_to_key(double x) {
-    if (x != x) return ~0ull;
-    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double key_to_real(unsigned long long k) {
-    if (k == ~0ull) return __longlong_as_double(0x7ff8000000000000ll); /* NaN */
-    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
-}
 
 template <typename T>
 __device__ __forceinline__ T warp_nanmax(T v) {
@@ -388,9 +426,7 @@ __device__ __forceinline__ void load_depths(const E *__restrict__ actions, long 
     }
 }
 
-/* FINAL: the last block turns the maxima into thresholds (one handle = the whole batch).  !FINAL: the maxima stay in
- * `cells` as keys -- a group of handles all-reduces (max) them over NCCL first, then mbt_fill_finalize_kernel runs. */
-template <typename T, typename E, bool VEC, bool FINAL>
+template <typename T, typename E, bool VEC>
 __global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_constant__ FillBatchArgs<T, E> g) {
     const StepParams<T> &p = g.p;
     const int A = p.action_dim;
@@ -398,6 +434,8 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_
     T m0 = neg_inf, m1 = neg_inf;
     constexpr int UNROLL = 8; /* independent row loads in flight per thread: few blocks (few atomics), deep loads */
     const long long nth = (long long)gridDim.x * MBT_BLOCK;
+    pdl_launch_dependents();
+    pdl_wait(); /* the actions (caller's policy / H2D copy) and the cleared cells (previous step kernel) are visible */
     for (long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x; i < g.n; i += UNROLL * nth) {
         E d0[UNROLL], d1[UNROLL];
 #pragma unroll
@@ -419,36 +457,10 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_
     m1 = warp_nanmax<T>(m1);
     if (lane == 0) { sm[warp][0] = m0; sm[warp][1] = m1; }
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    T b0 = sm[0][0], b1 = sm[0][1];
-    for (int w = 1; w < MBT_BLOCK / 32; ++w) { b0 = nanmax<T>(b0, sm[w][0]); b1 = nanmax<T>(b1, sm[w][1]); }
-    atomicMax(g.cells + 0, real_to_key((double)b0));
-    atomicMax(g.cells + 1, real_to_key((double)b1));
-    if (!FINAL) return;
-    __threadfence(); /* this block's maxima are visible before its ticket is taken */
-    if (atomicAdd(g.ticket, 1u) != gridDim.x - 1) return;
-    /* last block: every other block's atomicMax happened before its ticket; read and clear for the next step */
-    __threadfence();
-    const T a0 = (T)key_to_real(atomicExch(g.cells + 0, 0ull));
-    const T a1 = (T)key_to_real(atomicExch(g.cells + 1, 0ull));
-    T thr[2];
-    fill_batch_thresholds<T>(p, a0, a1, thr);
-    g.thr[0] = thr[0];
-    g.thr[1] = thr[1];
-    *g.ticket = 0u;
-}
-
-/* group of handles: thresholds from the all-reduced maxima (one thread); clears the cells for the next step */
-template <typename T>
-__global__ void mbt_fill_finalize_kernel(StepParams<T> p, unsigned long long *cells, T *thr_out) {
-    const T a0 = (T)key_to_real(cells[0]);
-    const T a1 = (T)key_to_real(cells[1]);
-    cells[0] = 0ull;
-    cells[1] = 0ull;
-    T thr[2];
-    fill_batch_thresholds<T>(p, a0, a1, thr);
-    thr_out[0] = thr[0];
-    thr_out[1] = thr[1];
+    if (threadIdx.x >= 2) return;
+    T b = sm[0][threadIdx.x]; /* thread 0: bid side, thread 1: ask side */
+    for (int w = 1; w < MBT_BLOCK / 32; ++w) b = nanmax<T>(b, sm[w][threadIdx.x]);
+    atomicMax(g.cells + threadIdx.x, real_to_key((double)b));
 }
 
 /* ------------------------------------------------------------------ reset */
@@ -634,7 +646,7 @@ __device__ __forceinline__ void policy_action(const RolloutArgs<T> &g, int A, in
 /* REC: compile the trajectory-recording stores in (mbt_rollout_record) or out (mbt_rollout, the fast path);
  * POL: policy kind fixed at compile time (fast path) or -1 = runtime */
 template <typename T, class V, bool REC, int POL>
-__global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_constant__ RolloutArgs<T> g) {
+__device__ __forceinline__ void mbt_rollout_body(const RolloutArgs<T> &g) {
     const long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
     const bool live = i < g.n;
     const StepParams<T> &p = g.p;
@@ -670,7 +682,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
             /* batch-reduced fill models: only policies whose action is uniform over the batch reach here (do_rollout),
              * so the deepest quote of the batch is this trajectory's own */
             T fill_thr[2] = {(T)0, (T)0};
-            if (V::dyn < 0 && fill_is_batch(p.fill)) fill_batch_thresholds<T>(p, a[0], a[1], fill_thr);
+            if (fill_is_batch(pick<V::fill>(p.fill))) fill_batch_thresholds<T>(p, a[0], a[1], fill_thr);
             const uint32_t nbits2 = second_normal_bits<T, V>(p, g.keys, g.traj_offset + (unsigned long long)i, n_step0 + (unsigned long long)k);
             int clipped = 0;
             const T rwd = step_one<T, V>(p, ck, s, a, r, q_init, &clipped, fill_thr, nbits2);
@@ -739,6 +751,11 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_con
         g.summary[threadIdx.x] = v;
     }
     if (threadIdx.x == 0) *g.ticket = 0u;
+}
+
+template <typename T, class V, bool REC, int POL>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_rollout_kernel(const __grid_constant__ RolloutArgs<T> g) {
+    mbt_rollout_body<T, V, REC, POL>(g);
 }
 
 #endif /* MBT_KERNELS_CUH */

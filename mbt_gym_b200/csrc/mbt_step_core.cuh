@@ -19,22 +19,45 @@
 #ifndef MBT_STEP_CORE_CUH
 #define MBT_STEP_CORE_CUH
 
-#include "../../include/mbt_b200.h"
-#include "../../include/mbt_math.h"
-#include "../../include/mbt_philox.h"
+#include "mbt_b200.h" /* include/ is on the include path (nvcc -I; NVRTC: in-memory headers by these names) */
+#include "mbt_math.h"
+#include "mbt_philox.h"
 
-/* NORM: 0 = no action/observation/reward normalisation compiled in; 1 = action AND observation normalisation compiled in
- * (the reference's default constructor, what SB3 sees), no reward scaling, all columns emitted; -1 = runtime flags. */
-template <int DYN, int MID, int ARR, int IMP, int REW, int NORM>
-struct Variant {
-    static constexpr int dyn = DYN, mid = MID, arr = ARR, imp = IMP, rew = REW, norm = NORM;
-    /* action / observation widths when the model kinds are fixed (0 = runtime) */
+/*
+ * Compile-time description of a configuration: every member is the MBT_* enum / flag value, or -1 = "read it from the
+ * runtime StepParams".  VariantFull fixes any subset; the ahead-of-time table (mbt_variants.h) uses the short form
+ * Variant<DYN, MID, ARR, IMP, REW, NORM>, and the run-time specialiser (mbt_jit.h, NVRTC) instantiates VariantFull with
+ * EVERYTHING fixed for the handle's configuration -- no model switch is left in the kernel.
+ *   na / no / nr   normalise action / observation / rewards compiled in (1), out (0), runtime (-1)
+ *   sel            observation column mask of the fused ReduceStateSizeWrapper (0 = all columns), or -1 = runtime
+ */
+MBT_HD constexpr int mbt_popcount8(int m) {
+    return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1) + ((m >> 4) & 1) + ((m >> 5) & 1) + ((m >> 6) & 1) + ((m >> 7) & 1);
+}
+
+template <int DYN, int MID, int ARR, int IMP, int REW, int FILL, int NA, int NO, int NR, int SEL>
+struct VariantFull {
+    static constexpr int dyn = DYN, mid = MID, arr = ARR, imp = IMP, rew = REW, fill = FILL, na = NA, no = NO, nr = NR, sel = SEL;
+    /* action width when the dynamics are fixed (0 = runtime) */
     static constexpr int A = DYN < 0 ? 0 : (DYN == MBT_DYN_SPEED ? 1 : (DYN == MBT_DYN_LIMIT_AND_MARKET ? 4 : 2));
-    /* (the specialised variants are only selected for the exponential fill function, which owns no state column) */
-    static constexpr int D = (DYN < 0 || ARR < 0 || IMP < 0) ? 0
-                                                             : 4 + (MID == MBT_MID_HESTON ? 1 : 0) + (ARR == MBT_ARR_HAWKES ? 2 : 0) +
-                                                                   ((IMP == MBT_IMP_TEMP_PERM || IMP == MBT_IMP_TEMP_TRANSIENT || IMP == MBT_IMP_TRANSIENT) ? 1 : 0);
+    /* state-matrix width D when every model that owns columns is fixed (0 = runtime): [cash, inventory, time, price],
+     * Heston's variance, Hawkes' two intensities, the exogenous-MM fill model's two depths, one impact column */
+    static constexpr bool limit_fills = DYN == MBT_DYN_LIMIT || DYN == MBT_DYN_LIMIT_AND_MARKET;
+    static constexpr int D = (DYN < 0 || MID < 0 || ARR < 0 || IMP < 0 || FILL < 0) ? 0
+                             : 4 + (MID == MBT_MID_HESTON ? 1 : 0) + (ARR == MBT_ARR_HAWKES ? 2 : 0) +
+                                   ((limit_fills && FILL == MBT_FILL_EXOGENOUS_MM) ? 2 : 0) +
+                                   ((IMP == MBT_IMP_TEMP_PERM || IMP == MBT_IMP_TEMP_TRANSIENT || IMP == MBT_IMP_TRANSIENT) ? 1 : 0);
+    /* emitted observation width (0 = runtime) */
+    static constexpr int Dout = (D == 0 || SEL < 0) ? 0 : (SEL == 0 ? D : mbt_popcount8(SEL));
 };
+
+/* short form of the ahead-of-time table.  NORM: 0 = no action/observation/reward normalisation and no column selection
+ * compiled in; 1 = action AND observation normalisation compiled in (the reference's default constructor, what SB3
+ * sees), no reward scaling, all columns; -1 = runtime flags.  Fixed dynamics imply the exponential fill function (the
+ * table only routes that one to the specialised variants, mbt_variants.h). */
+template <int DYN, int MID, int ARR, int IMP, int REW, int NORM>
+using Variant = VariantFull<DYN, MID, ARR, IMP, REW, (DYN >= 0 ? MBT_FILL_EXPONENTIAL : -1), (NORM < 0 ? -1 : NORM), (NORM < 0 ? -1 : NORM),
+                            (NORM < 0 ? -1 : 0), (NORM < 0 ? -1 : 0)>;
 using VariantGeneric = Variant<-1, -1, -1, -1, -1, -1>;
 
 /* math dispatch on the arithmetic type */
@@ -196,8 +219,7 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
                   const T *fill_thr = nullptr, uint32_t nbits2 = 0u) {
     const int dyn = pick<V::dyn>(p.dyn), mid = pick<V::mid>(p.mid), arr_kind = pick<V::arr>(p.arr),
               imp = pick<V::imp>(p.imp);
-    /* the specialised variants are only selected for the exponential fill function (variant_of) */
-    const int fill = V::dyn >= 0 ? MBT_FILL_EXPONENTIAL : p.fill;
+    const int fill = pick<V::fill>(p.fill);
     const T c0 = s.cash, q_cur = s.inv, S = s.mid; /* current_state = state.copy()   TradingEnvironment.py:105 */
     T arr_b = 0, arr_a = 0;
     T own_b = 0, own_a = 0; /* the agent's own executed fills (fill * arrival), for the jump midprice models */
@@ -310,23 +332,18 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
 
     /* rewards = reward_function.calculate(current_state, action, next_state, dones[0])   :108 */
     T rwd = reward_one<T, V>(p, ck, c0, q_cur, S, s, a, q_init);
-    if (V::norm >= 0) return rwd;
-    return p.normalise_rewards ? p.reward_scaling * rwd : rwd; /* :128-129 */
+    return pick<V::nr>(p.normalise_rewards) ? p.reward_scaling * rwd : rwd; /* :128-129 */
 }
 
 /* normalise_action(inverse=True)                                       TradingEnvironment.py:120-126 */
 template <typename T, class V>
 MBT_HD T denorm_action(const StepParams<T> &p, T x, int j) {
-    if (V::norm == 0) return x;
-    if (V::norm == 1) return (x + (T)1) * p.act_grad[j] + p.act_low[j];
-    return p.normalise_action ? (x + (T)1) * p.act_grad[j] + p.act_low[j] : x;
+    return pick<V::na>(p.normalise_action) ? (x + (T)1) * p.act_grad[j] + p.act_low[j] : x;
 }
 /* normalise_observation                                                 TradingEnvironment.py:112-118 */
 template <typename T, class V>
 MBT_HD T norm_obs(const StepParams<T> &p, T x, int d) {
-    if (V::norm == 0) return x;
-    if (V::norm == 1) return (x - p.obs_low[d]) / p.obs_grad[d] - (T)1;
-    return p.normalise_obs ? (x - p.obs_low[d]) / p.obs_grad[d] - (T)1 : x;
+    return pick<V::no>(p.normalise_obs) ? (x - p.obs_low[d]) / p.obs_grad[d] - (T)1 : x;
 }
 
 #endif /* MBT_STEP_CORE_CUH */

@@ -8,6 +8,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# GPU tests must run the kernels they claim to run: a failure of the run-time specialiser (NVRTC missing, compile error) is
+# an error of mbt_create here instead of a silent switch to the generic ahead-of-time kernel (include/mbt_b200.h, MBT_JIT)
+os.environ.setdefault("MBT_JIT", "require")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")

@@ -102,8 +102,8 @@ def test_two_rank_group_equals_one_handle(n_total):
         assert got["count"] == n_total and got["steps"] == want["steps"] and got["clipped"] == want["clipped"]
         for f in ("sum_return", "sum_return_sq", "sum_q", "sum_q_sq", "sum_action", "sum_reward_sq"):
             np.testing.assert_allclose(got[f], want[f], rtol=1e-12, err_msg=f)  # summation order differs across shards
-            np.testing.assert_allclose(res[r]["summary_torch"][f], want[f], rtol=1e-12, err_msg=f)
-            np.testing.assert_allclose(res[r]["summary_lib_again"][f], want[f], rtol=1e-12, err_msg=f)
+            # (a second episode, other draws:) the library's all-reduce against torch.distributed's on the same local summary
+            np.testing.assert_allclose(res[r]["summary_lib_again"][f], res[r]["summary_torch"][f], rtol=1e-14, err_msg=f)
         assert np.array_equal(res[r]["returns"], ret), "gathered returns: global-id order, bit-identical to one handle"
     spec = dict(SPECS["power_fill"], N=n_total, n_steps=6, normalise_action=False, normalise_obs=False)
     fenv = build_facade_env(spec)

@@ -10,7 +10,7 @@ import pytest
 
 from mbt_gym_b200 import _abi, _lib
 from oracle import oracle as O
-from tests.helpers import Golden, assert_same, build_facade_env, golden_specs
+from tests.helpers import Golden, ROOT, assert_same, build_facade_env, golden_names, golden_specs
 
 pytestmark = pytest.mark.gpu
 SPECS = golden_specs()
@@ -363,3 +363,58 @@ def test_midprice_increments_have_normal_tails_at_full_size():
     p4 = 2 * stats.norm.sf(4.0)
     assert abs(beyond4 - n * p4) < 5 * np.sqrt(n * p4), (beyond4, n * p4)
     assert 5.3 < zmax <= 6.31, zmax  # P(max |z| < 5.3) = exp(-24); the contract's cut-off is 6.3
+
+
+# ------------------------------------------------------------------ run-time specialised kernels (mbt_jit.h)
+@pytest.mark.parametrize("name", golden_names())
+def test_every_fixture_configuration_runs_a_kernel_without_model_switches(name):
+    """Either one of the fully specialised ahead-of-time variants, or a kernel compiled at run time for exactly this
+    configuration: no local memory, at most 50 registers (the generic kernel has 64).  The parity tests of this suite run
+    through these kernels (tests/conftest.py sets MBT_JIT=require)."""
+    g = Golden(name)
+    for prec in (_abi.MBT_F64, _abi.MBT_F32):
+        env = _lib.NativeEnv(g.config(prec))
+        info = env.kernel_info()
+        env.close()
+        assert info["jit_mode"] == 2 and info["message"] == ""
+        if info["aot_variant"] in (0, 4, 6, 9):  # generic / runtime-flag variants of the ahead-of-time table
+            assert info["step_is_jit"], info
+            assert info["step_local_bytes"] == 0 and 0 < info["step_registers"] <= 50, info
+        else:
+            assert not info["step_is_jit"]
+
+
+def test_generic_ahead_of_time_kernels_still_match_the_reference_when_the_specialiser_is_off():
+    """MBT_JIT=0 (no NVRTC on the machine): every configuration falls back to the ahead-of-time table -- the generic kernel
+    for most fixtures -- and must still reproduce the reference fixtures bit-for-bit."""
+    import os
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-q", "-x", "-k",
+                          "f64_matches_reference_fixture or f32_matches_oracle_bitwise or fused_rollout_matches"],
+                         cwd=ROOT, env=dict(os.environ, MBT_JIT="0"), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert " passed" in out.stdout
+
+
+def test_reconfigure_switches_the_specialised_kernel():
+    """An in-place edit that changes a model KIND (here the reward function) re-selects the kernel."""
+    g = Golden("gbm_nonlinear")
+    env = _lib.NativeEnv(g.config(_abi.MBT_F64))
+    h0 = env.kernel_info()["jit_hash"]
+    cfg = g.config(_abi.MBT_F64, reward=_abi.MBT_REW_RUNNING_INVENTORY_PENALTY, rew_phi=0.01, rew_alpha=0.1)
+    env.reconfigure(cfg)
+    info = env.kernel_info()
+    assert info["step_is_jit"] and info["jit_hash"] != h0
+    orc = O.OracleEnv(cfg)
+    env.seed(5); orc.seed(5)
+    obs = np.empty((env.N, env.D)); rew = np.empty(env.N)
+    env.reset(obs)
+    assert_same(obs, orc.reset())
+    a = np.full((env.N, 2), 0.4)
+    for _ in range(5):
+        env.step(a, obs, rew)
+        o, r, _d = orc.step(a)
+        assert_same(obs, o); assert_same(rew, r)
+    env.close()

@@ -24,8 +24,8 @@ def hostsim():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
     cpuinfo = open("/proc/cpuinfo").read() if os.path.exists("/proc/cpuinfo") else ""
     march = ["-march=x86-64-v3"] if (" fma" in cpuinfo and " avx2" in cpuinfo) else []
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", *march, "-x", "c++",
-                    SRC, "-o", SO], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", *march, "-I", os.path.join(ROOT, "include"),
+                    "-x", "c++", SRC, "-o", SO], check=True)
     lib = C.CDLL(SO)
     vp = C.c_void_p
     lib.hostsim_variant_of.argtypes = [C.POINTER(_abi.mbt_config)]
