@@ -420,4 +420,44 @@ MBT_HD float mbt_pow_f32(float x, float p) {
     return r;
 }
 
+/* ------------------------------------------------------------------ division by a uniform divisor */
+/*
+ * a / b, correctly rounded, from the correctly rounded reciprocal y = RN(1/b) that the HOST formed once (the divisor is
+ * uniform over the batch: an observation-space half-width, TradingEnvironment.py:112-118).  Markstein's sequence
+ *     q0 = RN(a*y);  r0 = RN(a - b*q0);  q1 = RN(q0 + r0*y)      q1 is a faithful rounding of a/b (error O(u^2) before rounding)
+ *     r1 =    a - b*q1 (exact);          q2 = RN(q1 + r1*y)      = RN(a/b)   [Markstein 1990: y = RN(1/b), q1 faithful]
+ * five multiply-add class operations instead of the ~15-instruction IEEE division sequence with its reciprocal seed and
+ * slow path -- the normalised observation row has one division per column.  Outside the range where no intermediate can
+ * overflow or lose bits to underflow (zeros, subnormal-ish, huge, inf, NaN numerators; y == 0 marks a divisor the host
+ * rejected) the plain division is used, so the result equals `a / b` bit for bit for EVERY input
+ * (tests/test_primitives.py compares 10^8 random and adversarial pairs).
+ */
+MBT_HD double mbt_div_rcp_f64(double a, double b, double y) {
+    const double aa = a < 0.0 ? -a : a;
+    if (!(y != 0.0 && aa >= 3.0549363634996047e-151 /* 2^-500 */ && aa <= 3.2733906078961419e+150 /* 2^500 */)) return a / b;
+    double q = a * y;
+    double r = fma(-b, q, a);
+    q = fma(r, y, q);
+    r = fma(-b, q, a);
+    return fma(r, y, q);
+}
+MBT_HD float mbt_div_rcp_f32(float a, float b, float y) {
+    const float aa = a < 0.0f ? -a : a;
+    if (!(y != 0.0f && aa >= 8.67361737988403547e-19f /* 2^-60 */ && aa <= 1.15292150460684698e+18f /* 2^60 */)) return a / b;
+    float q = a * y;
+    float r = fmaf(-b, q, a);
+    q = fmaf(r, y, q);
+    r = fmaf(-b, q, a);
+    return fmaf(r, y, q);
+}
+/* the reciprocal the host passes along: RN(1/b) when b is in the range the sequence above is proven for, else 0 */
+MBT_HD double mbt_rcp_for_div_f64(double b) {
+    const double ab = b < 0.0 ? -b : b;
+    return (ab >= 3.0549363634996047e-151 && ab <= 3.2733906078961419e+150) ? 1.0 / b : 0.0;
+}
+MBT_HD float mbt_rcp_for_div_f32(float b) {
+    const float ab = b < 0.0f ? -b : b;
+    return (ab >= 8.67361737988403547e-19f && ab <= 1.15292150460684698e+18f) ? 1.0f / b : 0.0f;
+}
+
 #endif /* MBT_MATH_H */

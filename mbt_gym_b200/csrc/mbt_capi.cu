@@ -152,16 +152,29 @@ static inline bool needs_fill_batch(const mbt_config &c) {
 }
 
 /*
- * MBT_L2_PERSIST=1 (opt-in, measured in profiles/r2_session_notes.md): keep the structure-of-arrays state block -- read and
- * rewritten by EVERY step, 25 MB for the BASELINE market at 2^20 trajectories -- resident in the 126 MB L2 with an
- * access-policy window on the handle's stream, while the caller's action / observation / reward buffers stream through.
+ * L2 residency of the state.  The structure-of-arrays state columns are read and rewritten by EVERY step (25 MB for the
+ * BASELINE market at 2^20 float64 trajectories) while the caller's action / observation / reward buffers only stream
+ * through; an access-policy window on the handle's stream marks the columns in use as persisting in the 126 MB L2 and
+ * everything else the kernels touch as streaming.  Measured: 15.9 -> 15.0 us per step (profiles/r2_session_notes.md).
+ * Only when the columns fit comfortably (<= 40 MB and the device's persisting limit); the device-wide set-aside is only
+ * ever raised, never shrunk (several handles may share the device).  MBT_L2_PERSIST=0 turns it off.
  */
 static bool l2_persist_enabled() {
     static const bool on = [] {
         const char *v = getenv("MBT_L2_PERSIST");
-        return v && v[0] == '1';
+        return !(v && v[0] == '0');
     }();
     return on;
+}
+
+/* state columns (of the 7 in the block: cash, inventory, midprice, x0, x1, q0, variance) a step of this config touches */
+static int state_columns_in_use(const mbt_config &c) {
+    int n = 3;
+    if (imp_has_state(c.impact)) n = 4;
+    if (c.arrival == MBT_ARR_HAWKES) n = 5;
+    if ((c.reward == MBT_REW_CJ_MM || c.reward == MBT_REW_CJ_OE) && c.q0_mode != MBT_Q0_CONST) n = 6;
+    if (c.midprice == MBT_MID_HESTON) n = 7;
+    return n;
 }
 
 static void apply_l2_window(mbt_env *e, cudaStream_t stream) {
@@ -170,17 +183,28 @@ static void apply_l2_window(mbt_env *e, cudaStream_t stream) {
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
     const size_t col_bytes = (((size_t)e->N * e->esz) + 255) & ~(size_t)255;
-    size_t bytes = col_bytes * 5; /* cash, inventory, midprice, x0, x1 (contiguous; q0 / variance follow) */
-    bytes = std::min(bytes, (size_t)std::max(0, max_window));
-    if (max_persist <= 0 || bytes == 0) return;
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)max_persist, bytes));
+    const size_t bytes = col_bytes * (size_t)state_columns_in_use(e->cfg);
     cudaStreamAttrValue v;
     memset(&v, 0, sizeof v);
-    v.accessPolicyWindow.base_ptr = e->state_block;
-    v.accessPolicyWindow.num_bytes = bytes;
-    v.accessPolicyWindow.hitRatio = bytes <= (size_t)max_persist ? 1.0f : (float)max_persist / (float)bytes;
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (max_persist > 0 && bytes <= (size_t)max_persist && bytes <= (size_t)max_window && bytes <= ((size_t)40 << 20)) {
+        size_t cur = 0;
+        cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+        if (cur < bytes) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
+        v.accessPolicyWindow.base_ptr = e->state_block;
+        v.accessPolicyWindow.num_bytes = bytes;
+        v.accessPolicyWindow.hitRatio = 1.0f;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } /* else: num_bytes = 0 clears a window this handle may have set before on this stream */
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaGetLastError();
+}
+
+/* a caller's stream the handle leaves (mbt_set_stream, mbt_destroy) must not keep a window over the handle's memory */
+static void clear_l2_window(mbt_env *e, cudaStream_t stream) {
+    if (!l2_persist_enabled() || !stream || stream == e->own_stream) return;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
     cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);
     cudaGetLastError();
 }
@@ -783,6 +807,7 @@ int mbt_destroy(mbt_env *e) {
     if (!e) return MBT_OK;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->stream) clear_l2_window(e, e->stream);
     cudaFree(e->state_block);
     cudaFree(e->d_clipped);
     cudaFree(e->d_counter_base);
@@ -898,6 +923,7 @@ int mbt_set_stream(mbt_env *e, void *cuda_stream) {
     if (next == e->stream) return MBT_OK; /* unchanged: nothing to order */
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream)); /* work queued on the old stream must finish before the new one is used */
+    clear_l2_window(e, e->stream);
     e->stream = next;
     apply_l2_window(e, next);
     return MBT_OK;
@@ -968,6 +994,7 @@ int mbt_reconfigure(mbt_env *e, const mbt_config *cfg) {
     e->cfg = *cfg;
     e->Dout = mbt_obs_out_dim(cfg, e->D);
     CU(cudaSetDevice(e->device));
+    apply_l2_window(e, e->stream);
     return jit_select_step(e);
 }
 

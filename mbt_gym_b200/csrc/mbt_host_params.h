@@ -177,7 +177,11 @@ static inline StepParams<T> mbt_make_params(const mbt_config &c, double t0, int 
     p.phi = (T)c.rew_phi; p.alpha = (T)c.rew_alpha; p.pexp = (T)c.rew_exponent; p.risk_aversion = (T)c.rew_risk_aversion;
     p.reward_scaling = (T)c.reward_scaling;
     for (int i = 0; i < MBT_MAX_ACTION_DIM; ++i) { p.act_low[i] = (T)c.act_low[i]; p.act_grad[i] = (T)c.act_grad[i]; }
-    for (int i = 0; i < MBT_MAX_OBS_DIM; ++i) { p.obs_low[i] = (T)c.obs_low[i]; p.obs_grad[i] = (T)c.obs_grad[i]; }
+    for (int i = 0; i < MBT_MAX_OBS_DIM; ++i) {
+        p.obs_low[i] = (T)c.obs_low[i];
+        p.obs_grad[i] = (T)c.obs_grad[i];
+        p.obs_rcp[i] = c.normalise_obs ? mbt_rcp_for_div_t(p.obs_grad[i]) : (T)0; /* reciprocal of the value the kernel divides by */
+    }
     return p;
 }
 

@@ -296,15 +296,28 @@ __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, b
     const uint32_t nbits2 = second_normal_bits<T, V>(p, g.keys, g.traj_offset + (unsigned long long)i, n_step);
     pdl_wait(); /* everything below reads what the previous kernel (previous step, the batch reduction, or the caller's policy) wrote */
 
+    /* the row's own loads are issued first: they do not depend on the batch thresholds computed below */
+    const int A = action_width<T, V>(p);
+    E a_io[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
+    Traj<T> s;
+    s.cash = s.inv = s.mid = s.x0 = s.x1 = s.var = (T)0;
+    const int rew_kind = pick<V::rew>(p.rew);
+    T q_init = p.q0_uniform;
+    if (live) {
+        load_row<E>(g.actions, i, A, a_io, VEC);
+        load_traj<T, V>(p, g.st, i, s);
+        if ((rew_kind == MBT_REW_CJ_MM || rew_kind == MBT_REW_CJ_OE) && p.q0_per_traj) q_init = g.st.q0[i];
+    }
+
     T fill_thr[2] = {(T)0, (T)0};
     if (fill_is_batch(pick<V::fill>(p.fill))) {
-        /* one thread per block turns the batch maxima into the step's two fill thresholds (2 pow at most) and shares them */
+        /* per block, two threads turn the batch maxima (keys left by mbt_fill_batch_kernel) into the step's two fill
+         * thresholds -- one pow each for the power function, side by side -- and share them */
         __shared__ T s_thr[2];
-        if (threadIdx.x == 0) {
-            T thr[2];
-            fill_batch_thresholds<T>(p, (T)key_to_real(__ldcg(g.fill_cells + 0)), (T)key_to_real(__ldcg(g.fill_cells + 1)), thr);
-            s_thr[0] = thr[0];
-            s_thr[1] = thr[1];
+        if (threadIdx.x < 2) {
+            const T m_own = (T)key_to_real(__ldcg(g.fill_cells + threadIdx.x));
+            const T m_other = (T)key_to_real(__ldcg(g.fill_cells + (threadIdx.x ^ 1u)));
+            s_thr[threadIdx.x] = fill_batch_threshold_side<T>(p, m_own, m_other, (int)threadIdx.x);
         }
         __syncthreads();
         fill_thr[0] = s_thr[0];
@@ -318,19 +331,10 @@ __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, b
     }
     if (!live) return;
 
-    const int A = action_width<T, V>(p);
-    E a_io[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
-    load_row<E>(g.actions, i, A, a_io, VEC);
     T a[MBT_MAX_ACTION_DIM] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < MBT_MAX_ACTION_DIM; ++j)
         if (j < A) a[j] = denorm_action<T, V>(p, (T)a_io[j], j);
-
-    Traj<T> s;
-    load_traj<T, V>(p, g.st, i, s);
-    const int rew_kind = pick<V::rew>(p.rew);
-    T q_init = p.q0_uniform;
-    if ((rew_kind == MBT_REW_CJ_MM || rew_kind == MBT_REW_CJ_OE) && p.q0_per_traj) q_init = g.st.q0[i];
 
     int clipped = 0;
     const T rwd = step_one<T, V>(p, g.ck, s, a, r, q_init, &clipped, fill_thr, nbits2);

@@ -69,6 +69,10 @@ MBT_HD float mbt_exp2k_t(float x, int k) { return mbt_exp2k_f32(x, k); }
 MBT_HD double mbt_exp2k_t(double x, int k) { return mbt_exp2k_f64(x, k); }
 MBT_HD float mbt_sqrt_t(float x) { return sqrtf(x); }
 MBT_HD double mbt_sqrt_t(double x) { return sqrt(x); }
+MBT_HD float mbt_div_rcp_t(float a, float b, float y) { return mbt_div_rcp_f32(a, b, y); }
+MBT_HD double mbt_div_rcp_t(double a, double b, double y) { return mbt_div_rcp_f64(a, b, y); }
+MBT_HD float mbt_rcp_for_div_t(float b) { return mbt_rcp_for_div_f32(b); }
+MBT_HD double mbt_rcp_for_div_t(double b) { return mbt_rcp_for_div_f64(b); }
 MBT_HD void mbt_real_t(uint32_t k, float *u) { *u = mbt_u24_to_real_f32(k); }
 MBT_HD void mbt_real_t(uint32_t k, double *u) { *u = mbt_u24_to_real_f64(k); }
 
@@ -103,6 +107,7 @@ struct StepParams {
     T phi, alpha, pexp, risk_aversion, reward_scaling;
     T act_low[MBT_MAX_ACTION_DIM], act_grad[MBT_MAX_ACTION_DIM];
     T obs_low[MBT_MAX_OBS_DIM], obs_grad[MBT_MAX_OBS_DIM];
+    T obs_rcp[MBT_MAX_OBS_DIM]; /* RN(1 / obs_grad[d]) in T, or 0: see mbt_div_rcp_f64 (include/mbt_math.h) */
 };
 
 /* The uniform clock of ONE step (every trajectory shares it, TradingEnvironment.py:216-220). */
@@ -158,6 +163,17 @@ MBT_HD T nanmax(T a, T b) {
  *   Triangular  np.max(1 - np.max(depths, 0) / max_fill_depth, 0)                 fill_probability_models.py:82
  *   Power       (1 + (fill_multiplier * np.max(depths, 0)) ** fill_exponent) ** -1   (`** -1` is 1/x in numpy)  :113
  */
+/* one side's threshold (the step kernel computes the two sides on two threads): `m` = that side's batch maximum, `m_other`
+ * the other side's (the triangular function reduces over both sides) */
+template <typename T>
+MBT_HD T fill_batch_threshold_side(const StepParams<T> &p, T m, T m_other, int side) {
+    if (p.fill == MBT_FILL_TRIANGULAR) {
+        const T pm = (T)1 - m / p.fill_max_depth, po = (T)1 - m_other / p.fill_max_depth;
+        return (side == 0 ? nanmax<T>(pm, po) : nanmax<T>(po, pm)) * (T)16777216.0; /* argument order of fill_batch_thresholds */
+    }
+    return ((T)1 / ((T)1 + mbt_pow_t(p.fill_mult * m, p.fill_pexp))) * (T)16777216.0;
+}
+
 template <typename T>
 MBT_HD void fill_batch_thresholds(const StepParams<T> &p, T m_bid, T m_ask, T *thr) {
     if (p.fill == MBT_FILL_TRIANGULAR) {
@@ -343,7 +359,8 @@ MBT_HD T denorm_action(const StepParams<T> &p, T x, int j) {
 /* normalise_observation                                                 TradingEnvironment.py:112-118 */
 template <typename T, class V>
 MBT_HD T norm_obs(const StepParams<T> &p, T x, int d) {
-    return pick<V::no>(p.normalise_obs) ? (x - p.obs_low[d]) / p.obs_grad[d] - (T)1 : x;
+    /* (x - low) / grad - 1 with the division done through the host's reciprocal: bit-identical to `/` (mbt_div_rcp_f64) */
+    return pick<V::no>(p.normalise_obs) ? mbt_div_rcp_t(x - p.obs_low[d], p.obs_grad[d], p.obs_rcp[d]) - (T)1 : x;
 }
 
 #endif /* MBT_STEP_CORE_CUH */

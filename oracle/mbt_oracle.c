@@ -186,4 +186,21 @@ void orc_vec_exp_f64(int64_t n, const double *x, double *y) { for (int64_t i = 0
 void orc_vec_log_f64(int64_t n, const double *x, double *y) { for (int64_t i = 0; i < n; ++i) y[i] = mbt_log_f64(x[i]); }
 void orc_vec_normal_f32(int64_t n, const uint32_t *b, float *y) { for (int64_t i = 0; i < n; ++i) y[i] = mbt_normal_from_bits_f32(b[i]); }
 void orc_vec_normal_f64(int64_t n, const uint32_t *b, double *y) { for (int64_t i = 0; i < n; ++i) y[i] = mbt_normal_from_bits_f64(b[i]); }
+/* the kernels' division-through-reciprocal (include/mbt_math.h) next to the plain division, for tests/test_primitives.py */
+int64_t orc_count_div_rcp_mismatch_f64(int64_t n, const double *a, const double *b) {
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        double q = mbt_div_rcp_f64(a[i], b[i], mbt_rcp_for_div_f64(b[i])), w = a[i] / b[i];
+        bad += memcmp(&q, &w, sizeof q) != 0 && !(q != q && w != w);
+    }
+    return bad;
+}
+int64_t orc_count_div_rcp_mismatch_f32(int64_t n, const float *a, const float *b) {
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        float q = mbt_div_rcp_f32(a[i], b[i], mbt_rcp_for_div_f32(b[i])), w = a[i] / b[i];
+        bad += memcmp(&q, &w, sizeof q) != 0 && !(q != q && w != w);
+    }
+    return bad;
+}
 void orc_vec_pow_f64(int64_t n, const double *x, double p, double *y) { for (int64_t i = 0; i < n; ++i) y[i] = mbt_pow_f64(x[i], p); }

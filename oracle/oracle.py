@@ -52,6 +52,10 @@ def lib():
         for name in ("exp_f32", "log_f32", "exp_f64", "log_f64", "normal_f32", "normal_f64"):
             getattr(L, "orc_vec_" + name).argtypes = [i64, vp, vp]
         L.orc_vec_pow_f64.argtypes = [i64, vp, f64, vp]
+        L.orc_count_div_rcp_mismatch_f64.argtypes = [i64, vp, vp]
+        L.orc_count_div_rcp_mismatch_f64.restype = i64
+        L.orc_count_div_rcp_mismatch_f32.argtypes = [i64, vp, vp]
+        L.orc_count_div_rcp_mismatch_f32.restype = i64
         _lib = L
     return _lib
 
@@ -165,6 +169,14 @@ def reward_eval(cfg, cur, act, nxt, is_terminal=False, q0=0.0, episode_length=1.
     lib().orc_reward_eval(C.byref(cfg), cur.shape[0], _ptr(cur), _ptr(act), _ptr(nxt), int(bool(is_terminal)),
                           float(q0), float(episode_length), _ptr(out))
     return out
+
+
+def div_rcp_mismatches(a, b):
+    """How many pairs the kernels' division-through-reciprocal (mbt_div_rcp_*) gets different from a / b (bitwise)."""
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    assert a.dtype == b.dtype and a.shape == b.shape
+    fn = lib().orc_count_div_rcp_mismatch_f64 if a.dtype == np.float64 else lib().orc_count_div_rcp_mismatch_f32
+    return int(fn(a.size, _ptr(a), _ptr(b)))
 
 
 def philox(ctr, key):

@@ -76,3 +76,42 @@ def test_draws_are_uniform_and_independent_across_trajectories_and_steps():
     # float32 uniforms are the same grid points
     u32, _ = O.draws(_abi.MBT_F32, 123, 0, 1000, 0)
     assert np.array_equal(u32.astype(np.float64), u0[:1000])
+
+
+def _hard_division_cases(p, n, rng):
+    """Pairs (a, b) of p-bit significands whose quotient lies within s * 2^-(2p) (relative) of a MIDPOINT between two
+    floating-point numbers -- the inputs on which a division that is not correctly rounded goes wrong.  With Qm odd
+    (p+1 bits, the midpoint scaled by 2^(p+1)) pick B = s * Qm^-1 mod 2^(p+1); then B * Qm = s (mod 2^(p+1)) and
+    A = (B * Qm - s) / 2^(p+1) is an integer with A / B = Qm / 2^(p+1) - s / (B * 2^(p+1))."""
+    mod = 1 << (p + 1)
+    out_a, out_b = [], []
+    while len(out_a) < n:
+        qm = int(rng.integers(1 << p, mod)) | 1
+        s = int(rng.integers(1, 64)) * (1 if rng.random() < 0.5 else -1)
+        b = (s * pow(qm, -1, mod)) % mod
+        if not (1 << (p - 1)) <= b < (1 << p):
+            continue
+        a = (b * qm - s) >> (p + 1)
+        if (a << (p + 1)) != b * qm - s or not (1 << (p - 1)) <= a < (1 << p):
+            continue
+        out_a.append(a); out_b.append(b)
+    return np.array(out_a, dtype=np.float64), np.array(out_b, dtype=np.float64)
+
+
+def test_division_through_the_hosts_reciprocal_equals_ieee_division_bitwise():
+    """mbt_div_rcp_* (include/mbt_math.h): what the kernels use for (obs - low) / grad -- bit-identical to `/` on random
+    pairs over the whole exponent range, on the special values, and on quotients adversarially close to rounding midpoints."""
+    rng = np.random.default_rng(2024)
+    for dt, p, emax in ((np.float64, 53, 600), (np.float32, 24, 70)):
+        n = 20_000_000 if dt == np.float64 else 10_000_000
+        a = (rng.standard_normal(n) * np.exp2(rng.uniform(-emax, emax, n))).astype(dt)
+        b = (rng.standard_normal(n) * np.exp2(rng.uniform(-emax, emax, n))).astype(dt)
+        assert O.div_rcp_mismatches(a, b) == 0
+        # realistic divisors (observation-space half-widths), numerators of any size incl. zeros, infinities, NaN
+        b = rng.choice(np.array([21600.0, 200.0, 0.5, 8.0, 1e4, 3.0, 100.0 / 3, 1e-3], dtype=dt), n)
+        a[: n // 50] = rng.choice(np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-300, 1e300, 5e-324], dtype=dt), n // 50)
+        assert O.div_rcp_mismatches(a, b) == 0
+        ha, hb = _hard_division_cases(p, 60_000, rng)
+        scale = np.exp2(rng.integers(-40, 40, ha.size)).astype(np.float64)
+        assert O.div_rcp_mismatches((ha * scale).astype(dt), hb.astype(dt)) == 0
+        assert O.div_rcp_mismatches((-ha).astype(dt), (hb * scale).astype(dt)) == 0
