@@ -66,6 +66,7 @@ def main():
             policy(obs_t)                                # warm up cuBLAS on the side stream (torch's capture recipe)
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
+    env.prepare_capture()                                # needed if the env was already stepped (harmless on a fresh one)
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph, stream=s), torch.no_grad():
         env.reset_device(out=obs_t)

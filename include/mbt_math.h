@@ -387,6 +387,29 @@ MBT_HD double mbt_u24_to_real_f64(uint32_t k) {
 #endif
 }
 
+/*
+ * The fill decision  unif < exp(x)  (fill_probability_models.py:33,57-58) on the draw contract's 24-bit uniform k * 2^-24,
+ * i.e.  k < exp(x) * 2^24.  The float version is the definition in float arithmetic.  The double version returns exactly
+ * what  (double)k < mbt_exp2k_f64(x, 24)  returns, but decides almost every draw with the FLOAT exponential: for
+ * -16 <= x <= 0 the float estimate pf of exp(x) * 2^24 is within 1.3e-6 (relative) of the double value --
+ *     |(float)x - x| <= 16 * 2^-24 = 9.6e-7 absolute, so exp changes by 9.6e-7 relative;  mbt_exp2k_f32 is accurate to
+ *     2 ulp = 2.4e-7 (tests/test_primitives.py);  the double exponential itself to 4 ulp = 9e-16
+ * -- so k below pf * (1 - 1.6e-5) or above pf * (1 + 1.6e-5) (a 12x margin) is on the same side of the double threshold;
+ * only the ~3e-5 of the draws that land inside the band evaluate the double exponential (saves ~2 x 30 float64
+ * instructions per env-step; the decisions, hence all results, are unchanged -- every float64 fixture still matches).
+ */
+MBT_HD int mbt_u24_below_exp_f32(uint32_t k, float x) { return (float)k < mbt_exp2k_f32(x, 24); }
+MBT_HD int mbt_u24_below_exp_f64(uint32_t k, double x) {
+    if (x <= 0.0 && x >= -16.0) {
+        const float pf = mbt_exp2k_f32((float)x, 24);
+        const float kf = (float)k; /* exact: k < 2^24 */
+        const float band = pf * 1.6e-5f;
+        if (kf < pf - band) return 1;
+        if (kf > pf + band) return 0;
+    }
+    return mbt_u24_to_real_f64(k) < mbt_exp2k_f64(x, 24);
+}
+
 /* x^p for the inventory penalties (reference: RewardFunctions.py:60-67,100-107,133-137,
  * `q ** inventory_exponent`).  numpy evaluates `** 2.0` as a square and `** 1.0` as the
  * identity (fast_scalar_power), so those two cases are exact; any other exponent goes

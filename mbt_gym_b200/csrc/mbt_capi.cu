@@ -721,7 +721,7 @@ static int do_reset_device(mbt_env *e, const mbt_reset_args *args, void *obs) {
         if (rcb) return rcb;
     }
     g.cash0 = (T)c.initial_cash;
-    g.t0 = (T)t0;
+    g.t0_obs = mbt_time_obs<T>(c, t0);
     g.mid0 = (T)c.mid_initial;
     g.lam0[0] = (T)c.arr_rate[0];
     g.lam0[1] = (T)c.arr_rate[1];
@@ -1299,6 +1299,7 @@ static int enqueue_rollout(mbt_env *e, const mbt_policy *pol, void *returns, voi
     for (int k = 0; k < steps; ++k) {
         clocks[k].ck = mbt_make_clock<T>(c, times[k], times[k + 1], e->t0);
         clocks[k].t_cur = (T)times[k];
+        clocks[k].t_cur_obs = mbt_time_obs<T>(c, times[k]);
     }
     const size_t clock_bytes = clocks.size() * sizeof(RolloutClock<T>);
     if (clock_bytes > e->clocks_cap) {

@@ -116,11 +116,21 @@ static inline int mbt_validate_config(const mbt_config *c, std::string &err) {
     return MBT_OK;
 }
 
+/* the time column of an observation: the uniform clock, normalised here with the very expression the kernels apply to the
+ * other columns (norm_obs), in the arithmetic type T */
+template <typename T>
+static inline T mbt_time_obs(const mbt_config &c, double t) {
+    if (!c.normalise_obs) return (T)t;
+    const T low = (T)c.obs_low[2], grad = (T)c.obs_grad[2];
+    return mbt_div_rcp_t((T)t - low, grad, mbt_rcp_for_div_t(grad)) - (T)1;
+}
+
 /* The uniform clock of the step that moves time from t_cur to t_next. */
 template <typename T>
 static inline StepClock<T> mbt_make_clock(const mbt_config &c, double t_cur, double t_next, double t0) {
     StepClock<T> ck;
     ck.t_next = (T)t_next;
+    ck.t_obs = mbt_time_obs<T>(c, t_next);
     ck.dt_r = (T)(t_next - t_cur);
     ck.done = t_next >= c.terminal_time - c.step_size / 2; /* TradingEnvironment.py:218-220 */
     clock_derive<T>(ck, (T)c.rew_phi, (T)c.rew_alpha, (T)(c.rew_terminal_time - t0));

@@ -165,13 +165,14 @@ __device__ __forceinline__ void store_rows_staged(T *__restrict__ base, long lon
 }
 
 /* observation row of one trajectory: [cash, inventory, time, midprice | arrival cols | impact col]
- * (TradingEnvironment.py:131-140,303-318), normalised on the way out (:112-118). */
+ * (TradingEnvironment.py:131-140,303-318), normalised on the way out (:112-118).  `t_obs` is the time column's value as
+ * emitted (the host normalises the uniform clock: StepClock::t_obs, mbt_time_obs). */
 template <typename T, class V>
-__device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T> &s, T t, T *row) {
+__device__ __forceinline__ int make_obs_row(const StepParams<T> &p, const Traj<T> &s, T t_obs, T *row) {
     const int arr = pick<V::arr>(p.arr), imp = pick<V::imp>(p.imp);
     row[0] = norm_obs<T, V>(p, s.cash, 0);
     row[1] = norm_obs<T, V>(p, s.inv, 1);
-    row[2] = norm_obs<T, V>(p, t, 2);
+    row[2] = t_obs;
     row[3] = norm_obs<T, V>(p, s.mid, 3);
     /* model columns at FIXED positions (no `row[d++]` with a runtime d: that would put the row in local memory).  Hawkes
      * intensities and a price-impact column never coexist: Hawkes needs limit-order dynamics, impact models need speed
@@ -342,7 +343,7 @@ __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, b
     store_traj<T, V>(p, g.st, i, s);
     if (g.obs) {
         T row[MBT_MAX_OBS_DIM];
-        make_obs_row<T, V>(p, s, g.ck.t_next, row);
+        make_obs_row<T, V>(p, s, g.ck.t_obs, row);
         const int D = obs_width<T, V>(p);
         E row_io[MBT_MAX_OBS_DIM];
 #pragma unroll
@@ -476,7 +477,7 @@ struct ResetArgs {
     long long n;
     unsigned long long seed, traj_offset, n_episode;
     const unsigned long long *counter_base; /* see StepArgs */
-    T cash0, t0, mid0, lam0[2], imp0, var0;
+    T cash0, t0_obs /* start time as the observation shows it */, mid0, lam0[2], imp0, var0;
     int q0_mode;
     T q0_const;
     long long q0_lo;
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_reset_kernel(const __grid_const
     if (g.q0_mode == MBT_Q0_UNIFORM_INT) g.st.q0[i] = s.inv; /* reward_function.reset  RewardFunctions.py:72,111 */
     if (g.obs) {
         T row[MBT_MAX_OBS_DIM];
-        const int d = make_obs_row<T, VariantGeneric>(p, s, g.t0, row);
+        const int d = make_obs_row<T, VariantGeneric>(p, s, g.t0_obs, row);
         E row_io[MBT_MAX_OBS_DIM];
 #pragma unroll
         for (int k = 0; k < MBT_MAX_OBS_DIM; ++k)
@@ -584,7 +585,8 @@ constexpr int MBT_SUMMARY_DOUBLES = 7; /* sum R, sum R^2, sum q, sum q^2, sum ac
 template <typename T>
 struct RolloutClock {
     StepClock<T> ck;
-    T t_cur; /* time column BEFORE the step: what the policy sees in its observation */
+    T t_cur;     /* time column BEFORE the step: what the policy sees in its observation */
+    T t_cur_obs; /* ... as a recorded observation shows it (normalised when normalise_obs) */
 };
 
 template <typename T>
@@ -668,7 +670,7 @@ __device__ __forceinline__ void mbt_rollout_body(const RolloutArgs<T> &g) {
         const unsigned long long n_step0 = g.n_step0 + (g.counter_base ? g.counter_base[0] : 0ull);
         if (REC && g.rec_obs) {
             T row[MBT_MAX_OBS_DIM];
-            make_obs_row<T, V>(p, s, g.clocks[0].t_cur, row);
+            make_obs_row<T, V>(p, s, g.clocks[0].t_cur_obs, row);
             store_row<T>(g.rec_obs, i, D, row, false);
         }
         for (int k = 0; k < g.steps; ++k) {
@@ -696,7 +698,7 @@ __device__ __forceinline__ void mbt_rollout_body(const RolloutArgs<T> &g) {
             if (REC && g.rec_rew) g.rec_rew[(long long)k * g.n + i] = rwd;
             if (REC && g.rec_obs) {
                 T row[MBT_MAX_OBS_DIM];
-                make_obs_row<T, V>(p, s, ck.t_next, row);
+                make_obs_row<T, V>(p, s, ck.t_obs, row);
                 store_row<T>(g.rec_obs, (long long)(k + 1) * g.n + i, D, row, false);
             }
         }

@@ -69,6 +69,8 @@ MBT_HD float mbt_exp2k_t(float x, int k) { return mbt_exp2k_f32(x, k); }
 MBT_HD double mbt_exp2k_t(double x, int k) { return mbt_exp2k_f64(x, k); }
 MBT_HD float mbt_sqrt_t(float x) { return sqrtf(x); }
 MBT_HD double mbt_sqrt_t(double x) { return sqrt(x); }
+MBT_HD int mbt_u24_below_exp_t(uint32_t k, float x) { return mbt_u24_below_exp_f32(k, x); }
+MBT_HD int mbt_u24_below_exp_t(uint32_t k, double x) { return mbt_u24_below_exp_f64(k, x); }
 MBT_HD float mbt_div_rcp_t(float a, float b, float y) { return mbt_div_rcp_f32(a, b, y); }
 MBT_HD double mbt_div_rcp_t(double a, double b, double y) { return mbt_div_rcp_f64(a, b, y); }
 MBT_HD float mbt_rcp_for_div_t(float b) { return mbt_rcp_for_div_f32(b); }
@@ -114,6 +116,8 @@ struct StepParams {
 template <typename T>
 struct StepClock {
     T t_next; /* time column after the step                           TradingEnvironment.py:216 */
+    T t_obs;  /* t_next as the observation shows it: normalised on the host when normalise_obs (:112-118) -- the clock is
+               * uniform, so one host evaluation of the same IEEE expression replaces one division per trajectory */
     T dt_r;   /* next[TIME] - current[TIME] as the rewards read it    RewardFunctions.py:58,99,131 */
     int done; /* this step is the terminal one                        TradingEnvironment.py:218-220 */
     /* products / quotient of UNIFORM quantities that the reward formulas contain: formed once per step (on the host for
@@ -262,18 +266,22 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
             off_b = p.half_spread;
             off_a = p.half_spread;
         } else { /* unif < exp(-kappa*depth)   fill_probability_models.py:28-34,57-58 */
-            T vb, va;
-            mbt_real_t(mbt_uniform_bits24(r.z), &vb);
-            mbt_real_t(mbt_uniform_bits24(r.w), &va);
+            const uint32_t kvb = mbt_uniform_bits24(r.z), kva = mbt_uniform_bits24(r.w);
             if (fill_is_batch(fill)) { /* unif < p, p one value per side for the whole batch   :82,113 */
+                T vb, va;
+                mbt_real_t(kvb, &vb);
+                mbt_real_t(kva, &va);
                 fil_b = (vb < fill_thr[0]) ? (T)1 : (T)0;
                 fil_a = (va < fill_thr[1]) ? (T)1 : (T)0;
             } else if (fill == MBT_FILL_EXOGENOUS_MM) { /* :160-163 */
+                T vb, va;
+                mbt_real_t(kvb, &vb);
+                mbt_real_t(kva, &va);
                 fil_b = (vb < fill_exogenous_threshold<T>(p, a[0], 0)) ? (T)1 : (T)0;
                 fil_a = (va < fill_exogenous_threshold<T>(p, a[1], 1)) ? (T)1 : (T)0;
-            } else {
-                fil_b = (vb < mbt_exp2k_t(p.neg_kappa * a[0], 24)) ? (T)1 : (T)0;
-                fil_a = (va < mbt_exp2k_t(p.neg_kappa * a[1], 24)) ? (T)1 : (T)0;
+            } else { /* k < exp(-kappa * depth) * 2^24 (mbt_u24_below_exp_*: float filter, double decision) */
+                fil_b = mbt_u24_below_exp_t(kvb, p.neg_kappa * a[0]) ? (T)1 : (T)0;
+                fil_a = mbt_u24_below_exp_t(kva, p.neg_kappa * a[1]) ? (T)1 : (T)0;
             }
             off_b = a[0];
             off_a = a[1];

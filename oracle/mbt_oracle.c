@@ -203,4 +203,20 @@ int64_t orc_count_div_rcp_mismatch_f32(int64_t n, const float *a, const float *b
     }
     return bad;
 }
+/* the float-filtered fill decision (mbt_u24_below_exp_f64) next to its definition, and the float estimate's relative error */
+int64_t orc_count_fill_filter_mismatch(int64_t n, const uint32_t *k, const double *x, double *max_rel_err_out) {
+    int64_t bad = 0;
+    double worst = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int want = mbt_u24_to_real_f64(k[i]) < mbt_exp2k_f64(x[i], 24);
+        bad += mbt_u24_below_exp_f64(k[i], x[i]) != want;
+        if (x[i] <= 0.0 && x[i] >= -16.0) {
+            const double exact = exp(x[i]) * 16777216.0, est = (double)mbt_exp2k_f32((float)x[i], 24);
+            const double rel = fabs(est - exact) / exact;
+            if (rel > worst) worst = rel;
+        }
+    }
+    if (max_rel_err_out) *max_rel_err_out = worst;
+    return bad;
+}
 void orc_vec_pow_f64(int64_t n, const double *x, double p, double *y) { for (int64_t i = 0; i < n; ++i) y[i] = mbt_pow_f64(x[i], p); }

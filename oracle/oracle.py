@@ -52,6 +52,8 @@ def lib():
         for name in ("exp_f32", "log_f32", "exp_f64", "log_f64", "normal_f32", "normal_f64"):
             getattr(L, "orc_vec_" + name).argtypes = [i64, vp, vp]
         L.orc_vec_pow_f64.argtypes = [i64, vp, f64, vp]
+        L.orc_count_fill_filter_mismatch.argtypes = [i64, vp, vp, C.POINTER(f64)]
+        L.orc_count_fill_filter_mismatch.restype = i64
         L.orc_count_div_rcp_mismatch_f64.argtypes = [i64, vp, vp]
         L.orc_count_div_rcp_mismatch_f64.restype = i64
         L.orc_count_div_rcp_mismatch_f32.argtypes = [i64, vp, vp]
@@ -177,6 +179,15 @@ def div_rcp_mismatches(a, b):
     assert a.dtype == b.dtype and a.shape == b.shape
     fn = lib().orc_count_div_rcp_mismatch_f64 if a.dtype == np.float64 else lib().orc_count_div_rcp_mismatch_f32
     return int(fn(a.size, _ptr(a), _ptr(b)))
+
+
+def fill_filter_check(k, x):
+    """(mismatches of the float-filtered fill decision against its float64 definition, worst relative error of the float
+    estimate of exp(x) * 2^24 over -16 <= x <= 0)."""
+    k, x = np.ascontiguousarray(k, np.uint32), np.ascontiguousarray(x, np.float64)
+    worst = C.c_double()
+    bad = lib().orc_count_fill_filter_mismatch(k.size, _ptr(k), _ptr(x), C.byref(worst))
+    return int(bad), worst.value
 
 
 def philox(ctr, key):

@@ -115,3 +115,22 @@ def test_division_through_the_hosts_reciprocal_equals_ieee_division_bitwise():
         scale = np.exp2(rng.integers(-40, 40, ha.size)).astype(np.float64)
         assert O.div_rcp_mismatches((ha * scale).astype(dt), hb.astype(dt)) == 0
         assert O.div_rcp_mismatches((-ha).astype(dt), (hb * scale).astype(dt)) == 0
+
+
+def test_float_filtered_fill_decision_equals_its_float64_definition():
+    """mbt_u24_below_exp_f64 decides `k < exp(x) * 2^24` with the float exponential unless k falls inside a band around the
+    float estimate: same decisions as the float64 definition for uniform draws AND for k placed right at the threshold,
+    and the float estimate's error stays an order of magnitude inside the band (1.6e-5)."""
+    rng = np.random.default_rng(77)
+    n = 20_000_000
+    x = rng.uniform(-18.0, 1.0, n)
+    x[: n // 10] = -1.5 * rng.uniform(0.0, 3.2, n // 10)  # the quoting range of the reference's markets
+    k = rng.integers(0, 1 << 24, n, dtype=np.uint32)
+    bad, worst = O.fill_filter_check(k, x)
+    assert bad == 0 and worst < 2.0e-6, (bad, worst)
+    # adversarial: k within a few integers / a few 1e-5 (relative) of the threshold
+    thr = np.exp(np.clip(x, -50, 1)) * 16777216.0
+    near = thr * (1 + rng.choice([0, 1e-7, -1e-7, 1e-6, -1e-6, 1.5e-5, -1.5e-5, 1.7e-5, -1.7e-5, 3e-5, -3e-5], n)) + rng.integers(-2, 3, n)
+    k2 = np.clip(np.rint(near), 0, (1 << 24) - 1).astype(np.uint32)
+    bad, _ = O.fill_filter_check(k2, x)
+    assert bad == 0

@@ -5,7 +5,9 @@
         -o gpurun_out/targets python tools/profile_targets.py [f64|f32]
 
 Order of launches: reset, 2 x step (AS), rollout (fixed action), reset, rollout (Avellaneda-Stoikov policy),
-then the power-fill market: reset, 2 x (fill_batch + step).
+then the power-fill market: reset, 2 x (fill_batch + step); then the reference's default-constructor flags (normalised
+actions + observations, ahead-of-time variant 10): 2 x step; then a market only the run-time specialiser serves
+(GBM midprice, non-linear Poisson arrivals, RunningInventoryPenalty, normalised observations): 2 x step.
 """
 import os
 import sys
@@ -62,6 +64,30 @@ def main():
         env.step(act, obs, rew, mem=_abi.MBT_MEM_DEVICE)
     env.sync()
     print("power-fill steps done; mean reward", float(rew.mean()))
+    env.close()
+
+    norm = dict(normalise_action=1, normalise_obs=1, act_low=[0.0, 0.0, 0, 0], act_grad=[1.535, 1.535, 0, 0],
+                obs_low=[-21600.0, -200.0, 0.0, 92.0, 0, 0, 0, 0], obs_grad=[21600.0, 200.0, 0.5, 8.0, 1, 1, 1, 1])
+    env = _lib.NativeEnv(_abi.new_config(fill=_abi.MBT_FILL_EXPONENTIAL, fill_exponent=1.5, **base, **norm), device=0)
+    env.seed(50)
+    env.reset()
+    for _ in range(2):
+        env.step(act, obs, rew, mem=_abi.MBT_MEM_DEVICE)
+    env.sync()
+    print("normalised AS steps done;", env.kernel_info())
+    env.close()
+
+    jit = dict(base, midprice=_abi.MBT_MID_GBM, arrival=_abi.MBT_ARR_POISSON_NONLINEAR,
+               reward=_abi.MBT_REW_RUNNING_INVENTORY_PENALTY, mid_drift=0.05, mid_vol=0.2)
+    norm_obs_only = dict(norm, normalise_action=0)
+    env = _lib.NativeEnv(_abi.new_config(fill=_abi.MBT_FILL_EXPONENTIAL, fill_exponent=1.5, rew_phi=0.01, rew_alpha=0.001,
+                                         **jit, **norm_obs_only), device=0)
+    env.seed(50)
+    env.reset()
+    for _ in range(2):
+        env.step(act, obs, rew, mem=_abi.MBT_MEM_DEVICE)
+    env.sync()
+    print("run-time specialised GBM market steps done;", env.kernel_info())
     env.close()
 
 
