@@ -234,7 +234,10 @@ MBT_HD T reward_one(const StepParams<T> &p, const StepClock<T> &ck, T c0, T q_cu
  *   nbits2  Heston only: the 32 normal bits of the step's SECOND Philox block (stream MBT_STREAM_STEP2)
  * returns the (scaled) reward; *clipped is set when inventory or cash hit their bounds.
  */
-template <typename T, class V>
+/* FILTER: decide exponential fills through the float filter (mbt_u24_below_exp_f64).  The fused rollout with a FIXED action
+ * turns it off: there the fill probability is loop-invariant and the plain comparison lets the compiler hoist the
+ * exponential out of the time loop altogether (same decisions either way). */
+template <typename T, class V, bool FILTER = true>
 MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, const T *a, mbt_u32x4 r, T q_init, int *clipped,
                   const T *fill_thr = nullptr, uint32_t nbits2 = 0u) {
     const int dyn = pick<V::dyn>(p.dyn), mid = pick<V::mid>(p.mid), arr_kind = pick<V::arr>(p.arr),
@@ -279,9 +282,15 @@ MBT_HD T step_one(const StepParams<T> &p, const StepClock<T> &ck, Traj<T> &s, co
                 mbt_real_t(kva, &va);
                 fil_b = (vb < fill_exogenous_threshold<T>(p, a[0], 0)) ? (T)1 : (T)0;
                 fil_a = (va < fill_exogenous_threshold<T>(p, a[1], 1)) ? (T)1 : (T)0;
-            } else { /* k < exp(-kappa * depth) * 2^24 (mbt_u24_below_exp_*: float filter, double decision) */
+            } else if (FILTER) { /* k < exp(-kappa * depth) * 2^24 (mbt_u24_below_exp_*: float filter, double decision) */
                 fil_b = mbt_u24_below_exp_t(kvb, p.neg_kappa * a[0]) ? (T)1 : (T)0;
                 fil_a = mbt_u24_below_exp_t(kva, p.neg_kappa * a[1]) ? (T)1 : (T)0;
+            } else {
+                T vb, va;
+                mbt_real_t(kvb, &vb);
+                mbt_real_t(kva, &va);
+                fil_b = (vb < mbt_exp2k_t(p.neg_kappa * a[0], 24)) ? (T)1 : (T)0;
+                fil_a = (va < mbt_exp2k_t(p.neg_kappa * a[1], 24)) ? (T)1 : (T)0;
             }
             off_b = a[0];
             off_a = a[1];
