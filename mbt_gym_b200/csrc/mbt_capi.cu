@@ -72,7 +72,7 @@ struct mbt_env {
     cudaEvent_t ev_in[MBT_PIPE_CHUNKS] = {}, ev_k[MBT_PIPE_CHUNKS] = {};
 
     /* batch reduction in front of the step (Triangular / Power fill functions): running maxima (keys), ticket, thresholds */
-    void *d_fill_partial = nullptr, *d_fill_thr = nullptr;
+    void *d_fill_partial = nullptr;
     unsigned int *d_fill_ticket = nullptr;
     int fill_blocks = 1;
 
@@ -499,7 +499,8 @@ static int launch_step_rows(mbt_env *e, const StepParams<T> &p, const StepClock<
     g.traj_offset = (unsigned long long)c.traj_offset + (unsigned long long)r0;
     g.n_step = (unsigned long long)e->n_step;
     g.clipped = e->d_clipped;
-    g.fill_thr = (const T *)e->d_fill_thr;
+    g.fill_cells = (unsigned long long *)e->d_fill_partial;
+    g.fill_ticket = e->d_fill_ticket;
     {
         int rcb = counter_base_for_launch(e, &g.counter_base);
         if (rcb) return rcb;
@@ -531,8 +532,6 @@ static int launch_fill_batch(mbt_env *e, const StepParams<T> &p, const void *act
     g.actions = (const E *)actions;
     g.n = e->N;
     g.cells = (unsigned long long *)e->d_fill_partial;
-    g.ticket = e->d_fill_ticket;
-    g.thr = (T *)e->d_fill_thr;
     const unsigned blocks = std::min<unsigned>(grid_for(e->N), (unsigned)e->fill_blocks);
     /* rows of 2 or 4 elements whose base is aligned to a 2-element vector: one vector load per row */
     const bool vec = (e->A == 2 || e->A == 4) && ((uintptr_t)actions % (2 * sizeof(E))) == 0;
@@ -546,27 +545,18 @@ static int launch_fill_batch(mbt_env *e, const StepParams<T> &p, const void *act
     const bool pdl = allow_pdl && use_pdl();
     cfg.attrs = pdl ? attr : nullptr;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (e->comm) {
-        /* group of handles: np.max(depths, 0) runs over the trajectories of ALL ranks -- shard maxima (keys), NCCL
-         * all-reduce (max) on the handle's stream, thresholds from the global maxima */
-        if (vec)
-            cudaLaunchKernelEx(&cfg, mbt_fill_batch_kernel<T, E, true, false>, g);
-        else
-            cudaLaunchKernelEx(&cfg, mbt_fill_batch_kernel<T, E, false, false>, g);
-        CU(cudaGetLastError());
-        int rc = group_allreduce_max_u64(e, g.cells, 2);
-        if (rc) return rc;
-        mbt_fill_finalize_kernel<T><<<1, 2, 0, e->stream>>>(p, g.cells, g.thr);
-        CU(cudaGetLastError());
-        e->launches += 2;
-        return MBT_OK;
-    }
     if (vec)
-        cudaLaunchKernelEx(&cfg, mbt_fill_batch_kernel<T, E, true, true>, g);
+        cudaLaunchKernelEx(&cfg, mbt_fill_batch_kernel<T, E, true>, g);
     else
-        cudaLaunchKernelEx(&cfg, mbt_fill_batch_kernel<T, E, false, true>, g);
+        cudaLaunchKernelEx(&cfg, mbt_fill_batch_kernel<T, E, false>, g);
     CU(cudaGetLastError());
     e->launches += 1;
+    if (e->comm) {
+        /* group of handles: np.max(depths, 0) runs over the trajectories of ALL ranks -- NCCL all-reduce (max) of the two
+         * keys on the handle's stream, between the reduction and the step */
+        int rc = group_allreduce_max_u64(e, g.cells, 2);
+        if (rc) return rc;
+    }
     return MBT_OK;
 }
 
@@ -823,7 +813,6 @@ int mbt_destroy(mbt_env *e) {
     cudaFree(e->d_counter_base);
     cudaFree(e->d_fill_partial);
     cudaFree(e->d_fill_ticket);
-    cudaFree(e->d_fill_thr);
     cudaFree(e->d_actions);
     cudaFree(e->d_obs);
     cudaFree(e->d_rew);
@@ -914,8 +903,6 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     CUB(cudaMemsetAsync(e->d_fill_partial, 0, 2 * sizeof(unsigned long long), e->stream));
     CUB(cudaMalloc((void **)&e->d_fill_ticket, sizeof(unsigned int)));
     CUB(cudaMemsetAsync(e->d_fill_ticket, 0, sizeof(unsigned int), e->stream));
-    CUB(cudaMalloc(&e->d_fill_thr, 2 * sizeof(double)));
-    CUB(cudaMemsetAsync(e->d_fill_thr, 0, 2 * sizeof(double), e->stream));
     /* episode summary: folded on the device by the rollout kernel, mirrored to pinned host memory on demand */
     CUB(cudaMalloc((void **)&e->d_summary, MBT_SUMMARY_DOUBLES * sizeof(double)));
     CUB(cudaMemsetAsync(e->d_summary, 0, MBT_SUMMARY_DOUBLES * sizeof(double), e->stream));

@@ -51,8 +51,10 @@ struct StepArgs {
     mbt_philox_keys keys; /* the ten Philox round keys of the seed, expanded on the host */
     unsigned long long traj_offset, n_step;
     unsigned long long *clipped;
-    const T *fill_thr; /* batch-reduced fill models: the step's two thresholds, written in front of this launch by
-                        * mbt_fill_batch_kernel's last block (or mbt_fill_finalize_kernel behind a group's all-reduce) */
+    /* batch-reduced fill models: the two running maxima of the quoted depths (order-preserving keys) that
+     * mbt_fill_batch_kernel left in front of this launch, and the ticket by which the last block clears them */
+    unsigned long long *fill_cells;
+    unsigned int *fill_ticket;
     /* CUDA-graph replay (mbt_fold_counters): NULL, or the device-resident base {steps, episodes} that is added to the
      * counters baked into this launch -- a captured episode replays with fresh random numbers every time */
     const unsigned long long *counter_base;
@@ -309,9 +311,24 @@ __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, b
     }
 
     T fill_thr[2] = {(T)0, (T)0};
-    if (fill_is_batch(pick<V::fill>(p.fill))) { /* two uniform scalars, L2-resident broadcast loads */
-        fill_thr[0] = __ldcg(g.fill_thr + 0);
-        fill_thr[1] = __ldcg(g.fill_thr + 1);
+    if (fill_is_batch(pick<V::fill>(p.fill))) {
+        /* per block, two threads turn the batch maxima (keys left by mbt_fill_batch_kernel) into the step's two fill
+         * thresholds -- one pow each for the power function, side by side -- and share them */
+        __shared__ T s_thr[2];
+        if (threadIdx.x < 2) {
+            const T m_own = (T)key_to_real(__ldcg(g.fill_cells + threadIdx.x));
+            const T m_other = (T)key_to_real(__ldcg(g.fill_cells + (threadIdx.x ^ 1u)));
+            s_thr[threadIdx.x] = fill_batch_threshold_side<T>(p, m_own, m_other, (int)threadIdx.x);
+        }
+        __syncthreads();
+        fill_thr[0] = s_thr[0];
+        fill_thr[1] = s_thr[1];
+        /* the last block to get here has seen every other block read the cells: clear them for the next step's reduction */
+        if (threadIdx.x == 0 && atomicAdd(g.fill_ticket, 1u) == gridDim.x - 1) {
+            g.fill_cells[0] = 0ull;
+            g.fill_cells[1] = 0ull;
+            *g.fill_ticket = 0u;
+        }
     }
     if (!live) return;
 
@@ -375,21 +392,22 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_step_kernel(const __grid_consta
  * over the trajectory axis, so a step's fill probability depends on the deepest quote of the whole batch.  This kernel
  * is that reduction: NaN-propagating max of the (de-normalised) depth columns, eight independent row loads in flight per
  * thread, warp shuffle -> shared -> ONE 64-bit atomicMax per block and side on an order-preserving integer key of the
- * value (NaN = the largest key, like np.max); the LAST block to finish (ticket counter) decodes the two maxima, writes the
- * two thresholds the step kernel compares its fill uniforms with, and clears the cells.  max is order-independent, so the
- * result is deterministic and equal to numpy's.  A group of handles stops after the atomics (FINAL = false), all-reduces
- * (max) the cells over NCCL and runs mbt_fill_finalize_kernel.  Reduction and step are launched programmatically
- * dependent: this kernel starts while the previous step drains and waits before it reads the actions; the step's Philox
- * prologue overlaps this kernel's tail.
+ * value (NaN = the largest key, like np.max).  max is order-independent, so the result is deterministic and equal to
+ * numpy's.  The maxima stay in `cells` as keys: the step kernel that follows decodes them (one thread per block) and its
+ * last block clears them; a group of handles all-reduces (max) the cells over NCCL in between.  Both kernels are launched
+ * programmatically dependent: this one starts while the previous step drains and waits before it reads the actions; the
+ * step's Philox prologue overlaps this kernel's tail.
+ * Measured alternatives at N = 2^20, float64, reduction + step per env-step (profiles/r2_session_notes.md): thresholds by
+ * this kernel's last block (ticket + fence, the round-1 design) 34.3 us; a third one-warp kernel between the two 33.0 us;
+ * this design 25.5 us (round 1: 35 us) against 15.3 us for a market without the batch reduction -- every additional
+ * grid-wide dependency costs more than the per-block threshold stage.
  */
 template <typename T, typename E>
 struct FillBatchArgs {
     StepParams<T> p;
     const E *actions; /* (N, A) */
     long long n;
-    unsigned long long *cells; /* [2] running maxima as keys; zero on entry, zero again on exit */
-    unsigned int *ticket;      /* zero on entry, zero again on exit */
-    T *thr;                    /* out: p_bid * 2^24, p_ask * 2^24 */
+    unsigned long long *cells; /* [2] running maxima as keys; zero on entry (cleared by the step kernel) */
 };
 
 template <typename T>
@@ -417,7 +435,7 @@ __device__ __forceinline__ void load_depths(const E *__restrict__ actions, long 
     }
 }
 
-template <typename T, typename E, bool VEC, bool FINAL>
+template <typename T, typename E, bool VEC>
 __global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_constant__ FillBatchArgs<T, E> g) {
     const StepParams<T> &p = g.p;
     const int A = p.action_dim;
@@ -452,29 +470,6 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_
     T b = sm[0][threadIdx.x]; /* thread 0: bid side, thread 1: ask side */
     for (int w = 1; w < MBT_BLOCK / 32; ++w) b = nanmax<T>(b, sm[w][threadIdx.x]);
     atomicMax(g.cells + threadIdx.x, real_to_key((double)b));
-    if (!FINAL) return;
-    __threadfence(); /* this block's maxima are visible before its ticket is taken */
-    __syncwarp(0x3u);
-    unsigned last = 0;
-    if (threadIdx.x == 0) last = atomicAdd(g.ticket, 1u) == gridDim.x - 1;
-    last = __shfl_sync(0x3u, last, 0);
-    if (!last) return;
-    /* last block: every other block's atomicMax happened before its ticket; each of the two threads finishes one side */
-    __threadfence();
-    const T m_own = (T)key_to_real(__ldcg(g.cells + threadIdx.x)), m_other = (T)key_to_real(__ldcg(g.cells + (threadIdx.x ^ 1u)));
-    g.thr[threadIdx.x] = fill_batch_threshold_side<T>(p, m_own, m_other, (int)threadIdx.x);
-    __syncwarp(0x3u);
-    g.cells[threadIdx.x] = 0ull;
-    if (threadIdx.x == 0) *g.ticket = 0u;
-}
-
-/* group of handles: thresholds from the all-reduced maxima (two threads); clears the cells for the next step */
-template <typename T>
-__global__ void mbt_fill_finalize_kernel(StepParams<T> p, unsigned long long *cells, T *thr_out) {
-    const T m_own = (T)key_to_real(cells[threadIdx.x]), m_other = (T)key_to_real(cells[threadIdx.x ^ 1u]);
-    thr_out[threadIdx.x] = fill_batch_threshold_side<T>(p, m_own, m_other, (int)threadIdx.x);
-    __syncwarp(0x3u);
-    cells[threadIdx.x] = 0ull;
 }
 
 /* ------------------------------------------------------------------ reset */
