@@ -642,9 +642,11 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
     bounds[0] = 0;
     if (N >= (1 << 17) && !batch) {
         if (pipe_schedule_geometric()) {
-            const int shifts[5] = {4, 3, 2, 1, 0}; /* cumulative end of chunk i = N >> shift */
-            chunks = 5;
-            for (int i = 0; i < 5; ++i) bounds[i + 1] = i == 4 ? N : ((N >> shifts[i]) + 255) & ~255ll;
+            static const int geo3 = getenv("MBT_PIPE_GEO3") != nullptr;
+            const int shifts5[5] = {4, 3, 2, 1, 0}, shifts3[3] = {3, 1, 0}; /* cumulative end of chunk i = N >> shift */
+            const int *shifts = geo3 ? shifts3 : shifts5;
+            chunks = geo3 ? 3 : 5;
+            for (int i = 0; i < chunks; ++i) bounds[i + 1] = i == chunks - 1 ? N : ((N >> shifts[i]) + 255) & ~255ll;
         } else {
             chunks = pipe_chunks();
             const long long rows = ((N + chunks - 1) / chunks + 255) & ~255ll;
@@ -654,6 +656,13 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
         bounds[1] = N;
     }
     const size_t arow = (size_t)e->A * sizeof(E), orow = (size_t)e->Dout * sizeof(E);
+    /* MBT_PIPE_TRACE=1: timestamps of every chunk's H2D / kernel / D2H completion on stderr (debugging the overlap) */
+    static const bool trace = getenv("MBT_PIPE_TRACE") != nullptr;
+    cudaEvent_t tr[3 * MBT_PIPE_CHUNKS + 1] = {};
+    if (trace) {
+        for (auto &ev : tr) cudaEventCreate(&ev);
+        cudaEventRecord(tr[3 * MBT_PIPE_CHUNKS], e->copy_in);
+    }
     for (int k = 0; k < chunks; ++k) {
         const long long r0 = bounds[k];
         if (r0 >= N) break;
@@ -662,6 +671,7 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
         CU(cudaMemcpyAsync((char *)e->d_actions + r0 * arow, (const char *)act_src + r0 * arow, n * arow,
                            cudaMemcpyHostToDevice, e->copy_in));
         CU(cudaEventRecord(e->ev_in[k], e->copy_in));
+        if (trace) cudaEventRecord(tr[3 * k], e->copy_in);
         CU(cudaStreamWaitEvent(e->stream, e->ev_in[k], 0));
         if (batch) {
             int rcb = launch_fill_batch<T, E>(e, p, e->d_actions, /*allow_pdl=*/false);
@@ -671,13 +681,35 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
                                      /*allow_pdl=*/false); /* ordered by stream events, not by the previous kernel */
         if (rc) return rc;
         CU(cudaEventRecord(e->ev_k[k], e->stream));
+        if (trace) cudaEventRecord(tr[3 * k + 1], e->stream);
         CU(cudaStreamWaitEvent(e->copy_out, e->ev_k[k], 0));
         if (obs_dst)
             CU(cudaMemcpyAsync((char *)obs_dst + r0 * orow, (const char *)e->d_obs + r0 * orow, n * orow,
                                cudaMemcpyDeviceToHost, e->copy_out));
-        if (rew_dst)
+        /* rewards: one copy per call, behind the last chunk (every D2H copy costs ~15 us of engine time on top of its
+         * bytes; the (N,) reward vector is a fifth of the output) -- unless MBT_PIPE_REW_PER_CHUNK=1 */
+        static const bool rew_per_chunk = getenv("MBT_PIPE_REW_PER_CHUNK") != nullptr;
+        const bool last = bounds[k + 1] >= N;
+        if (rew_dst && rew_per_chunk)
             CU(cudaMemcpyAsync((char *)rew_dst + r0 * sizeof(E), (const char *)e->d_rew + r0 * sizeof(E), n * sizeof(E),
                                cudaMemcpyDeviceToHost, e->copy_out));
+        else if (rew_dst && last)
+            CU(cudaMemcpyAsync(rew_dst, e->d_rew, (size_t)N * sizeof(E), cudaMemcpyDeviceToHost, e->copy_out));
+        if (trace) cudaEventRecord(tr[3 * k + 2], e->copy_out);
+    }
+    if (trace) {
+        cudaStreamSynchronize(e->copy_out);
+        cudaStreamSynchronize(e->stream);
+        fprintf(stderr, "[mbt pipe]");
+        for (int k = 0; k < chunks; ++k) {
+            float a = 0, b = 0, c2 = 0;
+            cudaEventElapsedTime(&a, tr[3 * MBT_PIPE_CHUNKS], tr[3 * k]);
+            cudaEventElapsedTime(&b, tr[3 * MBT_PIPE_CHUNKS], tr[3 * k + 1]);
+            cudaEventElapsedTime(&c2, tr[3 * MBT_PIPE_CHUNKS], tr[3 * k + 2]);
+            fprintf(stderr, "  chunk %d (%lld rows): h2d %.0f  kernel %.0f  d2h %.0f us |", k, bounds[k + 1] - bounds[k], 1e3 * a, 1e3 * b, 1e3 * c2);
+        }
+        fprintf(stderr, "\n");
+        for (auto &ev : tr) cudaEventDestroy(ev);
     }
     CU(cudaStreamSynchronize(e->copy_out));
     CU(cudaStreamSynchronize(e->stream));
