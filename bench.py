@@ -396,7 +396,7 @@ def e2e_leg(ctx, facade, workload, steps):
     return dt, checksum
 
 
-def episode_leg(ctx, env, stream, N, A, tdt, workload, mem_device, episodes=4):
+def episode_leg(ctx, env, stream, N, A, tdt, workload, mem_device, episodes=8):
     """Per-episode statistics: fused on-device rollout, summary all-reduced and returns all-gathered over NCCL by the
     library (mbt_group_rollout).  Two returns buffers alternate, so an episode's gather overlaps the next one's rollout."""
     from mbt_gym_b200 import _abi, sharding
@@ -438,22 +438,27 @@ def episode_leg(ctx, env, stream, N, A, tdt, workload, mem_device, episodes=4):
         for _ in range(10):
             merged_struct = env.group_summary(summ_local)
         coll_ms = 1e3 * (time.perf_counter() - t0) / 10
-    # (c) whole episodes back to back: reset + rollout + all-reduce (+ overlapped gather), wall clock per episode
+    # (c) whole episodes back to back: reset + rollout + all-reduce (+ overlapped gather), wall clock per episode (each call
+    # returns when the GLOBAL summary is on the host; the gather of episode i runs behind episode i+1's rollout)
     ctx.barrier()
+    per_ep = []
     t0 = time.perf_counter()
     for i in range(episodes):
+        t1 = time.perf_counter()
         summ = one(i)
+        per_ep.append(time.perf_counter() - t1)
     if world > 1:
         env.group_wait()
     torch.cuda.synchronize()
     ep_ms = 1e3 * (time.perf_counter() - t0) / episodes
+    ep_med_ms = 1e3 * float(np.median(per_ep))
     ctx.barrier()
-    rollout_ms, coll_ms, ep_ms = ctx.max_over_ranks([rollout_ms, coll_ms, ep_ms])
+    rollout_ms, coll_ms, ep_ms, ep_med_ms = ctx.max_over_ranks([rollout_ms, coll_ms, ep_ms, ep_med_ms])
     merged = sharding.summary_struct_to_dict(summ)
     table = sharding.results_table(merged, A)
     gathered = all_ret[(episodes - 1) % 2]
     return {"fused_rollout_ms": rollout_ms, "fused_rollout_env_steps_per_sec": N * world * summ.steps / (rollout_ms * 1e-3),
-            "summary_collective_ms": coll_ms, "episode_ms": ep_ms,
+            "summary_collective_ms": coll_ms, "episode_ms": ep_ms, "episode_ms_median": ep_med_ms, "episodes_timed": episodes,
             "episode_env_steps_per_sec": N * world * summ.steps / (ep_ms * 1e-3),
             "collective": ("library (mbt_group_rollout): ncclAllReduce of the 7-double device summary on the env's stream; "
                            "ncclAllGather of returns on the group's stream, overlapped with the next episode") if world > 1 else "none (1 GPU)",
@@ -662,6 +667,8 @@ def main():
                     "achieved_gbs": world * N * (A + D + 1) * esz / (e2e_ms / e2e_steps * 1e-3) / 1e9,
                     "pcie_peak_gbs": ceiling["gbs"], "pcie_peak_ms_per_step": ceiling["ms_per_step"],
                     "frac": ceiling["ms_per_step"] / (e2e_ms / e2e_steps),
+                    "frac_note": "bare-copy time / e2e step time: the bare copies wait for both directions every step, the library "
+                                 "pipelines chunks, so a value slightly above 1 is possible when the host link is saturated (N > 1)",
                     "pcie_peak_how": f"bare cudaMemcpyAsync of the same bytes (H2D + D2H on two streams, both waited for per step) on "
                                      f"all {world} ranks at once, measured in this run; a k-GPU table is in profiles/r2_pcie_probe_*.json"},
             "gpu_launches": int(launches),
