@@ -649,9 +649,16 @@ def main():
         mean_kernel_ms = elapsed_ms / args.steps
         achieved = N * b_step / (mean_kernel_ms * 1e-3) / 1e9
         T = "double" if args.precision == "f64" else "float"
-        prof, prof_src = ncu_profile_value(("mbt_step_kernel<" + T,), ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"]) \
-            if (args.workload == "as" and N == N_PER_GPU) else (None, None)
+        dram = ["dram__bytes_read.sum", "dram__bytes_write.sum"]
+        prof = prof_src = cold = cold_src = None
+        if args.workload == "as" and N == N_PER_GPU:
+            # steady state first (ncu --cache-control none on the running step loop), the cold single-launch capture second
+            prof, prof_src = ncu_profile_value(("mbt_step_kernel<" + T,), dram, f"profiles/r2_step_steady_{args.precision}.ncu_summary.csv")
+            cold, cold_src = ncu_profile_value(("mbt_step_kernel<" + T, "0, 1, 1, 0, 0, 1, 0, 0, 0, 0>"), dram, f"profiles/r2_targets_{args.precision}.ncu_summary.csv")
+            if prof is None:
+                prof, prof_src = cold, cold_src
         traffic = (prof["dram__bytes_read.sum"] + prof["dram__bytes_write.sum"]) if prof else None
+        traffic_cold = (cold["dram__bytes_read.sum"] + cold["dram__bytes_write.sum"]) if cold else None
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -674,10 +681,13 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": traffic, "traffic_source": prof_src,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture "
-                                         "(one launch under `ncu --set full`, caches flushed by ncu: a COLD launch -- reads = actions + "
-                                         "state columns; part of the written lines is still in L2 when the kernel's window ends, so "
-                                         "writes are under-counted)",
+                         "traffic_cold_launch": traffic_cold, "traffic_cold_source": cold_src,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures, read "
+                                         "at run time.  `traffic`: launches 60+ of the running step loop under `ncu --cache-control none` "
+                                         "(steady state: the state columns are L2-resident through the access-policy window, DRAM moves "
+                                         "actions in and observations / rewards out).  `traffic_cold_launch`: one launch under `ncu --set "
+                                         "full` with ncu's cache flush -- reads = actions + state columns; written lines still in L2 when "
+                                         "the kernel's window ends are not counted",
                          "dram_frac": (traffic / (mean_kernel_ms * 1e-3) / 1e9 / peak_gbs) if traffic else None,
                          "frac_note": "achieved = ALGORITHMIC bytes (SURVEY 8d: 104 B per env-step in f64) / median window time per "
                                       "step.  At N = 2^20 a step is ~5 us of fixed launch/ramp/drain cost plus ~15 ps per trajectory "

@@ -349,7 +349,9 @@ int mbt_fold_counters(mbt_env *env);
 int mbt_get_clip_count(mbt_env *env, int64_t *count);
 
 /* reward_function.calculate(current_state, action, next_state, is_terminal) on (n, D)/(n, A) buffers,
- * using the handle's reward parameters and the q0 / episode length captured at the last reset. */
+ * using the handle's reward parameters and the UNIFORM initial inventory / episode length captured at the last reset.
+ * (Per-trajectory initial inventories -- MBT_Q0_UNIFORM_INT, MBT_Q0_PER_TRAJ -- belong to the handle's own trajectories, not
+ * to caller rows: the Python facade refuses calculate() on explicit matrices when the captured inventories differ.) */
 int mbt_reward_eval(mbt_env *env, int64_t n, const void *current_state, const void *action,
                     const void *next_state, int is_terminal, void *rew_out, int mem);
 

@@ -122,3 +122,80 @@ def test_sb_agent_adapter_duck_types_a_stable_baselines_model():
     np.testing.assert_array_equal(act, np.stack([state[:, 1] + 1, state[:, 2] * 2], axis=1))
     agent.train(123)
     assert model.learned == 123 and agent.num_trajectories == 5
+
+
+def test_terminal_infos_is_a_lazy_but_real_list():
+    """SB3's VecMonitor / collect_rollouts index, slice, copy and assign into `infos`: the episode-end infos must be a list."""
+    import copy
+    import pickle
+
+    from mbt_gym_b200.gym.StableBaselinesTradingEnvironment import _TerminalInfos
+
+    obs = np.arange(12.0).reshape(4, 3)
+    infos = _TerminalInfos(obs, (np.array([1.0, 2, 3, 4]), 5, 0.1))
+    assert isinstance(infos, list) and len(infos) == 4 and bool(infos)
+    assert infos[2]["episode"] == {"r": 3.0, "l": 5, "t": 0.1} and np.array_equal(infos[-1]["terminal_observation"], obs[3])
+    infos[1]["TimeLimit.truncated"] = True      # mutation of a lazily built item sticks
+    infos[3] = {"replaced": 1}                  # item assignment before anything materialised the list
+    new_infos = list(infos[:])                  # what VecMonitor does
+    assert new_infos[1]["TimeLimit.truncated"] is True and new_infos[3] == {"replaced": 1} and len(new_infos) == 4
+    assert [i.get("episode", {}).get("r") for i in infos] == [1.0, 2.0, 3.0, None]
+    infos.append({})
+    assert len(infos) == 5 and infos == new_infos + [{}]
+    again = _TerminalInfos(obs)
+    assert pickle.loads(pickle.dumps(again))[2]["terminal_observation"][1] == 7.0
+    assert isinstance(copy.copy(_TerminalInfos(obs)), list) and len(copy.deepcopy(_TerminalInfos(obs))) == 4
+    with pytest.raises(IndexError):
+        _TerminalInfos(obs)[4]
+
+
+def test_pinned_pool_recycles_only_unreferenced_blocks(monkeypatch):
+    """The output pool's recycling rule, on ordinary memory (no CUDA here): a block is reused only when no array or view of
+    it is alive."""
+    import ctypes as C
+
+    from mbt_gym_b200 import _lib
+
+    class HostBlock(_lib._PinnedBlock):
+        def __init__(self, nbytes, device=0):
+            self.nbytes = max(int(nbytes), 1)
+            self._buf = (C.c_char * self.nbytes)()
+            self._ptr = C.c_void_p(C.addressof(self._buf))
+
+        def __del__(self):
+            pass
+
+    monkeypatch.setattr(_lib, "_PinnedBlock", HostBlock)
+    pool = _lib.PinnedPool(max_bytes=5 * 96)
+    a, b = pool.get((4, 3), np.float64), pool.get((4, 3), np.float64)
+    assert a.ctypes.data != b.ctypes.data and len(pool._blocks) == 2
+    a[:] = 1.0
+    view = a[:, 1]
+    del a
+    c = pool.get((4, 3), np.float64)            # `view` still references the first block: a third one is made
+    assert len(pool._blocks) == 3 and np.all(view == 1.0)
+    c[:] = 2.0
+    assert np.all(view == 1.0)
+    del b, c, view
+    d = pool.get((4, 3), np.float64)
+    assert len(pool._blocks) == 3               # reuse
+    e, f = pool.get((4, 3), np.float64), pool.get((4, 3), np.float64)
+    g = pool.get((4, 3), np.float64), pool.get((4, 3), np.float64)
+    assert len(pool._blocks) == 5 and g[1] is not None
+    assert pool.get((4, 3), np.float64) is None, "beyond max_bytes the pool declines (the caller falls back to np.empty)"
+    del d, e, f, g
+
+
+def test_public_attribute_edits_bump_the_version_private_ones_do_not():
+    from mbt_gym_b200 import _track
+
+    env = build_facade_env(SPECS["as_pnl"])
+    v0 = _track.version[0]
+    env._scratch = 1
+    env.model_dynamics.midprice_model._scratch = 2
+    assert _track.version[0] == v0
+    env.max_inventory = 7
+    env.model_dynamics.midprice_model.volatility = 3.0
+    env.reward_function.anything = 1
+    assert _track.version[0] == v0 + 3
+    assert env._build_config().max_inventory == 7.0 and env._build_config().mid_vol == 3.0
