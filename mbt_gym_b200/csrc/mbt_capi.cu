@@ -114,6 +114,8 @@ struct mbt_env {
     int jit_roll_state[5] = {};              /* 0 untried, 1 ready, -1 failed */
     std::string jit_error;                   /* why the specialiser is not in use (empty = in use or switched off) */
 
+    bool has_l2_window = false; /* MBT_L2_PERSIST=1: this handle raised the persisting-L2 set-aside */
+
     /* statistics */
     int64_t launches = 0;
     int timing = 0; /* 0 off, 1 two events around every kernel, 2 one event before every kernel (interval timing) */
@@ -152,20 +154,25 @@ static inline bool needs_fill_batch(const mbt_config &c) {
 }
 
 /*
- * L2 residency of the state.  The structure-of-arrays state columns are read and rewritten by EVERY step (25 MB for the
- * BASELINE market at 2^20 float64 trajectories) while the caller's action / observation / reward buffers only stream
- * through; an access-policy window on the handle's stream marks the columns in use as persisting in the 126 MB L2 and
- * everything else the kernels touch as streaming.  Measured: 15.9 -> 15.0 us per step (profiles/r2_session_notes.md).
- * Only when the columns fit comfortably (<= 40 MB and the device's persisting limit); the device-wide set-aside is only
- * ever raised, never shrunk (several handles may share the device).  MBT_L2_PERSIST=0 turns it off.
+ * L2 residency of the state (opt-in: MBT_L2_PERSIST=1).  The structure-of-arrays state columns are read and rewritten by
+ * EVERY step (25 MB for the BASELINE market at 2^20 float64 trajectories) while the caller's action / observation / reward
+ * buffers only stream through; an access-policy window on the handle's stream marks the columns in use as persisting in the
+ * 126 MB L2 and everything else the kernels touch as streaming.  Measured at N = 2^20: 14.6 -> 14.3 us per step (15.9 ->
+ * 14.8 before the float-filtered fill decision).  NOT the default: the persisting set-aside is a device-wide setting, and
+ * other work in the process pays for it -- a 2^24-trajectory handle stepped after a windowed 2^20 one ran 6 % slower
+ * (tools/l2_window_probe.py, profiles/r2_session_notes.md).  The set-aside is only ever raised while windowed handles exist
+ * and is given back (with the persisting lines) when the last of them is destroyed; a caller's stream the handle leaves
+ * loses the window.
  */
 static bool l2_persist_enabled() {
     static const bool on = [] {
         const char *v = getenv("MBT_L2_PERSIST");
-        return !(v && v[0] == '0');
+        return v && v[0] == '1';
     }();
     return on;
 }
+static int g_l2_window_handles = 0; /* handles that currently hold a window (per process; handles are created / destroyed
+                                       by their owning threads -- the counter is only a hint for giving the set-aside back) */
 
 /* state columns (of the 7 in the block: cash, inventory, midprice, x0, x1, q0, variance) a step of this config touches */
 static int state_columns_in_use(const mbt_config &c) {
@@ -195,6 +202,10 @@ static void apply_l2_window(mbt_env *e, cudaStream_t stream) {
         v.accessPolicyWindow.hitRatio = 1.0f;
         v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (!e->has_l2_window) {
+            e->has_l2_window = true;
+            g_l2_window_handles += 1;
+        }
     } /* else: num_bytes = 0 clears a window this handle may have set before on this stream */
     cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);
     cudaGetLastError();
@@ -840,6 +851,11 @@ int mbt_destroy(mbt_env *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->stream) clear_l2_window(e, e->stream);
+    if (e->has_l2_window && --g_l2_window_handles <= 0) { /* last windowed handle: give the set-aside back to everybody */
+        g_l2_window_handles = 0;
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    }
     cudaFree(e->state_block);
     cudaFree(e->d_clipped);
     cudaFree(e->d_counter_base);
