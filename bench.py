@@ -615,7 +615,11 @@ def main():
         oe_env.set_stream(None)
         oe.close()
 
-    # ---- n_sweep: fixed launch cost vs per-trajectory cost of the step kernel (1 GPU only)
+    facade.close()
+    del bufs
+    torch.cuda.empty_cache()
+    # ---- n_sweep: fixed launch cost vs per-trajectory cost of the step kernel (1 GPU only); every other handle is closed by
+    # now (a live handle's L2 window / persisting set-aside would cost the larger sizes a few per cent)
     n_sweep = None
     peak_gbs, peak_src, sm_max_mhz = measured_peaks()
     if world == 1 and not args.no_extras:
@@ -709,7 +713,6 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
-    facade.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

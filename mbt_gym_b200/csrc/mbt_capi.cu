@@ -154,20 +154,21 @@ static inline bool needs_fill_batch(const mbt_config &c) {
 }
 
 /*
- * L2 residency of the state (opt-in: MBT_L2_PERSIST=1).  The structure-of-arrays state columns are read and rewritten by
- * EVERY step (25 MB for the BASELINE market at 2^20 float64 trajectories) while the caller's action / observation / reward
- * buffers only stream through; an access-policy window on the handle's stream marks the columns in use as persisting in the
- * 126 MB L2 and everything else the kernels touch as streaming.  Measured at N = 2^20: 14.6 -> 14.3 us per step (15.9 ->
- * 14.8 before the float-filtered fill decision).  NOT the default: the persisting set-aside is a device-wide setting, and
- * other work in the process pays for it -- a 2^24-trajectory handle stepped after a windowed 2^20 one ran 6 % slower
- * (tools/l2_window_probe.py, profiles/r2_session_notes.md).  The set-aside is only ever raised while windowed handles exist
- * and is given back (with the persisting lines) when the last of them is destroyed; a caller's stream the handle leaves
- * loses the window.
+ * L2 residency of the state.  The structure-of-arrays state columns are read and rewritten by EVERY step (25 MB for the
+ * BASELINE market at 2^20 float64 trajectories, 42 MB with Hawkes intensities) while the caller's action / observation /
+ * reward buffers only stream through; an access-policy window on the handle's stream marks the columns in use as
+ * persisting in the 126 MB L2 and everything else the kernels touch as streaming.  Measured per step at N = 2^20, f64
+ * (profiles/r2_session_notes.md): AS 14.7 -> 14.3 us, CjMm 16.6 -> 15.7, OE 18.3 -> 16.3, Hawkes 25.2 -> 19.1.
+ * The persisting set-aside is a device-wide setting, so it is handled like any other resource the handle owns: only when
+ * the columns fit (<= 40 MiB and the device's limits), only ever raised while windowed handles exist, and given back (with
+ * the persisting lines) when the last of them is destroyed -- while it is raised, other L2-hungry work on the device runs
+ * a few per cent slower (a 2^24-trajectory handle next to a live windowed 2^20 one: 6 %, tools/l2_window_probe.py).
+ * A caller's stream the handle leaves loses the window.  MBT_L2_PERSIST=0 turns all of it off.
  */
 static bool l2_persist_enabled() {
     static const bool on = [] {
         const char *v = getenv("MBT_L2_PERSIST");
-        return v && v[0] == '1';
+        return !(v && v[0] == '0');
     }();
     return on;
 }
