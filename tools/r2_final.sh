@@ -1,6 +1,6 @@
 #!/bin/bash
 # final one-GPU session of the round: smoke, GPU tests, bench lines, ncu evidence (reps stay in /tmp: gpurun_out/ <= 64 MiB)
-OUT=gpurun_out/r2y
+OUT=gpurun_out/r2x
 mkdir -p $OUT
 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.txt 2>&1; echo "smoke rc=$?"; tail -1 $OUT/smoke.txt
 timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest_gpu.log
