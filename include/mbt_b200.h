@@ -93,7 +93,8 @@ extern "C" {
  * deepest quote of the whole batch -- one value per side (Power), or one value for both sides (Triangular, whose
  * outer `np.max(..., 0)` reduces the two sides as well).  The step therefore has a batch reduction in front of it
  * (mbt_fill_batch_kernel).  "Batch" = the trajectories of this handle, like one worker of the reference's
- * MultiprocessTradingEnv. */
+ * MultiprocessTradingEnv -- or, once the handle has joined a group (mbt_group_create), the trajectories of ALL ranks: the
+ * shard maxima are all-reduced (max) over NCCL between the reduction and the step. */
 #define MBT_FILL_TRIANGULAR 2 /* TriangularFillFunction  :68-91  p = max_side(1 - max_traj(depth)/max_fill_depth)        */
 #define MBT_FILL_POWER 3      /* PowerFillFunction       :94-123 p_side = 1/(1 + (multiplier*max_traj(depth))^exponent)  */
 /* ExogenousMmFillProbabilityModel :126-170: p = base * exp(-kappa * (depth - d)) beyond the exogenous best depth d of the
