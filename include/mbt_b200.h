@@ -430,6 +430,13 @@ int mbt_get_kernel_info(mbt_env *env, mbt_kernel_info *out);
  * 1 = rollout with `policy_kind` compiled in (or the recording kernel when `record`). */
 int mbt_jit_precompile(const mbt_config *cfg, int32_t kind, int32_t policy_kind, int32_t record);
 
+/* Histogram of the CURRENT inventory column (after a rollout or a step loop: the terminal inventories) over the integer
+ * bins lo .. hi (at most 4096): what the reference's results plot bins on the host (gym/helpers/plotting.py:94-110, the
+ * "inventory distribution" of the parity statistics).  counts_out (HOST, hi - lo + 3 int64): [0] = below lo,
+ * [1 + (q - lo)] = round(q) == q, [hi - lo + 2] = above hi or NaN.  group_sum != 0: the counts of ALL ranks of the handle's
+ * group (NCCL all-reduce on the handle's stream). */
+int mbt_inventory_histogram(mbt_env *env, int64_t lo, int64_t hi, int64_t *counts_out, int group_sum);
+
 /* Per-call statistics for bench.py: number of kernel launches issued by this handle so far, and the
  * device time (ms, CUDA events on the handle's stream) of the most recent step kernel when enabled. */
 int mbt_get_launch_count(mbt_env *env, int64_t *launches);

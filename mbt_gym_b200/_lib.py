@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "mbt_host_alloc", "mbt_host_alloc_near", "mbt_host_free", "mbt_checkpoint_size", "mbt_checkpoint_save",
     "mbt_checkpoint_load", "mbt_fold_counters", "mbt_prepare_capture", "mbt_get_seed", "mbt_set_counters", "mbt_reconfigure",
     "mbt_group_unique_id", "mbt_group_create", "mbt_group_destroy", "mbt_group_info", "mbt_group_rollout", "mbt_group_summary",
-    "mbt_group_wait", "mbt_get_kernel_info", "mbt_jit_precompile",
+    "mbt_group_wait", "mbt_get_kernel_info", "mbt_jit_precompile", "mbt_inventory_histogram",
 ]
 
 _lib = None
@@ -87,6 +87,7 @@ def load():
     L.mbt_group_wait.argtypes = [vp, C.c_int]
     L.mbt_get_kernel_info.argtypes = [vp, C.POINTER(_abi.mbt_kernel_info)]
     L.mbt_jit_precompile.argtypes = [cfgp, C.c_int32, C.c_int32, C.c_int32]
+    L.mbt_inventory_histogram.argtypes = [vp, C.c_int64, C.c_int64, i64p, C.c_int]
     if L.mbt_abi_version() != _abi.MBT_ABI_VERSION:
         raise ImportError(f"libmbt_b200.so ABI {L.mbt_abi_version()} != binding ABI {_abi.MBT_ABI_VERSION}")
     _lib = L
@@ -359,6 +360,12 @@ class NativeEnv:
         out = np.empty((cur.shape[0],), self.dtype)
         _check(load().mbt_reward_eval(self._h, cur.shape[0], _addr(cur), _addr(act), _addr(nxt), int(bool(is_terminal)),
                                       _addr(out), _abi.MBT_MEM_HOST))
+        return out
+
+    def inventory_histogram(self, lo, hi, group_sum=False):
+        """int64 counts of the current inventory column: [below lo, lo, lo+1, ..., hi, above hi or NaN]."""
+        out = np.zeros(int(hi) - int(lo) + 3, np.int64)
+        _check(load().mbt_inventory_histogram(self._h, int(lo), int(hi), out.ctypes.data_as(C.POINTER(C.c_int64)), int(bool(group_sum))))
         return out
 
     # -- checkpoint / resume

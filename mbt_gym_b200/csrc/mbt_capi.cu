@@ -1896,3 +1896,43 @@ int mbt_jit_precompile(const mbt_config *cfg, int32_t kind, int32_t policy_kind,
 }
 
 } /* extern "C" */
+
+extern "C" {
+
+int mbt_inventory_histogram(mbt_env *e, int64_t lo, int64_t hi, int64_t *counts_out, int group_sum) {
+    if (!e || !counts_out) return fail(MBT_E_INVALID_ARG, "NULL argument");
+    if (!(hi >= lo) || hi - lo + 1 > MBT_HIST_MAX_BINS) return fail(MBT_E_INVALID_ARG, "need lo <= hi and at most 4096 bins");
+    if (!e->started) return fail(MBT_E_STATE, "mbt_inventory_histogram called before mbt_reset");
+    if (group_sum && !e->comm) return fail(MBT_E_STATE, "the handle belongs to no group (mbt_group_create)");
+    if (stream_is_capturing(e)) return fail(MBT_E_STATE, "mbt_inventory_histogram is not capturable");
+    CU(cudaSetDevice(e->device));
+    const int bins = (int)(hi - lo + 1);
+    const size_t bytes = (size_t)(bins + 2) * sizeof(unsigned long long);
+    unsigned long long *d_counts = nullptr;
+    CU(cudaMallocAsync((void **)&d_counts, bytes, e->stream));
+    cudaError_t ce = cudaMemsetAsync(d_counts, 0, bytes, e->stream);
+    const unsigned blocks = std::min<unsigned>(grid_for(e->N), (unsigned)(e->sm_count * 8));
+    const size_t smem = (size_t)(bins + 2) * sizeof(unsigned int);
+    if (ce == cudaSuccess) {
+        if (e->cfg.precision == MBT_F64)
+            mbt_inventory_hist_kernel<double><<<blocks, MBT_BLOCK, smem, e->stream>>>((const double *)e->col[1], e->N, (long long)lo, bins, d_counts);
+        else
+            mbt_inventory_hist_kernel<float><<<blocks, MBT_BLOCK, smem, e->stream>>>((const float *)e->col[1], e->N, (long long)lo, bins, d_counts);
+        ce = cudaGetLastError();
+        e->launches += 1;
+    }
+    int rc = MBT_OK;
+    if (ce == cudaSuccess && group_sum) { /* counts of all ranks: NCCL all-reduce (sum) on the handle's stream */
+        int r = nccl_api()->AllReduce(d_counts, d_counts, (size_t)(bins + 2), NCCL_UINT64, NCCL_SUM, (nccl_comm_t)e->comm, e->stream);
+        if (r != 0) rc = fail(MBT_E_NCCL, std::string("ncclAllReduce failed: ") + nccl_api()->GetErrorString(r));
+    }
+    if (ce == cudaSuccess && rc == MBT_OK) ce = cudaMemcpyAsync(counts_out, d_counts, bytes, cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t se = cudaStreamSynchronize(e->stream);
+    cudaFreeAsync(d_counts, e->stream);
+    if (rc) return rc;
+    if (ce != cudaSuccess || se != cudaSuccess)
+        return fail(MBT_E_CUDA, std::string("mbt_inventory_histogram: ") + cudaGetErrorString(ce != cudaSuccess ? ce : se));
+    return MBT_OK;
+}
+
+} /* extern "C" */

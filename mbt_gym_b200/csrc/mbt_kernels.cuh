@@ -564,6 +564,35 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_scatter_state_kernel(StepParams
     if (imp_has_state(p.imp)) st.x0[i] = row[d];
 }
 
+/* ------------------------------------------------------------------ inventory histogram */
+/*
+ * Histogram of the inventory column over integer bins lo .. hi (the reference plots np.histogram of terminal inventories,
+ * gym/helpers/plotting.py:94-110; north_star: "inventory distribution").  counts[0] = below lo, counts[1 + (q - lo)] for
+ * lo <= round(q) <= hi, counts[hi - lo + 2] = above hi or NaN.  Shared-memory histogram per block (bins <= 4096), one global
+ * 64-bit atomicAdd per non-empty bin and block.  Integer counts: the result does not depend on the order of the atomics.
+ */
+constexpr int MBT_HIST_MAX_BINS = 4096;
+template <typename T>
+__global__ void __launch_bounds__(MBT_BLOCK) mbt_inventory_hist_kernel(const T *__restrict__ inv, long long n, long long lo, int bins,
+                                                                       unsigned long long *counts) {
+    extern __shared__ unsigned int sh[];
+    for (int b = threadIdx.x; b < bins + 2; b += MBT_BLOCK) sh[b] = 0u;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * MBT_BLOCK;
+    for (long long i = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x; i < n; i += stride) {
+        const double q = (double)inv[i];
+        int slot = bins + 1; /* NaN / above */
+        if (q == q) {
+            const double r = rint(q) - (double)lo;
+            slot = r < 0.0 ? 0 : (r < (double)bins ? 1 + (int)r : bins + 1);
+        }
+        atomicAdd(&sh[slot], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins + 2; b += MBT_BLOCK)
+        if (sh[b]) atomicAdd(counts + b, (unsigned long long)sh[b]);
+}
+
 /* ------------------------------------------------------------------ reward on caller rows */
 template <typename T>
 __global__ void __launch_bounds__(MBT_BLOCK) mbt_reward_kernel(StepParams<T> p, int is_terminal, const T *cur, const T *act, const T *nxt,

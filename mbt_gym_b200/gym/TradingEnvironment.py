@@ -360,6 +360,20 @@ class TradingEnvironment(_track.Tracked, _EnvBase):
             return native.rollout(policy, ret, q), ret, q
         return native.rollout(policy)
 
+    def inventory_histogram(self, lo=None, hi=None, group_sum=False):
+        """Distribution of the current (after an episode: terminal) inventories, binned on the device: returns
+        `(inventories, counts)` for the integer bins lo..hi (default: -max_inventory..max_inventory, at most 4096 bins)
+        plus `(below, above)` -- what the reference's results plot histograms on the host (helpers/plotting.py:94-110).
+        `group_sum=True` sums the counts of all ranks of the handle's library group (sharding.create_group)."""
+        native = self._ensure_native()
+        if not self._started:
+            raise RuntimeError("inventory_histogram() called before reset()")
+        q = int(min(self.max_inventory, 2047))
+        lo = -q if lo is None else int(lo)
+        hi = q if hi is None else int(hi)
+        c = native.inventory_histogram(lo, hi, group_sum)
+        return np.arange(lo, hi + 1), c[1:-1], (int(c[0]), int(c[-1]))
+
     # ------------------------------------------------------------------ internals
     @property
     def _intercept_obs_norm(self):

@@ -49,6 +49,7 @@ def _worker(rank, world, port, n_total, q):
     env.group_wait()
     out["summary"] = sharding.summary_struct_to_dict(summ)
     out["returns"] = allr.cpu().numpy()
+    out["hist"] = env.inventory_histogram(60, 100, group_sum=True)  # terminal inventories of ALL ranks (NCCL sum)
     # the same exchange through torch.distributed (cross-check of the library path)
     env.reset(mem=_abi.MBT_MEM_DEVICE)
     local = env.rollout(_policy(1, -1.0), loc, None, mem=_abi.MBT_MEM_DEVICE)
@@ -96,6 +97,8 @@ def test_two_rank_group_equals_one_handle(n_total):
     one.reset()
     ret = np.empty(n_total)
     want = sharding.summary_struct_to_dict(one.rollout(_policy(1, -1.0), ret))
+    want_hist = one.inventory_histogram(60, 100)
+    assert want_hist.sum() == n_total
     one.close()
     for r in range(world):
         got = res[r]["summary"]
@@ -105,6 +108,7 @@ def test_two_rank_group_equals_one_handle(n_total):
             # (a second episode, other draws:) the library's all-reduce against torch.distributed's on the same local summary
             np.testing.assert_allclose(res[r]["summary_lib_again"][f], res[r]["summary_torch"][f], rtol=1e-14, err_msg=f)
         assert np.array_equal(res[r]["returns"], ret), "gathered returns: global-id order, bit-identical to one handle"
+        assert np.array_equal(res[r]["hist"], want_hist), "inventory histogram summed over the group"
     spec = dict(SPECS["power_fill"], N=n_total, n_steps=6, normalise_action=False, normalise_obs=False)
     fenv = build_facade_env(spec)
     acts = np.random.default_rng(1).uniform(0.0, 2.5, size=(6, n_total, 2))

@@ -418,3 +418,26 @@ def test_reconfigure_switches_the_specialised_kernel():
         o, r, _d = orc.step(a)
         assert_same(obs, o); assert_same(rew, r)
     env.close()
+
+
+# ------------------------------------------------------------------ inventory distribution on the device
+def test_inventory_histogram_equals_numpy_bincount():
+    """north_star's "inventory distribution" / the reference's results histogram (helpers/plotting.py:94-110): binned on the
+    device from the inventory column, equal to numpy's count of the terminal inventories -- also with bins that cut the range
+    (below / above counters) and for float32 state."""
+    from mbt_gym_b200.agents.BaselineAgents import FixedSpreadAgent
+
+    for precision in ("float64", "float32"):
+        env = build_facade_env(dict(SPECS["as_pnl"], N=200_000, n_steps=60, max_inventory=60), precision=precision)
+        env.reset()
+        summ, ret, q = env.rollout_summary(FixedSpreadAgent(env, half_spread=0.6).to_policy(env), return_trajectory_stats=True)
+        inv, counts, (below, above) = env.inventory_histogram()
+        assert below == 0 and above == 0 and counts.sum() == 200_000
+        want = np.array([(q == v).sum() for v in inv])
+        assert np.array_equal(counts, want)
+        assert abs((inv * counts).sum() - summ.sum_q) < 1e-6
+        inv, counts, (below, above) = env.inventory_histogram(lo=-2, hi=3)
+        assert below == (q < -2).sum() and above == (q > 3).sum() and np.array_equal(counts, [(q == v).sum() for v in range(-2, 4)])
+        with pytest.raises(_lib.MbtError):
+            env._native.inventory_histogram(0, 5000)
+        env.close()
