@@ -1,12 +1,12 @@
 #!/bin/bash
 # eight-GPU session: host-link ceiling at 1/2/4/8 active GPUs, bench at 8 and 4 GPUs (NCCL_DEBUG=INFO like the driver may set it)
-OUT=gpurun_out/r2g8
+OUT=gpurun_out/r2g8b
 mkdir -p $OUT
 { lscpu | head -20; nvidia-smi topo -m; free -g; } > $OUT/host.txt 2>&1
 TR8="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541"
 TR4="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29542"
-timeout 400 $TR8 tools/pcie_probe_multi.py --out $OUT/pcie_probe.json --reps 30 > $OUT/pcie_probe.stdout 2> $OUT/pcie_probe.stderr; echo "probe rc=$?"
-grep -E "default|affinity " $OUT/pcie_probe.stderr | grep -v wc | head -30
+echo "probe skipped (profiles/r2_pcie_probe_8gpu.json)"
+
 NCCL_DEBUG=INFO timeout 600 $TR8 bench.py --gpus 8 --steps 20 --warmup 5 > $OUT/bench_8gpu.json 2> $OUT/bench_8gpu.stderr; echo "bench8 rc=$?"
 grep -c "nranks 8" $OUT/bench_8gpu.stderr; grep -v "NCCL INFO" $OUT/bench_8gpu.stderr | tail -5
 timeout 600 $TR4 bench.py --gpus 4 --steps 20 --warmup 5 > $OUT/bench_4gpu.json 2> $OUT/bench_4gpu.stderr; echo "bench4 rc=$?"
