@@ -427,8 +427,7 @@ typedef struct mbt_kernel_info {
 } mbt_kernel_info;
 int mbt_get_kernel_info(mbt_env *env, mbt_kernel_info *out);
 /* Compile the specialised kernel of `cfg` into the on-disk cache WITHOUT a CUDA device (build machines): kind 0 = step,
- * 1 = rollout with `policy_kind` compiled in (or the recording kernel when `record`), 2 = the cooperative
- * reduction + step kernel of the batch-reduced fill models (a no-op for other configurations). */
+ * 1 = rollout with `policy_kind` compiled in (or the recording kernel when `record`). */
 int mbt_jit_precompile(const mbt_config *cfg, int32_t kind, int32_t policy_kind, int32_t record);
 
 /* Histogram of the CURRENT inventory column (after a rollout or a step loop: the terminal inventories) over the integer

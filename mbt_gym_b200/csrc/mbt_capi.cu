@@ -110,11 +110,6 @@ struct mbt_env {
 
     /* run-time specialised kernels of this configuration (mbt_jit.h); NULL = the ahead-of-time table is used */
     const mbt_jit::Module *jit_step = nullptr;
-    const mbt_jit::Module *jit_coop = nullptr; /* batch-reduced fill models: reduction + step in one cooperative kernel */
-    int jit_coop_state = 0;                    /* 0 untried, 1 ready, -1 unavailable */
-    unsigned int *d_coop_bar = nullptr;        /* its monotonic grid-barrier counter */
-    unsigned int coop_launches = 0;            /* launches so far: cell parity of the next one */
-    unsigned int coop_arrivals = 0;            /* blocks launched so far (mod 2^32): the barrier counter's value before the next one */
     const mbt_jit::Module *jit_roll[5] = {}; /* MBT_POL_FIXED .. MBT_POL_SCHEDULE, [4] = recording */
     int jit_roll_state[5] = {};              /* 0 untried, 1 ready, -1 failed */
     std::string jit_error;                   /* why the specialiser is not in use (empty = in use or switched off) */
@@ -350,21 +345,10 @@ static bool wants_jit(const mbt_config &c) {
     return v == 0 || v == 4 || v == 6 || v == 9;
 }
 
-/* MBT_COOP=0: batch-reduced fill models always use the two-kernel form (reduction kernel + step kernel) */
-static bool coop_enabled() {
-    static const bool on = [] {
-        const char *v = getenv("MBT_COOP");
-        return !(v && v[0] == '0');
-    }();
-    return on;
-}
-
 /* (re)select the step kernel of the handle's configuration: called by mbt_create and mbt_reconfigure, never inside a
  * stream capture.  Returns an error only when MBT_JIT=require. */
 static int jit_select_step(mbt_env *e) {
     e->jit_step = nullptr;
-    e->jit_coop = nullptr;
-    e->jit_coop_state = 0;
     for (int i = 0; i < 5; ++i) { e->jit_roll[i] = nullptr; e->jit_roll_state[i] = 0; }
     e->jit_error.clear();
     if (mbt_jit::mode() == 0 || !wants_jit(e->cfg)) return MBT_OK;
@@ -375,18 +359,6 @@ static int jit_select_step(mbt_env *e) {
         e->jit_step = nullptr;
         e->jit_error = err;
         if (mbt_jit::mode() == 2) return fail(rc, "MBT_JIT=require: " + err);
-        return MBT_OK;
-    }
-    if (needs_fill_batch(e->cfg) && coop_enabled()) { /* reduction + step in one cooperative kernel (mbt_step_coop_body) */
-        int coop_ok = 0;
-        cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, e->device);
-        const mbt_jit::Key ck = mbt_jit::key_of(e->cfg, e->io_esz == 8, mbt_jit::STEP_COOP, 0, 0);
-        if (coop_ok && mbt_jit::module_of(ck, &e->jit_coop, err) == MBT_OK && e->jit_coop->blocks_per_sm > 0) {
-            e->jit_coop_state = 1;
-        } else {
-            e->jit_coop = nullptr;
-            e->jit_coop_state = -1; /* the two-kernel form keeps running */
-        }
     }
     return MBT_OK;
 }
@@ -600,59 +572,6 @@ static int launch_fill_batch(mbt_env *e, const StepParams<T> &p, const void *act
     return MBT_OK;
 }
 
-/* batch-reduced fill models, one handle, eager launch: reduction + grid barrier + step in ONE cooperative kernel */
-template <typename T, typename E>
-static int launch_step_coop(mbt_env *e, const StepParams<T> &p, const StepClock<T> &ck, const void *actions, void *obs, void *rew) {
-    const mbt_config &c = e->cfg;
-    StepCoopArgs<T, E> a;
-    StepArgs<T, E> &g = a.s;
-    g.p = p;
-    g.ck = ck;
-    g.st = dev_state<T>(e);
-    g.actions = (const E *)actions;
-    g.obs = (E *)obs;
-    g.rew = (E *)rew;
-    g.n = e->N;
-    g.keys = mbt_philox_expand(e->seed);
-    g.traj_offset = (unsigned long long)c.traj_offset;
-    g.n_step = (unsigned long long)e->n_step;
-    g.clipped = e->d_clipped;
-    g.fill_cells = (unsigned long long *)e->d_fill_partial;
-    g.fill_ticket = e->d_fill_ticket;
-    {
-        int rcb = counter_base_for_launch(e, &g.counter_base);
-        if (rcb) return rcb;
-    }
-    const unsigned grid = std::min<unsigned>(grid_for(e->N), (unsigned)(e->sm_count * e->jit_coop->blocks_per_sm));
-    a.cells = (unsigned long long *)e->d_fill_partial + 2;
-    a.bar = e->d_coop_bar;
-    a.parity = (int)(e->coop_launches & 1u);
-    /* the counter has received one arrival per block of every launch so far: this launch is complete at + grid
-     * (mod 2^32; compared wrap-safe in the kernel) */
-    a.bar_target = e->coop_arrivals + grid;
-    const bool vec = rows_vector_aligned<E>(e, g.actions, g.obs);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(MBT_BLOCK);
-    cfg.stream = e->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1; /* all blocks resident at once, or the launch fails: the barrier cannot deadlock */
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    void *args[1] = {&a};
-    cudaError_t le = cudaLaunchKernelExC(&cfg, (const void *)(vec ? e->jit_coop->k0 : e->jit_coop->k1), args);
-    if (le != cudaSuccess) {
-        cudaGetLastError();
-        e->jit_coop_state = -1; /* e.g. the device is shared and the grid does not fit: two-kernel form from now on */
-        return fail(MBT_E_CUDA, std::string("cooperative step launch failed: ") + cudaGetErrorString(le));
-    }
-    e->coop_launches += 1u;
-    e->coop_arrivals += grid;
-    e->launches += 1;
-    return MBT_OK;
-}
-
 static void advance_clock(mbt_env *e, double t_next) {
     e->t = t_next;
     e->k += 1;
@@ -668,17 +587,6 @@ static int do_step_device(mbt_env *e, const void *actions, void *obs, void *rew,
     int rc = timing_begin(e);
     if (rc) return rc;
     const bool batch = needs_fill_batch(c);
-    if (batch && e->jit_coop_state == 1 && !e->comm && !stream_is_capturing(e)) {
-        rc = launch_step_coop<T, E>(e, p, ck, actions, obs, rew);
-        if (rc == MBT_OK) {
-            rc = timing_end(e);
-            if (rc) return rc;
-            advance_clock(e, t_next);
-            if (done_out) *done_out = (uint8_t)ck.done;
-            return fold_eager(e);
-        }
-        if (e->jit_coop_state == 1) return rc; /* a real error; otherwise the launch was refused: two-kernel form below */
-    }
     if (batch) {
         /* (device-counter mode: the previous launch may be the one-thread fold kernel, which is not PDL-aware) */
         rc = launch_fill_batch<T, E>(e, p, actions, /*allow_pdl=*/!e->device_counters);
@@ -954,7 +862,6 @@ int mbt_destroy(mbt_env *e) {
     cudaFree(e->d_counter_base);
     cudaFree(e->d_fill_partial);
     cudaFree(e->d_fill_ticket);
-    cudaFree(e->d_coop_bar);
     cudaFree(e->d_actions);
     cudaFree(e->d_obs);
     cudaFree(e->d_rew);
@@ -1041,11 +948,8 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     CUB(cudaMemsetAsync(e->d_counter_base, 0, 2 * sizeof(unsigned long long), e->stream));
     /* batch-reduction cells (a few bytes; allocated for every handle: mbt_reconfigure may switch the fill function) */
     e->fill_blocks = std::max(1, e->sm_count * fill_blocks_per_sm()); /* every block ends in 3 same-address atomics */
-    /* [0..1] the two-kernel form's cells, [2..5] the cooperative kernel's two pairs (launch parity) */
-    CUB(cudaMalloc(&e->d_fill_partial, 6 * sizeof(unsigned long long)));
-    CUB(cudaMemsetAsync(e->d_fill_partial, 0, 6 * sizeof(unsigned long long), e->stream));
-    CUB(cudaMalloc((void **)&e->d_coop_bar, sizeof(unsigned int)));
-    CUB(cudaMemsetAsync(e->d_coop_bar, 0, sizeof(unsigned int), e->stream));
+    CUB(cudaMalloc(&e->d_fill_partial, 2 * sizeof(unsigned long long)));
+    CUB(cudaMemsetAsync(e->d_fill_partial, 0, 2 * sizeof(unsigned long long), e->stream));
     CUB(cudaMalloc((void **)&e->d_fill_ticket, sizeof(unsigned int)));
     CUB(cudaMemsetAsync(e->d_fill_ticket, 0, sizeof(unsigned int), e->stream));
     /* episode summary: folded on the device by the rollout kernel, mirrored to pinned host memory on demand */
@@ -1980,11 +1884,8 @@ int mbt_jit_precompile(const mbt_config *cfg, int32_t kind, int32_t policy_kind,
     int rc = mbt_validate_config(cfg, err);
     if (rc) return fail(rc, err);
     if (!wants_jit(*cfg)) return MBT_OK; /* served by a fully specialised ahead-of-time variant */
-    const bool step_kind = kind == 0 || kind == 2;
-    const int io64 = cfg->precision == MBT_F64 && (!step_kind || cfg->io_precision == MBT_IO_SAME);
-    if (kind == 2 && !needs_fill_batch(*cfg)) return MBT_OK;
-    const mbt_jit::Key key = step_kind ? mbt_jit::key_of(*cfg, io64, kind == 0 ? mbt_jit::STEP : mbt_jit::STEP_COOP, 0, 0)
-                                       : mbt_jit::key_of(*cfg, io64, mbt_jit::ROLLOUT, record ? -1 : policy_kind, record ? 1 : 0);
+    const int io64 = cfg->precision == MBT_F64 && (kind != 0 || cfg->io_precision == MBT_IO_SAME);
+    const mbt_jit::Key key = mbt_jit::key_of(*cfg, io64, kind == 0 ? mbt_jit::STEP : mbt_jit::ROLLOUT, record ? -1 : policy_kind, record ? 1 : 0);
     std::vector<char> cubin;
     unsigned long long h = 0;
     bool from_disk = false;

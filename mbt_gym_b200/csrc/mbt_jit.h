@@ -46,7 +46,7 @@ struct EmbeddedHeader {
 };
 #include "_jit_embed.inc" /* static const EmbeddedHeader kHeaders[]; static const int kNumHeaders; */
 
-enum Kind { STEP = 0, ROLLOUT = 1, STEP_COOP = 2 /* batch reduction + step in one cooperative kernel */ };
+enum Kind { STEP = 0, ROLLOUT = 1 };
 
 struct Key {
     int dyn, mid, arr, imp, rew, fill, na, no, nr, sel;
@@ -72,7 +72,6 @@ struct Module {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t k0 = nullptr, k1 = nullptr; /* STEP: (whole-row vector access, scalar access); ROLLOUT: k0 */
     int regs = 0, local_bytes = 0;
-    int blocks_per_sm = 0; /* STEP_COOP: resident blocks per SM (cooperative grid = SMs x this) */
     double compile_ms = 0;
     bool from_disk = false;
     unsigned long long hash = 0;
@@ -151,13 +150,6 @@ static inline std::string source_of(const Key &k) {
                  "{ mbt_step_body<%s, %s, VJ, true>(g); }\n"
                  "extern \"C\" __global__ void __launch_bounds__(MBT_BLOCK) mbt_jit_step(const __grid_constant__ StepArgs<%s, %s> g) "
                  "{ mbt_step_body<%s, %s, VJ, false>(g); }\n",
-                 T, E, T, E, T, E, T, E);
-    else if (k.kind == STEP_COOP)
-        snprintf(buf + n, sizeof buf - n,
-                 "extern \"C\" __global__ void __launch_bounds__(MBT_BLOCK) mbt_jit_step_vec(const __grid_constant__ StepCoopArgs<%s, %s> g) "
-                 "{ mbt_step_coop_body<%s, %s, VJ, true>(g); }\n"
-                 "extern \"C\" __global__ void __launch_bounds__(MBT_BLOCK) mbt_jit_step(const __grid_constant__ StepCoopArgs<%s, %s> g) "
-                 "{ mbt_step_coop_body<%s, %s, VJ, false>(g); }\n",
                  T, E, T, E, T, E, T, E);
     else
         snprintf(buf + n, sizeof buf - n,
@@ -293,8 +285,8 @@ static inline int module_of(const Key &key, const Module **out, std::string &err
     int rc = cubin_of(key, cubin, &m.hash, &m.from_disk, &m.compile_ms, err);
     if (rc) return rc;
     cudaError_t ce = cudaLibraryLoadData(&m.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&m.k0, m.lib, key.kind == ROLLOUT ? "mbt_jit_rollout" : "mbt_jit_step_vec");
-    if (ce == cudaSuccess && key.kind != ROLLOUT) ce = cudaLibraryGetKernel(&m.k1, m.lib, "mbt_jit_step");
+    if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&m.k0, m.lib, key.kind == STEP ? "mbt_jit_step_vec" : "mbt_jit_rollout");
+    if (ce == cudaSuccess && key.kind == STEP) ce = cudaLibraryGetKernel(&m.k1, m.lib, "mbt_jit_step");
     if (ce != cudaSuccess) {
         cudaGetLastError();
         err = std::string("loading the specialised kernel failed: ") + cudaGetErrorString(ce);
@@ -307,15 +299,6 @@ static inline int module_of(const Key &key, const Module **out, std::string &err
         m.local_bytes = (int)fa.localSizeBytes;
     } else {
         cudaGetLastError();
-    }
-    if (key.kind == STEP_COOP) { /* how many blocks of the cooperative kernel are resident per SM */
-        int nb0 = 0, nb1 = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, (const void *)m.k0, 256, 0) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, (const void *)m.k1, 256, 0) != cudaSuccess) {
-            cudaGetLastError();
-            nb0 = nb1 = 0;
-        }
-        m.blocks_per_sm = nb0 < nb1 ? nb0 : nb1;
     }
     auto ins = table.emplace(src, m);
     *out = &ins.first->second;

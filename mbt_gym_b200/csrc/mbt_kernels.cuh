@@ -283,10 +283,8 @@ __device__ __forceinline__ double key_to_real(unsigned long long k) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-/* thr_pre: batch-reduced fill models, the step's two thresholds when the caller already holds them (the cooperative kernel
- * below); NULL = decode them from g.fill_cells in a block-level stage */
 template <typename T, typename E, class V, bool VEC>
-__device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, bool full_warp, E *warp_smem, const T *thr_pre = nullptr) {
+__device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, bool full_warp, E *warp_smem) {
     const StepParams<T> &p = g.p;
     const bool live = i < g.n; /* (the threads past the end still take part in the block-level stage below) */
     /* state-independent prologue: the step's 128 random bits depend only on (seed, trajectory id, step index) */
@@ -313,10 +311,7 @@ __device__ __forceinline__ void step_row(const StepArgs<T, E> &g, long long i, b
     }
 
     T fill_thr[2] = {(T)0, (T)0};
-    if (fill_is_batch(pick<V::fill>(p.fill)) && thr_pre) {
-        fill_thr[0] = thr_pre[0];
-        fill_thr[1] = thr_pre[1];
-    } else if (fill_is_batch(pick<V::fill>(p.fill))) {
+    if (fill_is_batch(pick<V::fill>(p.fill))) {
         /* per block, two threads turn the batch maxima (keys left by mbt_fill_batch_kernel) into the step's two fill
          * thresholds -- one pow each for the power function, side by side -- and share them */
         __shared__ T s_thr[2];
@@ -475,106 +470,6 @@ __global__ void __launch_bounds__(MBT_BLOCK) mbt_fill_batch_kernel(const __grid_
     T b = sm[0][threadIdx.x]; /* thread 0: bid side, thread 1: ask side */
     for (int w = 1; w < MBT_BLOCK / 32; ++w) b = nanmax<T>(b, sm[w][threadIdx.x]);
     atomicMax(g.cells + threadIdx.x, real_to_key((double)b));
-}
-
-
-/* ------------------------------------------------------------------ batch reduction + step in ONE cooperative kernel */
-/*
- * The two-kernel form above pays a grid-wide dependency (kernel boundary) on top of the second pass over the action
- * matrix.  When every block of the grid is resident at once (cooperative launch: grid = SMs x resident blocks per SM)
- * both passes fit in one kernel with a grid barrier in between:
- *     pass 1   grid-stride max of the two depth columns -> one atomicMax per block and side into this launch's cells
- *     barrier  arrive (atomicAdd) + spin on an acquire load until all blocks of THIS launch arrived; the counter is
- *              monotonic across launches (target = (launch index + 1) * gridDim, compared wrap-safe), the cells are
- *              double-buffered by launch parity and block 0 clears the other pair for the next launch
- *     pass 2   thresholds per block (two threads, shared memory), then the ordinary step_row over the same rows, whose
- *              action loads now hit L2
- * Used for handles outside a group and outside stream capture (the launch index is baked by the host); otherwise the
- * two-kernel form runs.  Same arithmetic, same results.
- */
-template <typename T, typename E>
-struct StepCoopArgs {
-    StepArgs<T, E> s;
-    unsigned long long *cells; /* [4]: pair (launch parity) x side, keys */
-    unsigned int *bar;         /* monotonic arrival counter */
-    unsigned int bar_target;   /* (launch index + 1) * gridDim.x  (mod 2^32) */
-    int parity;                /* launch index & 1 */
-};
-
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-template <typename T, typename E, class V, bool VEC>
-__device__ __forceinline__ void mbt_step_coop_body(const StepCoopArgs<T, E> &c) {
-    const StepArgs<T, E> &g = c.s;
-    const StepParams<T> &p = g.p;
-    constexpr bool FIXED_W = V::Dout > 0;
-    constexpr int SW = FIXED_W ? V::Dout : MBT_MAX_OBS_DIM;
-    constexpr bool NO_STAGE = FIXED_W && (V::Dout == 4 || V::Dout == 2 || V::Dout == 1);
-    __shared__ E smem[NO_STAGE ? 1 : (MBT_BLOCK / 32) * 32 * SW];
-    __shared__ T sm_max[MBT_BLOCK / 32][2];
-    __shared__ T s_thr[2];
-    E *warp_smem = NO_STAGE ? smem : smem + (threadIdx.x >> 5) * 32 * SW;
-    const long long stride = (long long)gridDim.x * MBT_BLOCK;
-    const long long first = (long long)blockIdx.x * MBT_BLOCK + threadIdx.x;
-    unsigned long long *cells = c.cells + 2 * c.parity;
-    if (blockIdx.x == 0 && threadIdx.x < 2) c.cells[2 * (c.parity ^ 1) + threadIdx.x] = 0ull; /* next launch's pair */
-
-    /* pass 1: deepest quote of the batch, per side */
-    const int A = action_width<T, V>(p);
-    const T neg_inf = -(T)INFINITY;
-    T m0 = neg_inf, m1 = neg_inf;
-    constexpr int UNROLL = 4; /* independent row loads in flight per thread (a thread owns ~3.5 rows at N = 2^20) */
-    for (long long i = first; i < g.n; i += UNROLL * stride) {
-        E d0[UNROLL], d1[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            d0[u] = d1[u] = (E)0;
-            if (i + u * stride < g.n) load_depths<E, VEC>(g.actions, i + u * stride, A, d0[u], d1[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-            if (i + u * stride < g.n) {
-                m0 = nanmax<T>(m0, denorm_action<T, V>(p, (T)d0[u], 0));
-                m1 = nanmax<T>(m1, denorm_action<T, V>(p, (T)d1[u], 1));
-            }
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    m0 = warp_nanmax<T>(m0);
-    m1 = warp_nanmax<T>(m1);
-    if (lane == 0) { sm_max[warp][0] = m0; sm_max[warp][1] = m1; }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-        T b = sm_max[0][threadIdx.x];
-        for (int w = 1; w < MBT_BLOCK / 32; ++w) b = nanmax<T>(b, sm_max[w][threadIdx.x]);
-        atomicMax(cells + threadIdx.x, real_to_key((double)b));
-        __threadfence(); /* the maximum is visible device-wide before this block arrives */
-    }
-    /* grid barrier */
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        atomicAdd(c.bar, 1u);
-        while ((int)(ld_acquire_u32(c.bar) - c.bar_target) < 0) __nanosleep(40);
-        __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-        const T m_own = (T)key_to_real(__ldcg(cells + threadIdx.x)), m_other = (T)key_to_real(__ldcg(cells + (threadIdx.x ^ 1u)));
-        s_thr[threadIdx.x] = fill_batch_threshold_side<T>(p, m_own, m_other, (int)threadIdx.x);
-    }
-    __syncthreads();
-    const T thr[2] = {s_thr[0], s_thr[1]};
-
-    /* pass 2: the step itself (whole warps walk together, so the staged observation stores keep their full-warp test) */
-    for (long long i0 = (long long)blockIdx.x * MBT_BLOCK; i0 < g.n; i0 += stride) {
-        const long long i = i0 + threadIdx.x;
-        const long long warp_row0 = i - (long long)(threadIdx.x & 31u);
-        const bool full_warp = !NO_STAGE && (warp_row0 + 32 <= g.n);
-        step_row<T, E, V, VEC>(g, i, full_warp, warp_smem, thr);
-    }
 }
 
 /* ------------------------------------------------------------------ reset */

@@ -21,7 +21,6 @@ def main(verbose=True):
         for prec in (_abi.MBT_F64, _abi.MBT_F32):
             cfg = g.config(prec)
             _lib.jit_precompile(cfg, 0)
-            _lib.jit_precompile(cfg, 2)  # (only the batch-reduced fill models have this one)
             n += 1
             for pol in (_abi.MBT_POL_FIXED, _abi.MBT_POL_AVELLANEDA_STOIKOV):
                 if pol == _abi.MBT_POL_AVELLANEDA_STOIKOV and cfg.dynamics != _abi.MBT_DYN_LIMIT:
