@@ -9,6 +9,8 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <cctype>
 #include <cstdint>
 #include <cstdio>
@@ -69,7 +71,7 @@ struct mbt_env {
     void *d_actions = nullptr, *d_obs = nullptr, *d_rew = nullptr;
     void *h_actions = nullptr, *h_obs = nullptr, *h_rew = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr; /* H2D / D2H copy engines for the pipelined host path */
-    cudaEvent_t ev_in[MBT_PIPE_CHUNKS] = {}, ev_k[MBT_PIPE_CHUNKS] = {};
+    cudaEvent_t ev_in[MBT_PIPE_CHUNKS] = {}, ev_k[MBT_PIPE_CHUNKS] = {}, ev_out[MBT_PIPE_CHUNKS] = {};
 
     /* batch reduction in front of the step (Triangular / Power fill functions): running maxima (keys), ticket, thresholds */
     void *d_fill_partial = nullptr;
@@ -318,25 +320,82 @@ static bool host_ptr_is_pinned(const void *p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-/* parallel memcpy between pageable user memory and pinned staging (a single thread tops out well below PCIe) */
-static void par_memcpy(void *dst, const void *src, size_t bytes) {
-    const size_t chunk = 4u << 20;
-    unsigned hw = std::thread::hardware_concurrency();
-    size_t nthreads = std::min<size_t>(std::max(1u, std::min(hw, 8u)), (bytes + chunk - 1) / chunk);
-    if (nthreads <= 1) {
-        memcpy(dst, src, bytes);
-        return;
+/*
+ * Parallel memcpy between pageable caller memory and pinned staging.  A single thread copies at ~10 GB/s, far below the
+ * PCIe rate, and creating threads per call cost more than the copy (round 1: up to 8 std::threads per mbt_step -- 0.9 ms
+ * of a 2.0 ms step for an ordinary NumPy action array).  One process-wide pool of persistent workers (created on first
+ * use, never joined: they sleep on a condition variable) splits a copy into equal parts; the calling thread takes one part
+ * itself.  Calls from different handles' threads serialise on the pool's mutex (the copies are memory-bound anyway).
+ * MBT_COPY_THREADS overrides the worker count (default: a quarter of the hardware threads, 2..8).
+ */
+class CopyPool {
+public:
+    static CopyPool &get() {
+        static CopyPool *pool = new CopyPool(); /* leaked on purpose: workers may outlive static destruction */
+        return *pool;
     }
-    std::vector<std::thread> th;
-    size_t per = (bytes / nthreads + 63) & ~(size_t)63;
-    for (size_t i = 0; i < nthreads; ++i) {
-        size_t off = i * per;
-        if (off >= bytes) break;
-        size_t len = std::min(per, bytes - off);
-        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+    void copy(void *dst, const void *src, size_t bytes) {
+        const size_t min_part = 256u << 10;
+        size_t parts = std::min<size_t>(workers_.size() + 1, (bytes + min_part - 1) / min_part);
+        if (parts <= 1) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        const size_t per = ((bytes / parts) + 63) & ~(size_t)63;
+        std::unique_lock<std::mutex> call(call_mu_); /* one parallel copy at a time */
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            dst_ = (char *)dst; src_ = (const char *)src; bytes_ = bytes; per_ = per;
+            next_part_ = 1; /* part 0 is the caller's */
+            parts_ = parts;
+            pending_ = parts - 1;
+            generation_ += 1;
+        }
+        cv_work_.notify_all();
+        memcpy(dst, src, std::min(per, bytes));
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
     }
-    for (auto &t : th) t.join();
-}
+
+private:
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int n = (int)std::min(8u, std::max(2u, hw / 4));
+        if (const char *v = getenv("MBT_COPY_THREADS")) n = std::max(1, std::min(64, atoi(v)));
+        for (int i = 0; i + 1 < n; ++i) {
+            workers_.emplace_back([this] { run(); });
+            workers_.back().detach();
+        }
+    }
+    void run() {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_work_.wait(lk, [&] { return generation_ != seen; });
+            seen = generation_;
+            while (next_part_ < parts_) {
+                const size_t part = next_part_++;
+                const size_t off = part * per_;
+                char *d = dst_;
+                const char *s = src_;
+                const size_t len = off < bytes_ ? std::min(per_, bytes_ - off) : 0;
+                lk.unlock();
+                if (len) memcpy(d + off, s + off, len);
+                lk.lock();
+                if (--pending_ == 0) cv_done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_work_, cv_done_;
+    char *dst_ = nullptr;
+    const char *src_ = nullptr;
+    size_t bytes_ = 0, per_ = 0, next_part_ = 0, parts_ = 0, pending_ = 0;
+    unsigned long long generation_ = 0;
+};
+
+static void par_memcpy(void *dst, const void *src, size_t bytes) { CopyPool::get().copy(dst, src, bytes); }
 
 /* ------------------------------------------------------------------ run-time specialisation (mbt_jit.h) */
 /* configurations whose ahead-of-time variant still reads model kinds or normalisation flags at run time */
@@ -635,10 +694,14 @@ static int pipe_chunks() {
  * Host-buffer step: the batch is cut into row chunks and each chunk flows H2D(actions) -> kernel -> D2H(obs, rewards)
  * on three streams, so the two copy engines (PCIe is full duplex) and the SMs overlap; the call returns when the last
  * chunk's results are in the caller's buffers.  `act_src`, `obs_dst`, `rew_dst` are pinned (caller's own pinned
- * buffers, or the handle's staging).
+ * buffers, or the handle's staging).  Pageable caller arrays take part in the pipeline chunk by chunk: `act_pageable`
+ * (ordinary NumPy actions) is copied into the pinned `act_src` right before each chunk's upload, and `obs_user` receives
+ * each chunk from the pinned `obs_dst` as soon as its download has finished -- both by the persistent copy pool, both
+ * overlapped with the transfers of the other chunks (round 1 staged the whole arrays before / after the pipeline).
  */
 template <typename T, typename E>
-static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst, void *rew_dst, uint8_t *done_out) {
+static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst, void *rew_dst, uint8_t *done_out,
+                                  const void *act_pageable, void *obs_user) {
     const mbt_config &c = e->cfg;
     const double t_next = e->t + c.step_size;
     const StepParams<T> p = mbt_make_params<T>(c, e->t0, e->q0_per_traj, e->q0_uniform);
@@ -680,6 +743,7 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
         if (r0 >= N) break;
         const long long n = std::min(bounds[k + 1], N) - r0;
         if (n <= 0) continue;
+        if (act_pageable) par_memcpy((char *)const_cast<void *>(act_src) + r0 * arow, (const char *)act_pageable + r0 * arow, (size_t)n * arow);
         CU(cudaMemcpyAsync((char *)e->d_actions + r0 * arow, (const char *)act_src + r0 * arow, n * arow,
                            cudaMemcpyHostToDevice, e->copy_in));
         CU(cudaEventRecord(e->ev_in[k], e->copy_in));
@@ -698,6 +762,7 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
         if (obs_dst)
             CU(cudaMemcpyAsync((char *)obs_dst + r0 * orow, (const char *)e->d_obs + r0 * orow, n * orow,
                                cudaMemcpyDeviceToHost, e->copy_out));
+        if (obs_user) CU(cudaEventRecord(e->ev_out[k], e->copy_out));
         /* rewards: one copy per call, behind the last chunk (every D2H copy costs ~15 us of engine time on top of its
          * bytes; the (N,) reward vector is a fifth of the output) -- unless MBT_PIPE_REW_PER_CHUNK=1 */
         static const bool rew_per_chunk = getenv("MBT_PIPE_REW_PER_CHUNK") != nullptr;
@@ -722,6 +787,15 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
         }
         fprintf(stderr, "\n");
         for (auto &ev : tr) cudaEventDestroy(ev);
+    }
+    if (obs_user) { /* hand each finished chunk to the caller's pageable array while the later chunks are still in flight */
+        for (int k = 0; k < chunks; ++k) {
+            const long long r0 = bounds[k];
+            const long long n = std::min(bounds[k + 1], N) - r0;
+            if (r0 >= N || n <= 0) continue;
+            CU(cudaEventSynchronize(e->ev_out[k]));
+            par_memcpy((char *)obs_user + r0 * orow, (const char *)obs_dst + r0 * orow, (size_t)n * orow);
+        }
     }
     CU(cudaStreamSynchronize(e->copy_out));
     CU(cudaStreamSynchronize(e->stream));
@@ -880,6 +954,7 @@ int mbt_destroy(mbt_env *e) {
     for (int i = 0; i < MBT_PIPE_CHUNKS; ++i) {
         if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
         if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]);
+        if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
     }
     if (e->copy_in) cudaStreamDestroy(e->copy_in);
     if (e->copy_out) cudaStreamDestroy(e->copy_out);
@@ -936,6 +1011,7 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     for (int i = 0; i < MBT_PIPE_CHUNKS; ++i) {
         CUB(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
         CUB(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
     }
     /* columns padded to 256 B so every column base is aligned for any vector width */
     const size_t col_bytes = (((size_t)e->N * e->esz) + 255) & ~(size_t)255;
@@ -1109,8 +1185,10 @@ int mbt_step(mbt_env *e, const void *actions, void *obs_out, void *rew_out, uint
     if (rc) return rc;
     const size_t ab = (size_t)e->N * e->A * e->io_esz, ob = (size_t)e->N * e->Dout * e->io_esz, rb = (size_t)e->N * e->io_esz;
     const void *src = actions;
-    if (!host_ptr_is_pinned(actions)) { /* pageable caller memory: stage through the handle's pinned buffer */
-        par_memcpy(e->h_actions, actions, ab);
+    const bool stage_act = !host_ptr_is_pinned(actions); /* pageable caller memory: through the handle's pinned buffer */
+    const bool pipelined = !host_path_zero_copy();
+    if (stage_act) {
+        if (!pipelined) par_memcpy(e->h_actions, actions, ab); /* (the pipeline stages chunk by chunk) */
         src = e->h_actions;
     }
     const bool un_obs = obs_out && !host_ptr_is_pinned(obs_out), un_rew = rew_out && !host_ptr_is_pinned(rew_out);
@@ -1127,10 +1205,11 @@ int mbt_step(mbt_env *e, const void *actions, void *obs_out, void *rew_out, uint
         if (rc) return rc;
         CU(cudaStreamSynchronize(e->stream));
     } else {
-        rc = MBT_CALL_TE(e, do_step_host_pipelined, e, src, obs_dst, rew_dst, done_out);
+        rc = MBT_CALL_TE(e, do_step_host_pipelined, e, src, obs_dst, rew_dst, done_out, stage_act ? actions : nullptr,
+                         un_obs ? obs_out : nullptr);
         if (rc) return rc;
     }
-    if (un_obs) par_memcpy(obs_out, e->h_obs, ob);
+    if (un_obs && !pipelined) par_memcpy(obs_out, e->h_obs, ob);
     if (un_rew) par_memcpy(rew_out, e->h_rew, rb);
     return MBT_OK;
 }

@@ -441,3 +441,26 @@ def test_inventory_histogram_equals_numpy_bincount():
         with pytest.raises(_lib.MbtError):
             env._native.inventory_histogram(0, 5000)
         env.close()
+
+
+# ------------------------------------------------------------------ pageable caller arrays through the chunked pipeline
+def test_pageable_arrays_through_the_chunked_pipeline_equal_the_pinned_path():
+    """Ordinary NumPy action arrays and `copy_outputs=True` outputs are staged / unstaged chunk by chunk inside the
+    H2D -> kernel -> D2H pipeline (N >= 2^17 uses several chunks): same results as pinned buffers, for a row count that
+    is not a multiple of the chunk granularity."""
+    n = (1 << 18) + 12345
+    spec = dict(SPECS["hawkes_pnl"], N=n, n_steps=6)
+    rng = np.random.default_rng(0)
+    acts = rng.uniform(0.1, 1.5, size=(6, n, 2))
+    pinned_env = build_facade_env(spec)
+    pageable_env = build_facade_env(spec, copy_outputs=True)
+    a_pin = pinned_env.pinned_actions()
+    o1, o2 = pinned_env.reset(), pageable_env.reset()
+    assert o2.flags.owndata and np.array_equal(o1, o2)
+    for k in range(6):
+        a_pin[:] = acts[k]
+        o1, r1, d1, _ = pinned_env.step(a_pin)
+        o2, r2, d2, _ = pageable_env.step(acts[k].copy())
+        assert o2.flags.owndata and r2.flags.owndata
+        assert np.array_equal(o1, o2) and np.array_equal(r1, r2) and d1[0] == d2[0]
+    pinned_env.close(); pageable_env.close()
