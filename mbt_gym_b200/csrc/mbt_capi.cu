@@ -71,7 +71,7 @@ struct mbt_env {
     void *d_actions = nullptr, *d_obs = nullptr, *d_rew = nullptr;
     void *h_actions = nullptr, *h_obs = nullptr, *h_rew = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr; /* H2D / D2H copy engines for the pipelined host path */
-    cudaEvent_t ev_in[MBT_PIPE_CHUNKS] = {}, ev_k[MBT_PIPE_CHUNKS] = {}, ev_out[MBT_PIPE_CHUNKS] = {};
+    cudaEvent_t ev_in[MBT_PIPE_CHUNKS] = {}, ev_k[MBT_PIPE_CHUNKS] = {};
 
     /* batch reduction in front of the step (Triangular / Power fill functions): running maxima (keys), ticket, thresholds */
     void *d_fill_partial = nullptr;
@@ -694,14 +694,16 @@ static int pipe_chunks() {
  * Host-buffer step: the batch is cut into row chunks and each chunk flows H2D(actions) -> kernel -> D2H(obs, rewards)
  * on three streams, so the two copy engines (PCIe is full duplex) and the SMs overlap; the call returns when the last
  * chunk's results are in the caller's buffers.  `act_src`, `obs_dst`, `rew_dst` are pinned (caller's own pinned
- * buffers, or the handle's staging).  Pageable caller arrays take part in the pipeline chunk by chunk: `act_pageable`
- * (ordinary NumPy actions) is copied into the pinned `act_src` right before each chunk's upload, and `obs_user` receives
- * each chunk from the pinned `obs_dst` as soon as its download has finished -- both by the persistent copy pool, both
- * overlapped with the transfers of the other chunks (round 1 staged the whole arrays before / after the pipeline).
+ * buffers, or the handle's staging).  A pageable action array (an ordinary NumPy array: what `agent.get_action(obs)` returns)
+ * takes part in the pipeline chunk by chunk: `act_pageable` is copied into the pinned `act_src` by the persistent copy pool
+ * right before each chunk's upload, overlapped with the transfers of the earlier chunks (round 1 staged the whole array in
+ * front of the pipeline with threads created per call: 2.0 ms per step, now 1.4-1.5; pinned actions: 1.0).  Pageable OUTPUT
+ * arrays (`copy_outputs=True`) are filled after the pipeline: writing 42 MB of never-touched pages is page-fault-bound
+ * (3-5 ms) however it is chunked -- the default pooled pinned outputs avoid it.
  */
 template <typename T, typename E>
 static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst, void *rew_dst, uint8_t *done_out,
-                                  const void *act_pageable, void *obs_user) {
+                                  const void *act_pageable) {
     const mbt_config &c = e->cfg;
     const double t_next = e->t + c.step_size;
     const StepParams<T> p = mbt_make_params<T>(c, e->t0, e->q0_per_traj, e->q0_uniform);
@@ -715,7 +717,15 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
     long long bounds[MBT_PIPE_CHUNKS + 1];
     int chunks = 1;
     bounds[0] = 0;
-    if (N >= (1 << 17) && !batch) {
+    if (N >= (1 << 17) && !batch && act_pageable) {
+        /* pageable action array: the host copy into pinned staging (~20 GB/s on the measured hosts) is the slowest stage, so
+         * equal chunks -- chunk k+1 is staged while chunk k is on the wire, and the call ends one chunk after the last host
+         * copy.  Measured per step at N = 2^20: 16 chunks 1.39-1.55 ms, 8 chunks 1.61-1.64 ms (pinned actions: 1.02 ms;
+         * round 1's staging in front of the pipeline: 1.95-2.05 ms). */
+        chunks = MBT_PIPE_CHUNKS;
+        const long long rows = ((N + chunks - 1) / chunks + 255) & ~255ll;
+        for (int i = 1; i <= chunks; ++i) bounds[i] = std::min(N, rows * i);
+    } else if (N >= (1 << 17) && !batch) {
         if (pipe_schedule_geometric()) {
             static const int geo3 = getenv("MBT_PIPE_GEO3") != nullptr;
             const int shifts5[5] = {4, 3, 2, 1, 0}, shifts3[3] = {3, 1, 0}; /* cumulative end of chunk i = N >> shift */
@@ -762,7 +772,6 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
         if (obs_dst)
             CU(cudaMemcpyAsync((char *)obs_dst + r0 * orow, (const char *)e->d_obs + r0 * orow, n * orow,
                                cudaMemcpyDeviceToHost, e->copy_out));
-        if (obs_user) CU(cudaEventRecord(e->ev_out[k], e->copy_out));
         /* rewards: one copy per call, behind the last chunk (every D2H copy costs ~15 us of engine time on top of its
          * bytes; the (N,) reward vector is a fifth of the output) -- unless MBT_PIPE_REW_PER_CHUNK=1 */
         static const bool rew_per_chunk = getenv("MBT_PIPE_REW_PER_CHUNK") != nullptr;
@@ -787,15 +796,6 @@ static int do_step_host_pipelined(mbt_env *e, const void *act_src, void *obs_dst
         }
         fprintf(stderr, "\n");
         for (auto &ev : tr) cudaEventDestroy(ev);
-    }
-    if (obs_user) { /* hand each finished chunk to the caller's pageable array while the later chunks are still in flight */
-        for (int k = 0; k < chunks; ++k) {
-            const long long r0 = bounds[k];
-            const long long n = std::min(bounds[k + 1], N) - r0;
-            if (r0 >= N || n <= 0) continue;
-            CU(cudaEventSynchronize(e->ev_out[k]));
-            par_memcpy((char *)obs_user + r0 * orow, (const char *)obs_dst + r0 * orow, (size_t)n * orow);
-        }
     }
     CU(cudaStreamSynchronize(e->copy_out));
     CU(cudaStreamSynchronize(e->stream));
@@ -954,7 +954,6 @@ int mbt_destroy(mbt_env *e) {
     for (int i = 0; i < MBT_PIPE_CHUNKS; ++i) {
         if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
         if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]);
-        if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
     }
     if (e->copy_in) cudaStreamDestroy(e->copy_in);
     if (e->copy_out) cudaStreamDestroy(e->copy_out);
@@ -1011,7 +1010,6 @@ int mbt_create(const mbt_config *cfg, int device, mbt_env **out) {
     for (int i = 0; i < MBT_PIPE_CHUNKS; ++i) {
         CUB(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
         CUB(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming));
-        CUB(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
     }
     /* columns padded to 256 B so every column base is aligned for any vector width */
     const size_t col_bytes = (((size_t)e->N * e->esz) + 255) & ~(size_t)255;
@@ -1205,11 +1203,10 @@ int mbt_step(mbt_env *e, const void *actions, void *obs_out, void *rew_out, uint
         if (rc) return rc;
         CU(cudaStreamSynchronize(e->stream));
     } else {
-        rc = MBT_CALL_TE(e, do_step_host_pipelined, e, src, obs_dst, rew_dst, done_out, stage_act ? actions : nullptr,
-                         un_obs ? obs_out : nullptr);
+        rc = MBT_CALL_TE(e, do_step_host_pipelined, e, src, obs_dst, rew_dst, done_out, stage_act ? actions : nullptr);
         if (rc) return rc;
     }
-    if (un_obs && !pipelined) par_memcpy(obs_out, e->h_obs, ob);
+    if (un_obs) par_memcpy(obs_out, e->h_obs, ob);
     if (un_rew) par_memcpy(rew_out, e->h_rew, rb);
     return MBT_OK;
 }

@@ -27,7 +27,7 @@ def run(name, make_action, **kw):
         ts.append(time.perf_counter() - t0)
         if d[0]:
             f.reset()
-    print(f"{name:58s} {1e3 * np.median(ts):.3f} ms per step (median of 40)")
+    print(f"{name:58s} {1e3 * np.median(ts):.3f} ms per step (median of 40)", flush=True)
     f.close()
 
 
