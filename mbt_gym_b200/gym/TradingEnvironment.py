@@ -64,6 +64,7 @@ class TradingEnvironment(_track.Tracked, _EnvBase):
         self._episode_open = False  # between reset() and the step that returned done
         self._seen_version = -1     # _track.version the device handle was last validated against
         self._pool = None
+        self._act_scratch = None  # page-locked (N, A) buffer for actions that need a dtype / layout conversion
         self._infos = None
         self.precision = {"float64": _abi.MBT_F64, "f64": _abi.MBT_F64, "float32": _abi.MBT_F32, "f32": _abi.MBT_F32}[str(precision)]
         self.dtype = np.dtype(np.float64 if self.precision == _abi.MBT_F64 else np.float32)
@@ -211,8 +212,20 @@ class TradingEnvironment(_track.Tracked, _EnvBase):
             native = self._ensure_native()
         if hasattr(action, "is_cuda") and action.is_cuda:
             return self._step_device(native, action)
-        a = action if (type(action) is np.ndarray and action.dtype == self.io_dtype and action.flags.c_contiguous) \
-            else np.ascontiguousarray(action, dtype=self.io_dtype)
+        if type(action) is np.ndarray and action.dtype == self.io_dtype and action.flags.c_contiguous:
+            a = action
+        else:
+            a = np.asarray(action)
+            if a.shape == (self.num_trajectories, native.A) and a.dtype.kind in "fiu":
+                # a conversion is needed anyway (e.g. SB3's float32 actions into a float64 environment): convert straight
+                # into page-locked memory, so the upload is a direct DMA instead of a second staging copy
+                scratch = self._act_scratch
+                if scratch is None or scratch.shape != a.shape or scratch.dtype != self.io_dtype:
+                    scratch = self._act_scratch = _lib.PinnedArray(a.shape, self.io_dtype, self.device).array
+                np.copyto(scratch, a, casting="unsafe")
+                a = scratch
+            else:
+                a = np.ascontiguousarray(action, dtype=self.io_dtype)
         if a.shape != (self.num_trajectories, native.A):
             if a.size == self.num_trajectories * native.A and self.num_trajectories == 1:
                 a = a.reshape(1, native.A)
