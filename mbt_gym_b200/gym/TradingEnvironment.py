@@ -560,7 +560,8 @@ class TradingEnvironment(_track.Tracked, _EnvBase):
         return obs, rew
 
     def _dones(self, done):
-        return np.full((self.num_trajectories,), bool(done))  # a fresh array every step, like the reference's (:218-220)
+        # a fresh array every step, like the reference's (:218-220)
+        return np.ones((self.num_trajectories,), bool) if done else np.zeros((self.num_trajectories,), bool)
 
     def _calculate_infos(self):
         if self.info_calculator is not None:
