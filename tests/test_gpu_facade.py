@@ -32,7 +32,7 @@ def test_env_step_reproduces_reference_fixture(name, copy_outputs):
     env.close()
 
 
-def test_ring_outputs_survive_the_next_steps_and_copy_mode_returns_fresh_arrays():
+def test_returned_arrays_survive_the_next_steps_and_copy_mode_returns_ordinary_arrays():
     g = Golden("as_pnl")
     env = build_facade_env(SPECS["as_pnl"])
     env.reset()
