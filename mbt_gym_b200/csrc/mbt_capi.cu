@@ -21,6 +21,11 @@
 #include <thread>
 #include <vector>
 
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h> /* header-only; ranges cost nothing unless a tool (ncu --nvtx, nsys) is attached */
+#define MBT_HAVE_NVTX 1
+#endif
+
 #include "mbt_b200.h"
 #include "mbt_host_params.h"
 #include "mbt_variants.h"
@@ -44,6 +49,16 @@ static int fail(int code, const std::string &msg) {
             return fail(MBT_E_CUDA, _b);                                                              \
         }                                                                                             \
     } while (0)
+
+/* NVTX range around an ABI call: `ncu --nvtx --nvtx-include "mbt_step/"` or an nsys timeline attribute the launches to it */
+struct NvtxRange {
+#ifdef MBT_HAVE_NVTX
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+#else
+    explicit NvtxRange(const char *) {}
+#endif
+};
 
 /* ------------------------------------------------------------------ handle */
 constexpr int MBT_TIMING_RING = 8192;
@@ -1148,6 +1163,7 @@ static int d2h(mbt_env *e, void *host_dst, const void *dev_src, void *pinned_sta
 }
 
 int mbt_reset(mbt_env *e, const mbt_reset_args *args, void *obs_out, int mem) {
+    NvtxRange nvtx("mbt_reset");
     if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
     if (mem != MBT_MEM_HOST && mem != MBT_MEM_DEVICE) return fail(MBT_E_INVALID_ARG, "mem must be MBT_MEM_HOST or MBT_MEM_DEVICE");
     CU(cudaSetDevice(e->device));
@@ -1171,6 +1187,7 @@ int mbt_reset(mbt_env *e, const mbt_reset_args *args, void *obs_out, int mem) {
 }
 
 int mbt_step(mbt_env *e, const void *actions, void *obs_out, void *rew_out, uint8_t *done_out, int mem) {
+    NvtxRange nvtx("mbt_step");
     if (!e) return fail(MBT_E_INVALID_ARG, "env is NULL");
     if (!actions) return fail(MBT_E_INVALID_ARG, "actions is NULL");
     if (mem != MBT_MEM_HOST && mem != MBT_MEM_DEVICE) return fail(MBT_E_INVALID_ARG, "mem must be MBT_MEM_HOST or MBT_MEM_DEVICE");
@@ -1576,6 +1593,7 @@ static int do_rollout(mbt_env *e, const mbt_policy *pol, mbt_summary *summary, v
 extern "C" {
 
 int mbt_rollout(mbt_env *e, const mbt_policy *policy, mbt_summary *summary_out, void *returns_out, void *terminal_q_out, int mem) {
+    NvtxRange nvtx("mbt_rollout");
     if (!e || !policy) return fail(MBT_E_INVALID_ARG, "NULL argument");
     if (!e->started) return fail(MBT_E_STATE, "mbt_rollout called before mbt_reset");
     if (e->t >= e->cfg.terminal_time - e->cfg.step_size / 2) return fail(MBT_E_STATE, "episode already finished; call mbt_reset");
@@ -1600,6 +1618,7 @@ int mbt_rollout(mbt_env *e, const mbt_policy *policy, mbt_summary *summary_out, 
 }
 
 int mbt_rollout_record(mbt_env *e, const mbt_policy *policy, mbt_summary *summary_out, const mbt_record *record, int mem) {
+    NvtxRange nvtx("mbt_rollout_record");
     if (!e || !policy || !record) return fail(MBT_E_INVALID_ARG, "NULL argument");
     if (!e->started) return fail(MBT_E_STATE, "mbt_rollout_record called before mbt_reset");
     if (e->t >= e->cfg.terminal_time - e->cfg.step_size / 2) return fail(MBT_E_STATE, "episode already finished; call mbt_reset");
@@ -1849,6 +1868,7 @@ static int group_allreduce_summary(mbt_env *e) {
 }
 
 int mbt_group_rollout(mbt_env *e, const mbt_policy *policy, mbt_summary *summary_out, void *returns_local, void *returns_all) {
+    NvtxRange nvtx("mbt_group_rollout");
     if (!e || !policy) return fail(MBT_E_INVALID_ARG, "NULL argument");
     if (!e->comm) return fail(MBT_E_STATE, "the handle belongs to no group (mbt_group_create)");
     if (!e->started) return fail(MBT_E_STATE, "mbt_group_rollout called before mbt_reset");
