@@ -28,7 +28,7 @@ from mbt_gym_b200.stochastic_processes.price_impact_models import TemporaryAndPe
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=8 * (1 << 20), help="trajectories over ALL GPUs")
+    ap.add_argument("--trajectories", dest="n", type=int, default=8 * (1 << 20), help="trajectories over ALL GPUs")
     ap.add_argument("--episodes", type=int, default=3)
     args = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
