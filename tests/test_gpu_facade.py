@@ -418,3 +418,52 @@ def test_cuda_graph_replay_of_captured_episodes_equals_eager_episodes():
         got = eager_episode(env)
     assert_same(got[1], want[4][1], what="next episode after checkpoint restore")
     env.close()
+
+
+def test_vecenv_adapter_survives_the_access_patterns_of_sb3_collect_rollouts_and_vecmonitor():
+    """stable-baselines3 is not installed here, so its two consumers of `infos` / `dones` are restated from its source
+    (common/on_policy_algorithm.py collect_rollouts + base_class._update_info_buffer, common/vec_env/vec_monitor.py
+    step_wait) and run against the adapter for two whole episodes: indexing, slicing, copying, item assignment and
+    iteration must all work on ordinary steps (the env's list of empty dicts) and on episode ends (_TerminalInfos)."""
+    from mbt_gym_b200.gym.StableBaselinesTradingEnvironment import StableBaselinesTradingEnvironment
+
+    spec = dict(SPECS["as_pnl"], N=257, n_steps=12)
+    venv = StableBaselinesTradingEnvironment(build_facade_env(spec))
+    n = venv.num_envs
+    obs = venv.reset()
+    ep_returns, ep_lengths = np.zeros(n), np.zeros(n, dtype=int)   # VecMonitor state
+    ep_info_buffer, terminal_seen = [], 0
+    rng = np.random.default_rng(0)
+    for t in range(24):
+        actions = rng.uniform(0.1, 1.2, size=(n, 2)).astype(np.float32)   # SB3 policies emit float32
+        venv.step_async(actions)
+        new_obs, rewards, dones, infos = venv.step_wait()
+        # --- VecMonitor.step_wait
+        ep_returns += rewards
+        ep_lengths += 1
+        new_infos = list(infos[:])
+        for i in range(len(dones)):
+            if dones[i]:
+                info = infos[i].copy()
+                info["episode"] = {"r": ep_returns[i], "l": ep_lengths[i], "t": 0.0}
+                ep_returns[i] = 0
+                ep_lengths[i] = 0
+                new_infos[i] = info
+        infos = new_infos
+        # --- BaseAlgorithm._update_info_buffer
+        for idx, info in enumerate(infos):
+            maybe_ep_info = info.get("episode")
+            if maybe_ep_info is not None:
+                ep_info_buffer.extend([maybe_ep_info])
+        # --- OnPolicyAlgorithm.collect_rollouts: bootstrap with the terminal observation on time-limit truncation
+        for idx, done in enumerate(dones):
+            if done and infos[idx].get("terminal_observation") is not None:
+                terminal_seen += 1
+                assert infos[idx]["terminal_observation"].shape == obs.shape[1:]
+                assert not infos[idx].get("TimeLimit.truncated", False)
+        assert new_obs.shape == obs.shape and rewards.shape == (n,) and dones.shape == (n,) and dones.dtype == bool
+        obs = new_obs
+    assert terminal_seen == 2 * n and len(ep_info_buffer) == 2 * n
+    assert all(e["l"] == 12 for e in ep_info_buffer)
+    assert venv.env_is_wrapped(object) == [False] * n
+    venv.close()
